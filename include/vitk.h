@@ -1,0 +1,225 @@
+/*
+ * vitk.h -- C-ABI of libvitk.so: hand-written sm_100a CUDA kernels for the ViT-B/16 PAD hot path.
+ *
+ * The reference (ArchitRastogi20/vit-spoof-detection-pda) has no FFI layer: its hot path is a
+ * torch.nn.Module that bottoms out in timm -> torch -> cuDNN/cuBLAS/SDPA/ATen library kernels.
+ * Every entry point below replaces one of those library-call sites (K1..K12 in SURVEY.md 2.1);
+ * the reference interface each one stands in for is cited as /root/reference file:line.
+ *
+ * Conventions
+ *   - extern "C", POD arguments only: device pointers, integer sizes, float scalars, the CUDA
+ *     stream as void* (cudaStream_t).  No torch types.  The library allocates nothing persistent:
+ *     the caller owns every buffer (parameters, gradients, activations, workspace).
+ *   - every entry returns int: 0 = ok, non-zero = cudaError_t or VITK_ERR_*;
+ *     vitk_last_error_string() describes the last failure on the calling thread.
+ *   - all work is enqueued on the caller's stream; no hidden synchronisation.
+ *   - "rows" M = batch * 197 tokens; DIM 768, 12 heads x 64, MLP 3072 are compile-time constants
+ *     of the kernels (the reference fixes model_name = vit_base_patch16_224, train_advanced.py:33).
+ *   - dtype arguments: VITK_F32 / VITK_BF16 describe the storage type of activation buffers.
+ *     precision VITK_PREC_FP32_VALIDATE = fp32 storage + fp32 FFMA arithmetic everywhere (the 1e-4
+ *     parity mode); VITK_PREC_BF16 = bf16 GEMM/attention operands on tcgen05 / mma tensor cores,
+ *     fp32 accumulation, fp32 residual stream, LayerNorm/softmax/loss/Adam in fp32
+ *     (mirrors the reference's autocast placement).
+ */
+#ifndef VITK_H_
+#define VITK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITK_VERSION 100
+
+/* model constants (timm vit_base_patch16_224, train_advanced.py:33,190) */
+#define VITK_IMG 224
+#define VITK_PATCH 16
+#define VITK_NPATCH 196
+#define VITK_NTOK 197
+#define VITK_DIM 768
+#define VITK_HEADS 12
+#define VITK_HEAD_DIM 64
+#define VITK_MLP 3072
+#define VITK_HEAD_HIDDEN 512
+
+enum { VITK_OK = 0, VITK_ERR_ARG = 10001, VITK_ERR_UNSUPPORTED = 10002, VITK_ERR_DRIVER = 10003 };
+enum { VITK_F32 = 0, VITK_BF16 = 1 };
+enum { VITK_PREC_FP32_VALIDATE = 0, VITK_PREC_BF16 = 1 };
+
+/* epilogues of the Linear forward (replaces cuBLASLt + ATen add/gelu call sites K4,K6,K7,K8) */
+enum {
+  VITK_EPI_BIAS = 0,          /* y = x W^T + b                                 (out: act dtype)          */
+  VITK_EPI_BIAS_GELU = 1,     /* u = x W^T + b ; g = gelu_erf(u)               (out: u and g, act dtype) */
+  VITK_EPI_BIAS_RESIDUAL = 2, /* y = res + x W^T + b                           (res, out: fp32)          */
+  VITK_EPI_QKV_SCATTER = 3    /* y = x W^T + b written head-major [36][M][64]  (out: act dtype)          */
+};
+/* matrix storage of an activation operand */
+enum {
+  VITK_LAYOUT_ROWMAJOR = 0,   /* [M][C] */
+  VITK_LAYOUT_HEADMAJOR = 1   /* [C/64][M][64]  (q,k,v and their gradients) */
+};
+/* GEMM engine: the tcgen05/TMEM kernel, or the SIMT FFMA kernel (always used by FP32_VALIDATE) */
+enum { VITK_ENGINE_AUTO = 0, VITK_ENGINE_SIMT = 1, VITK_ENGINE_TCGEN05 = 2 };
+
+int vitk_version(void);
+const char* vitk_last_error_string(void);
+/* number of SMs / compute capability of the current device (host query; 0 on failure) */
+int vitk_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* process-wide default GEMM engine for VITK_PREC_BF16 (tests sweep both); returns previous value */
+int vitk_set_gemm_engine(int engine);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (768).  Replaces ATen native_layer_norm reached from timm
+ * Block.norm1/.norm2, vit.norm (eps 1e-6) and classifier[0] (eps 1e-5, train_advanced.py:194).
+ *   x: fp32 [rows] with row stride x_stride (elements); y: y_dtype, dense [rows][768];
+ *   mean/rstd: fp32 [rows] saved for backward (may be NULL in eval).
+ * bwd: dx = (dres ? dres : 0) + LN'(dy) ; also written as bf16 to dx16 when non-NULL;
+ *   dgamma/dbeta are ACCUMULATED (+=) into fp32 [768]; partial is caller scratch of
+ *   vitk_layernorm_bwd_scratch_floats() floats.
+ * ------------------------------------------------------------------------------------------- */
+int vitk_layernorm_fwd(const float* x, int64_t x_stride, const float* gamma, const float* beta,
+                       void* y, int y_dtype, float* mean, float* rstd, int rows, float eps, void* stream);
+int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, int64_t x_stride,
+                       const float* gamma, const float* mean, const float* rstd, const float* dres,
+                       float* dx, void* dx16, float* dgamma, float* dbeta, float* partial,
+                       int rows, void* stream);
+size_t vitk_layernorm_bwd_scratch_floats(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * nn.Linear forward / backward (timm Attention.qkv, Attention.proj, Mlp.fc1, Mlp.fc2).
+ *   fwd   : Y[M,N]  = X[M,K] W[N,K]^T + b, epilogue as above.   `aux` = u (pre-GELU) for BIAS_GELU,
+ *           residual (fp32) for BIAS_RESIDUAL.
+ *   dgrad : dX[M,K] = dY[M,N] W[N,K]   ; if gelu_u != NULL: dX *= gelu'(gelu_u)  (dX, gelu_u: [M,K])
+ *   wgrad : dW[N,K] += dY[M,N]^T X[M,K]; db[N] += colsum(dY)   (dW, db fp32; += so autograd-style
+ *           accumulation and split-K share one code path; caller zeroes the gradient buffer)
+ * X/dY/W are `dtype` (VITK_F32 for FP32_VALIDATE, VITK_BF16 otherwise; W then is the bf16 shadow).
+ * ------------------------------------------------------------------------------------------- */
+int vitk_linear_fwd(const void* x, int x_layout, const void* w, const float* bias, void* y, void* aux,
+                    int M, int N, int K, int epilogue, int dtype, int engine, void* stream);
+int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, const void* gelu_u,
+                      int M, int N, int K, int dtype, int engine, void* stream);
+int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, float* dw, float* db,
+                      int M, int N, int K, int dtype, int engine, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Patch embedding (timm PatchEmbed.proj = Conv2d(3,768,k16,s16) + _pos_embed; K1,K2).
+ *   fwd  : x0[b,1+p,:] = patch(b,p) . Wpe^T + bpe + pos[1+p] ; x0[b,0,:] = cls + pos[0]   (fp32 out)
+ *          `patches` is caller scratch [B*197][768] of `dtype`: the cast image regrouped per token
+ *          (row b*197+t, k = c*256+i*16+j), CLS rows (t = 0) zero, so fwd and wgrad are plain
+ *          token-row GEMMs and the CLS/pos handling lives in the GEMM epilogue.
+ *   wgrad: dWpe += dx0^T patches ; dbpe += colsum(dx0[:,1:]) ; dpos += sum_b dx0 ; dcls += sum_b dx0[b,0]
+ *          `dx0_act` = dx0 in `dtype` (row-major [B*197][768]); images need no gradient.
+ * ------------------------------------------------------------------------------------------- */
+int vitk_patch_embed_fwd(const float* images, const void* wpe, const float* bpe, const float* cls,
+                         const float* pos, void* patches, float* x0, int batch, int dtype, int engine,
+                         void* stream);
+int vitk_patch_embed_wgrad(const float* dx0, const void* dx0_act, const void* patches, float* dwpe,
+                           float* dbpe, float* dcls, float* dpos, int batch, int dtype, int engine,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head self-attention core, N=197, d=64, 12 heads, scale 1/8, no mask, no dropout
+ * (timm Attention -> F.scaled_dot_product_attention; K5).
+ *   qkv : head-major [36][M][64]  (q heads 0..11, k heads 12..23, v heads 24..35)
+ *   out : row-major [M][768] (heads concatenated), lse: fp32 [12][M] (log-sum-exp of scaled scores)
+ *   bwd : dqkv head-major [36][M][64] from dout [M][768]
+ * ------------------------------------------------------------------------------------------- */
+int vitk_attn_fwd(const void* qkv, void* out, float* lse, int batch, int dtype, void* stream);
+int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                  int batch, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Classifier head on the CLS feature (train_advanced.py:193-200, 204) -- fp32 always.
+ *   feat [B][768] (CLS rows of vit.norm output, dense) -> logits [B][C]
+ *   LN(1e-5) -> *mask1 -> Linear(768,512) -> GELU -> *mask2 -> Linear(512,C)
+ *   mask1 [B][768] / mask2 [B][512] are pre-scaled dropout masks (0 or 1/(1-p)); NULL = no dropout.
+ *   save: caller buffer of vitk_head_save_floats(B) floats (activations for backward).
+ *   bwd: dfeat [B][768]; parameter grads ACCUMULATED (+=).
+ * ------------------------------------------------------------------------------------------- */
+size_t vitk_head_save_floats(int batch);
+int vitk_head_fwd(const float* feat, const float* ln_w, const float* ln_b, const float* w1,
+                  const float* b1, const float* w2, const float* b2, const float* mask1,
+                  const float* mask2, float* logits, float* save, int batch, int num_classes, void* stream);
+int vitk_head_bwd(const float* dlogits, float* save, const float* ln_w, const float* w1,
+                  const float* w2, const float* mask1, const float* mask2, float* dfeat, float* dln_w,
+                  float* dln_b, float* dw1, float* db1, float* dw2, float* db2, int batch,
+                  int num_classes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Focal loss + gradient (FocalLoss.forward, train_advanced.py:98-107) fused with the eval
+ * post-processing (softmax P(live)=probs[:,1], argmax: train_advanced.py:342,387-394; test.py:212-217).
+ *   alpha: fp32 [C] per-class weights (scalar alpha = all entries equal; class weights:
+ *   train_advanced.py:521-529).  reduction: 0 = mean, 1 = sum, 2 = none.
+ *   loss_per_sample [B] (always written); loss_out [1] (mean or sum); dlogits [B][C] = d loss / d logits
+ *   scaled by grad_scale (use 1/world for data parallel); probs1 [B] / preds int64 [B] / ncorrect int32[1]
+ *   optional (NULL to skip).  C <= 8.
+ * ------------------------------------------------------------------------------------------- */
+int vitk_focal_fwd_bwd(const float* logits, const int64_t* targets, const float* alpha, float gamma,
+                       int reduction, float grad_scale, float* loss_per_sample, float* loss_out,
+                       float* dlogits, float* probs1, int64_t* preds, int* ncorrect, int batch,
+                       int num_classes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam / AdamW over one flat fp32 parameter buffer
+ * (torch.optim.AdamW at train_advanced.py:592-597, Adam-L2 per README.md:140-147,
+ *  clip_grad_norm_ at :334, GradScaler.unscale_ at :333).
+ *   pass 1: vitk_grad_sumsq  -> sumsq[0] = sum(g^2) over the flat grads (deterministic 2-stage)
+ *           (`partial` = caller scratch of vitk_grad_sumsq_scratch_floats() floats)
+ *   pass 2: vitk_adam_step   -> g' = g * grad_mult * clipcoef, clipcoef = min(1, max_norm /
+ *           (sqrt(sumsq)*grad_mult + 1e-6)) when sumsq != NULL and max_norm > 0 (torch semantics);
+ *           mode 0 (Adam-L2): g' += wd*p before the moments; mode 1 (AdamW): p *= 1 - lr*wd first.
+ *           Writes p, m, v and (when p16 != NULL) the bf16 shadow of p in the same pass.
+ *           step is the 1-based step count (bias corrections 1-beta^step).
+ * ------------------------------------------------------------------------------------------- */
+size_t vitk_grad_sumsq_scratch_floats(void);
+int vitk_grad_sumsq(const float* g, size_t n, float* partial, float* sumsq, void* stream);
+int vitk_adam_step(float* p, const float* g, float* m, float* v, void* p16, size_t n, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int mode, int step,
+                   float grad_mult, const float* sumsq, float max_norm, void* stream);
+/* p16 = bf16(p) over a flat buffer (after load_state_dict / external optimizers) */
+int vitk_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-model drivers: one call enqueues the full encoder+head forward (a1,a2,a3 of SURVEY.md 8a)
+ * or one backward stage, so Python makes O(depth) ctypes calls and the sequence is CUDA-graph
+ * capturable.  Flat parameter layout = state_dict order, each tensor padded to a
+ * multiple of 64 elements: query it with vitk_param_layout().
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vitk_model {
+  int32_t batch, depth, num_classes, precision; /* VITK_PREC_*                                        */
+  int32_t training;                             /* 1: save activations for backward                   */
+  int32_t engine;                               /* VITK_ENGINE_*                                      */
+  const float* params;                          /* flat fp32 master parameters                        */
+  const void* params16;                         /* flat bf16 shadow (same offsets); NULL in FP32 mode */
+  float* grads;                                 /* flat fp32 gradients (same offsets), accumulated    */
+  void* workspace;                              /* vitk_workspace_bytes() bytes, 256-B aligned        */
+  const float* images;                          /* [B][3][224][224] fp32 NCHW                         */
+  float* logits;                                /* [B][C] fp32                                        */
+  const float* mask1;                           /* optional dropout masks of the head (see head_fwd)  */
+  const float* mask2;
+  const float* dlogits;                         /* [B][C] fp32, input of backward                     */
+  int32_t frozen_backbone;                      /* 1: backward stops after the head (config 4)        */
+  int32_t reserved;
+} vitk_model;
+
+/* n_tensors = 4 + 12*depth + 8; offsets/sizes in elements, state_dict order. returns total elements */
+int64_t vitk_param_layout(int depth, int num_classes, int64_t* offsets, int64_t* sizes, int max_tensors);
+size_t vitk_workspace_bytes(int batch, int depth, int precision, int training);
+int vitk_model_fwd(const vitk_model* m, void* stream);
+/* backward stages in the order gradients become final (DP buckets are all-reduced in between):
+ *   stage 0            : head + final norm              -> grads of classifier.*, vit.norm.*
+ *   stage 1 + (depth-1-i): block i (i = depth-1 .. 0)   -> grads of vit.blocks.i.*
+ *   stage depth+1      : patch embedding, cls, pos      -> grads of vit.patch_embed.*, cls, pos    */
+int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream);
+int vitk_model_num_bwd_stages(int depth);
+
+/* debug knobs of the tcgen05 engine (tests only): key 0 = swap LBO/SBO of MN-major operands,
+ * key 1 = force split-K count, key 2 = force BLOCK_N (128) */
+int vitk_debug_set(int key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITK_H_ */

@@ -1,0 +1,252 @@
+"""End-to-end parity of the drop-in module / loss / optimizer against the oracle on identical
+random-init weights and synthetic images (north_star: logits and gradients within 1e-4 relative in the
+fp32 validation mode, within 2e-2 max-abs in bf16, argmax equal, loss curves matching over 200 steps)."""
+import copy
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vit_oracle as vo  # checker only
+
+if torch.cuda.is_available():
+    import vit_spoof_detection_pda_b200 as pkg
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    DEV = torch.device("cuda:0")
+else:
+    pkg = DEV = None
+
+FP32_TOL = 1e-4
+BF16_ABS = 2e-2
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def make_pair(depth, precision, dropout=0.0, seed=42):
+    ref = vo.OracleViTFaceAntiSpoofing(dropout=dropout, depth=depth)
+    vo.seeded_init_(ref, seed=seed)
+    m = pkg.ViTFaceAntiSpoofing(dropout=dropout, depth=depth, precision=precision)
+    missing = m.load_state_dict(ref.state_dict(), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return ref, m.to(DEV)
+
+
+def test_state_dict_contract_and_roundtrip(tmp_path):
+    ref, m = make_pair(12, "fp32")
+    sd = m.state_dict()
+    spec = vo.expected_state_dict_spec(12)
+    assert list(sd.keys()) == [n for n, _ in spec] and len(sd) == 156
+    for n, shape in spec:
+        assert tuple(sd[n].shape) == shape and sd[n].dtype == torch.float32
+    assert m.vit.num_features == 768
+    assert [i for i, mod in enumerate(m.classifier) if list(mod.parameters())] == [0, 2, 5]
+    # checkpoint container of train_advanced.py:476-484 / test.py:174-177
+    path = tmp_path / "ckpt.pth"
+    torch.save({"epoch": 3, "model_state_dict": sd, "metrics": {}, "config": {}}, path)
+    ck = torch.load(path, weights_only=False, map_location="cpu")
+    ref2 = vo.OracleViTFaceAntiSpoofing(depth=12)
+    ref2.load_state_dict(ck["model_state_dict"], strict=True)
+    for (n, a), (_, b) in zip(ref.state_dict().items(), ref2.state_dict().items()):
+        assert torch.equal(a, b), n
+
+
+@pytest.mark.parametrize("depth", [2, 12])
+def test_fp32_forward_matches_reference_golden(golden_dir, depth):
+    g = torch.load(os.path.join(golden_dir, "model_golden.pt"), weights_only=False)[f"depth{depth}"]
+    _, m = make_pair(depth, "fp32")
+    images, labels = vo.synthetic_batch(g["batch"], seed=g["seed"])
+    m.train()
+    out = m(images.to(DEV))
+    loss = pkg.FocalLoss(0.25, 2.0)(out, labels.to(DEV))
+    loss.backward()
+    assert rel(out, g["logits"]) < FP32_TOL
+    assert abs(loss.item() - g["loss"].item()) < FP32_TOL * max(1.0, abs(g["loss"].item()))
+    for n, p in m.named_parameters():
+        r = g["grads"][n]
+        assert abs(float(p.grad.double().norm()) - r["norm"]) <= 2e-4 * max(r["norm"], 1e-12), n
+        assert float((p.grad.flatten()[:4].cpu() - r["head"]).abs().max()) <= 2e-4 * r["absmax"] + 1e-12, n
+
+
+@pytest.mark.parametrize("depth,batch", [(2, 3), (12, 2), (12, 8)])
+def test_fp32_all_gradients_vs_oracle(depth, batch):
+    ref, m = make_pair(depth, "fp32")
+    images, labels = vo.synthetic_batch(batch, seed=7)
+    ref.train()
+    out_r = ref(images)
+    vo.OracleFocalLoss(0.25, 2.0)(out_r, labels).backward()
+    m.train()
+    out = m(images.to(DEV))
+    pkg.FocalLoss(0.25, 2.0)(out, labels.to(DEV)).backward()
+    assert rel(out, out_r) < FP32_TOL
+    worst = ("", 0.0)
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        e = rel(p.grad, q.grad)
+        if e > worst[1]:
+            worst = (n, e)
+    assert worst[1] < FP32_TOL, worst
+
+
+@pytest.mark.parametrize("engine", ["tcgen05", "simt"])
+def test_bf16_logits_grads_argmax(engine):
+    from vit_spoof_detection_pda_b200 import _lib as L
+    ref, m = make_pair(12, "bf16")
+    m.engine = L.ENGINE_TCGEN05 if engine == "tcgen05" else L.ENGINE_SIMT
+    batch = 8
+    images, labels = vo.synthetic_batch(batch, seed=11)
+    ref.train()
+    out_r = ref(images)
+    vo.OracleFocalLoss(0.25, 2.0)(out_r, labels).backward()
+    m.train()
+    out = m(images.to(DEV))
+    pkg.FocalLoss(0.25, 2.0)(out, labels.to(DEV)).backward()
+    err = float((out.cpu() - out_r).abs().max())
+    assert err < BF16_ABS, err
+    margin = (out_r[:, 1] - out_r[:, 0]).abs()
+    decided = margin > 2 * err            # argmax is only meaningful where the margin exceeds the error
+    assert torch.equal(out.argmax(1).cpu()[decided], out_r.argmax(1)[decided])
+    print(f"bf16[{engine}] logits max-abs err {err:.3e}; margins min {margin.min():.3e} median {margin.median():.3e}; "
+          f"argmax compared on {int(decided.sum())}/{batch}")
+    worst_abs, worst_rel = 0.0, ("", 0.0)
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        worst_abs = max(worst_abs, float((p.grad.cpu() - q.grad).abs().max()))
+        e = rel(p.grad, q.grad)
+        if e > worst_rel[1]:
+            worst_rel = (n, e)
+    print(f"bf16[{engine}] grads worst max-abs {worst_abs:.3e}, worst rel-to-scale {worst_rel}")
+    assert worst_abs < BF16_ABS
+    assert worst_rel[1] < 0.1, worst_rel
+
+
+def test_eval_batch_invariance_and_postprocess():
+    ref, m = make_pair(12, "bf16")
+    m.eval()
+    images, _ = vo.synthetic_batch(8, seed=5)
+    x = images.to(DEV)
+    with torch.no_grad():
+        full = m(x)
+        singles = torch.cat([m(x[i:i + 1]) for i in range(8)])
+    assert float((full - singles).abs().max()) < 1e-2
+    probs, preds = pkg.eval_postprocess(full)
+    assert torch.allclose(probs, F.softmax(full, 1)[:, 1], atol=1e-6)
+    assert torch.equal(preds, full.argmax(1))
+    logits_r, p_live, preds_r = vo.oracle_eval_step(ref, images)
+    assert float((full.cpu() - logits_r).abs().max()) < BF16_ABS
+
+
+def test_frozen_backbone_head_only_grads():
+    ref, m = make_pair(2, "fp32")
+    for p in m.vit.parameters():
+        p.requires_grad_(False)
+    for p in ref.vit.parameters():
+        p.requires_grad_(False)
+    images, labels = vo.synthetic_batch(4, seed=3)
+    vo.OracleFocalLoss(0.25, 2.0)(ref(images), labels).backward()
+    m.train()
+    pkg.FocalLoss(0.25, 2.0)(m(images.to(DEV)), labels.to(DEV)).backward()
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        if n.startswith("vit."):
+            assert p.grad is None, n
+        else:
+            assert rel(p.grad, q.grad) < FP32_TOL, n
+
+
+def test_head_dropout_with_injected_masks():
+    ref, m = make_pair(2, "fp32", dropout=0.1)
+    images, labels = vo.synthetic_batch(4, seed=9)
+    m.train()
+    out = m(images.to(DEV))
+    m1, m2 = [t.cpu() for t in m.last_masks]
+    assert 0.8 < float((m1 > 0).float().mean()) < 0.98
+    feat = ref.vit(images)
+    c = ref.classifier
+    h = c[0](feat) * m1
+    h = c[3](c[2](h)) * m2
+    out_r = c[5](h)
+    assert rel(out, out_r) < FP32_TOL
+
+
+def test_gradient_accumulation_and_stock_optimizer():
+    ref, m = make_pair(2, "fp32")
+    crit_r, crit = vo.OracleFocalLoss(0.25, 2.0), pkg.FocalLoss(0.25, 2.0)
+    opt_r = torch.optim.AdamW(ref.parameters(), lr=3e-4, weight_decay=0.05)
+    opt = torch.optim.AdamW(m.parameters(), lr=3e-4, weight_decay=0.05)   # stock optimizer on the drop-in module
+    m.train(); ref.train()
+    for step in range(2):
+        for micro in range(2):                                            # two backward passes, no zero_grad between
+            images, labels = vo.synthetic_batch(2, seed=20 + 2 * step + micro)
+            crit_r(ref(images), labels).backward()
+            crit(m(images.to(DEV)), labels.to(DEV)).backward()
+        for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+            assert rel(p.grad, q.grad) < 2 * FP32_TOL, (step, n)
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt_r.step(); opt.step()
+        opt_r.zero_grad(set_to_none=True); opt.zero_grad(set_to_none=True)
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        assert rel(p, q) < 1e-5, n
+
+
+@pytest.mark.parametrize("precision,kind,tol", [("fp32", "adam", 2e-3), ("fp32", "adamw", 2e-3), ("bf16", "adam", 5e-2)])
+def test_loss_curve_200_steps(precision, kind, tol):
+    """Reference step order (train_advanced.py:322-346) for 200 steps; the checker runs the oracle on the GPU
+    in fp32 with TF32 disabled (same arithmetic as its CPU form, just faster)."""
+    depth, batch, steps = 12, 8, 200
+    lr, wd = (1e-5, 1e-4) if kind == "adam" else (3e-4, 0.05)
+    ref, m = make_pair(depth, precision)
+    ref = ref.to(DEV)
+    opt_r = vo.make_optimizer(ref.parameters(), kind, lr=lr, weight_decay=wd)
+    opt = pkg.FusedAdam(m.parameters(), lr=lr, weight_decay=wd, adamw=(kind == "adamw"))
+    sched_r = torch.optim.lr_scheduler.CosineAnnealingLR(opt_r, T_max=steps, eta_min=1e-6)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=steps, eta_min=1e-6)
+    crit_r, crit = vo.OracleFocalLoss(0.25, 2.0), pkg.FocalLoss(0.25, 2.0)
+    m.train()
+    lr_hist, l_hist, acc_equal = [], [], 0
+    for s in range(steps):
+        images, labels = vo.synthetic_batch(batch, seed=1000 + s)
+        images, labels = images.to(DEV), labels.to(DEV)
+        loss_r, acc_r, _ = vo.oracle_train_step(ref, crit_r, opt_r, images, labels, 1.0, sched_r)
+        out = m(images)
+        loss, met = crit(out, labels, with_metrics=True)
+        loss.backward()
+        pkg.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        sched.step()
+        lr_hist.append(loss_r)
+        l_hist.append(loss.item())
+        acc_equal += int(abs(met["ncorrect"].item() / batch - acc_r) < 1e-6)
+    dev = max(abs(a - b) for a, b in zip(l_hist, lr_hist))
+    print(f"loss curve [{precision},{kind}]: max |dloss| over {steps} steps = {dev:.3e}; first {l_hist[0]:.5f}/{lr_hist[0]:.5f} "
+          f"last {l_hist[-1]:.5f}/{lr_hist[-1]:.5f}; accuracy equal on {acc_equal}/{steps} steps")
+    assert dev < tol
+    if precision == "fp32":
+        assert acc_equal >= steps - 2
+
+
+def test_fused_adam_state_dict_layout():
+    _, m = make_pair(2, "fp32")
+    opt = pkg.FusedAdam(m.parameters(), lr=1e-3, weight_decay=0.01)
+    images, labels = vo.synthetic_batch(2, seed=1)
+    m.train()
+    pkg.FocalLoss()(m(images.to(DEV)), labels.to(DEV)).backward()
+    opt.step()
+    sd = opt.state_dict()
+    stock = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0.01)
+    stock.load_state_dict(copy.deepcopy(sd))        # torch accepts the layout -> checkpoints interchange
+    assert len(sd["state"]) == len(list(m.parameters()))
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_cpu_tensors_fail_loudly():
+    m = pkg.ViTFaceAntiSpoofing(dropout=0.0, depth=1, precision="fp32")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 224, 224))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.FocalLoss()(torch.zeros(2, 2), torch.zeros(2, dtype=torch.long))

@@ -1,0 +1,13 @@
+"""vit_spoof_detection_pda_b200 -- B200-native ViT-B/16 PAD hot path (libvitk: hand-written sm_100a CUDA).
+
+Public API mirrors the reference's own objects for this path (/root/reference/train_advanced.py):
+``ViTFaceAntiSpoofing`` (:187-204), ``FocalLoss`` (:90-107), and fused stand-ins for
+``torch.optim.AdamW`` (:592-597) and ``torch.nn.utils.clip_grad_norm_`` (:334).
+"""
+from . import _lib
+from .dp import DataParallel
+from .loss import FocalLoss, eval_postprocess
+from .module import ViTFaceAntiSpoofing
+from .optim import FusedAdam, clip_grad_norm_
+
+__all__ = ["ViTFaceAntiSpoofing", "FocalLoss", "FusedAdam", "clip_grad_norm_", "DataParallel", "eval_postprocess", "_lib"]

@@ -1,0 +1,37 @@
+// libvitk: version, error reporting, device query.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vitk {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int sm_count() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached = n;
+  return n;
+}
+}  // namespace vitk
+
+extern "C" {
+int vitk_version(void) { return VITK_VERSION; }
+const char* vitk_last_error_string(void) { return vitk::g_err; }
+int vitk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  VITK_CUDA(cudaGetDevice(&dev));
+  if (sm_count) VITK_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major) VITK_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor) VITK_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return VITK_OK;
+}
+}

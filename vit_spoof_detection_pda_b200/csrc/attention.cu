@@ -1,0 +1,34 @@
+// C-ABI of the attention core + engine dispatch (fp32 -> FFMA kernel, bf16 -> tensor-core kernel).
+#include "common.cuh"
+
+namespace vitk {
+int attn_fwd_simt(const void* qkv, void* out, float* lse, int batch, int dtype, cudaStream_t st);
+int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
+                  int dtype, cudaStream_t st);
+int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t st);
+int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
+                 cudaStream_t st);
+
+int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dtype, cudaStream_t st) {
+  if (dtype == VITK_BF16 && default_engine() != VITK_ENGINE_SIMT) return attn_fwd_mma(qkv, out, lse, batch, st);
+  return attn_fwd_simt(qkv, out, lse, batch, dtype, st);
+}
+int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
+                      int dtype, cudaStream_t st) {
+  if (dtype == VITK_BF16 && default_engine() != VITK_ENGINE_SIMT)
+    return attn_bwd_mma(qkv, out, dout, lse, dqkv, batch, st);
+  return attn_bwd_simt(qkv, out, dout, lse, dqkv, batch, dtype, st);
+}
+}  // namespace vitk
+
+using namespace vitk;
+
+extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int batch, int dtype, void* stream) {
+  VITK_CHECK_ARG(qkv && out && batch > 0 && (dtype == VITK_F32 || dtype == VITK_BF16));
+  return attn_fwd_dispatch(qkv, out, lse, batch, dtype, (cudaStream_t)stream);
+}
+extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                             int batch, int dtype, void* stream) {
+  VITK_CHECK_ARG(qkv && out && dout && lse && dqkv && batch > 0 && (dtype == VITK_F32 || dtype == VITK_BF16));
+  return attn_bwd_dispatch(qkv, out, dout, lse, dqkv, batch, dtype, (cudaStream_t)stream);
+}

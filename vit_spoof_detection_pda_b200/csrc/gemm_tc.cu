@@ -1,0 +1,503 @@
+// tcgen05 / TMEM / TMA GEMM engine for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+//   C[i][j] = sum_r A(i,r) * B(j,r)  + fused epilogue (gemm.cuh)
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0        TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier expect_tx)
+//   warp 1        MMA issuer     (one elected lane: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16,
+//                                 accumulators double-buffered in TMEM; tcgen05.commit -> mbarriers)
+//   warps 2..5    epilogue       (tcgen05.ld 32x32b -> registers -> bias/GELU/residual/scatter -> global)
+// Both operands may be K-major (reduction index contiguous: forward X W^T) or MN-major (row index
+// contiguous: dgrad's W, wgrad's dY^T and X) -- the major-ness is a bit in the instruction descriptor
+// plus the canonical 128B-swizzle shared-memory layout the TMA boxes are written in -- and may be stored
+// head-major ([C/64][M][64], q/k/v and their gradients), which is just a different 3-D tensor map.
+// Work items are (m-tile, n-tile, k-split); split-K items accumulate with fp32 atomics (wgrad).
+//
+// Replaces the cuBLASLt GEMMs behind timm's nn.Linear layers (SURVEY.md 2.1 K4,K6,K7,K8 and their
+// autograd backward), reached from /root/reference/train_advanced.py:327-330.
+#include <cuda.h>
+
+#include "gemm.cuh"
+
+namespace vitk {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;              // 64 bf16 = 128 B = one swizzle row
+constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARP0 = 2;
+constexpr uint32_t TC_A_STAGE_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+
+// operand addressing modes (see header comment)
+enum { OP_KM_FLAT = 0, OP_KM_SPLIT = 1, OP_MN_FLAT = 2, OP_MN_SPLIT = 3 };
+
+struct TcParams {
+  int32_t I, J, R;
+  int32_t a_mode, b_mode;
+  int32_t n_tiles_m, n_tiles_n, splits, kb_total, kb_per_split;
+  uint32_t idesc;
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // bytes
+  uint32_t a_kstep, b_kstep;            // bytes advanced per UMMA_K=16 step
+  EpiParams ep;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 64-bit shared-memory matrix descriptor (SWIZZLE_128B, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// vectorised epilogue: one thread owns row i, 32 consecutive columns j0..j0+31
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+    reinterpret_cast<uint4*>(dst)[q] = u;
+  }
+}
+__device__ __forceinline__ void load_bf16x32(const bf16* src, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 u = reinterpret_cast<const uint4*>(src)[q];
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[q * 8 + 0] = a.x; v[q * 8 + 1] = a.y; v[q * 8 + 2] = b.x; v[q * 8 + 3] = b.y;
+    v[q * 8 + 4] = c.x; v[q * 8 + 5] = c.y; v[q * 8 + 6] = d.x; v[q * 8 + 7] = d.y;
+  }
+}
+__device__ __forceinline__ void add_bias32(const float* __restrict__ bias, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    v[q * 4 + 0] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
+  }
+}
+
+__device__ __forceinline__ void epilogue_row32(const EpiParams& ep, int i, int j0, float (&v)[32]) {
+  switch (ep.mode) {
+    case E_STORE: {
+      if (ep.bias) add_bias32(ep.bias + j0, v);
+      if (ep.out_dtype == VITK_BF16) {
+        store_bf16x32(reinterpret_cast<bf16*>(ep.out) + (int64_t)i * ep.ldc + j0, v);
+      } else {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+    } break;
+    case E_BIAS_GELU: {
+      add_bias32(ep.bias + j0, v);
+      const int64_t o = (int64_t)i * ep.ldc + j0;
+      if (ep.aux) store_bf16x32(reinterpret_cast<bf16*>(ep.aux) + o, v);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] = gelu_erf(__bfloat162float(__float2bfloat16_rn(v[q])));
+      store_bf16x32(reinterpret_cast<bf16*>(ep.out) + o, v);
+    } break;
+    case E_BIAS_RESIDUAL: {
+      add_bias32(ep.bias + j0, v);
+      const int64_t o = (int64_t)i * ep.ldc + j0;
+      const float4* r = reinterpret_cast<const float4*>(ep.residual + o);
+      float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 rv = r[q];
+        d[q] = make_float4(rv.x + v[q * 4], rv.y + v[q * 4 + 1], rv.z + v[q * 4 + 2], rv.w + v[q * 4 + 3]);
+      }
+    } break;
+    case E_QKV_SCATTER: {
+      add_bias32(ep.bias + j0, v);
+      const int64_t o = (int64_t)(j0 >> 6) * ep.hm_rows * 64 + (int64_t)i * 64 + (j0 & 63);
+      store_bf16x32(reinterpret_cast<bf16*>(ep.out) + o, v);
+    } break;
+    case E_GELU_BWD: {
+      const int64_t o = (int64_t)i * ep.ldc + j0;
+      float u[32];
+      load_bf16x32(reinterpret_cast<const bf16*>(ep.aux) + o, u);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] *= gelu_erf_grad(u[q]);
+      store_bf16x32(reinterpret_cast<bf16*>(ep.out) + o, v);
+    } break;
+    case E_ACCUM: {
+      float* d = reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + q * 4), "f"(v[q * 4]), "f"(v[q * 4 + 1]),
+                     "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3]) : "memory");
+    } break;
+    case E_PATCH: {
+      const int t = i % VITK_NTOK;
+      const float4* pe = reinterpret_cast<const float4*>(ep.residual + (int64_t)t * ep.ldc + j0);
+      float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j0);
+      if (t == 0) {
+        const float4* c = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.aux) + j0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 a = c[q], p = pe[q];
+          d[q] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+        }
+      } else {
+        add_bias32(ep.bias + j0, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 p = pe[q];
+          d[q] = make_float4(v[q * 4] + p.x, v[q * 4 + 1] + p.y, v[q * 4 + 2] + p.z, v[q * 4 + 3] + p.w);
+        }
+      }
+    } break;
+    default: break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN> struct TcCfg {
+  static constexpr uint32_t B_STAGE_BYTES = BN * TC_BK * 2;
+  static constexpr uint32_t STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (256 or 512: powers of two)
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void tc_issue_operand_loads(const CUtensorMap* map, int mode, uint32_t dst, uint32_t bar,
+                                                       int row0, int rows_in_tile, int r0) {
+  // K-major: one box [rows_in_tile][64 r]; MN-major: rows_in_tile/64 boxes [64 r][64 rows], 8 KB apart
+  if (mode == OP_KM_FLAT) {
+    tma_load_3d(dst, map, bar, r0, row0, 0);
+  } else if (mode == OP_KM_SPLIT) {
+    tma_load_3d(dst, map, bar, 0, row0, r0 >> 6);
+  } else if (mode == OP_MN_FLAT) {
+    for (int a = 0; a < rows_in_tile / 64; ++a) tma_load_3d(dst + a * 8192, map, bar, row0 + a * 64, r0, 0);
+  } else {
+    for (int a = 0; a < rows_in_tile / 64; ++a) tma_load_3d(dst + a * 8192, map, bar, 0, r0, (row0 >> 6) + a);
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barrier layout: full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                 "r"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int n_items = p.n_tiles_m * p.n_tiles_n * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item % (p.n_tiles_m * p.n_tiles_n), split = item / (p.n_tiles_m * p.n_tiles_n);
+        const int i0 = (tile / p.n_tiles_n) * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          tc_issue_operand_loads(&map_a, p.a_mode, sa, full_bar(stage), i0, TC_BM, kb * TC_BK);
+          tc_issue_operand_loads(&map_b, p.b_mode, sa + TC_A_STAGE_BYTES, full_bar(stage), j0, BN, kb * TC_BK);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int split = item / (p.n_tiles_m * p.n_tiles_n);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + TC_A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * p.a_kstep, p.a_lbo, p.a_sbo);
+            const uint64_t bdesc = make_smem_desc(sb + k * p.b_kstep, p.b_lbo, p.b_sbo);
+            tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));      // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int tile = item % (p.n_tiles_m * p.n_tiles_n);
+      const int i0 = (tile / p.n_tiles_n) * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int i = i0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t raw[32];
+        tc_ld32(taddr + c * 32, raw);
+        if (i < p.I) {
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
+          epilogue_row32(p.ep, i, j0 + c * 32, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// Builds the 3-D map of one operand and returns its addressing mode.
+static int make_operand_map(const void* base, const MatLayout& l, int rows, int R, int tile_rows, CUtensorMap* map, int* mode) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return VITK_ERR_DRIVER; }
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  if (l.split == 0 && l.s_col == 1) {             // K-major flat: (r, row)
+    *mode = OP_KM_FLAT;
+    dims[0] = R; dims[1] = rows; dims[2] = 1;
+    strides[0] = (cuuint64_t)l.s_row * 2; strides[1] = strides[0] * rows;
+    box[0] = TC_BK; box[1] = tile_rows; box[2] = 1;
+  } else if (l.split == 2 && l.s_col == 1 && l.s_row == 64) {  // K-major, reduction index stored in 64-blocks
+    *mode = OP_KM_SPLIT;
+    dims[0] = 64; dims[1] = rows; dims[2] = R / 64;
+    strides[0] = 128; strides[1] = (cuuint64_t)l.s_blk * 2;
+    box[0] = 64; box[1] = tile_rows; box[2] = 1;
+  } else if (l.split == 0 && l.s_row == 1) {      // MN-major flat: (row, r)
+    *mode = OP_MN_FLAT;
+    dims[0] = rows; dims[1] = R; dims[2] = 1;
+    strides[0] = (cuuint64_t)l.s_col * 2; strides[1] = strides[0] * R;
+    box[0] = 64; box[1] = TC_BK; box[2] = 1;
+  } else if (l.split == 1 && l.s_row == 1 && l.s_col == 64) {  // MN-major, row index stored in 64-blocks
+    *mode = OP_MN_SPLIT;
+    dims[0] = 64; dims[1] = R; dims[2] = rows / 64;
+    strides[0] = 128; strides[1] = (cuuint64_t)l.s_blk * 2;
+    box[0] = 64; box[1] = TC_BK; box[2] = 1;
+  } else {
+    set_error("gemm_tc: operand layout not expressible as a TMA tensor map");
+    return VITK_ERR_UNSUPPORTED;
+  }
+  if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15)) {
+    set_error("gemm_tc: operand base/strides must be 16-byte aligned");
+    return VITK_ERR_ARG;
+  }
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u)", (int)r,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)strides[0], (unsigned long long)strides[1], box[0], box[1], box[2]);
+    return VITK_ERR_DRIVER;
+  }
+  return VITK_OK;
+}
+
+static int g_tc_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+template <int BN>
+static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    VITK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  CUtensorMap map_a, map_b;
+  TcParams p{};
+  p.I = pr.I; p.J = pr.J; p.R = pr.R;
+  VITK_TRY(make_operand_map(pr.A, pr.la, pr.I, pr.R, TC_BM, &map_a, &p.a_mode));
+  VITK_TRY(make_operand_map(pr.B, pr.lb, pr.J, pr.R, BN, &map_b, &p.b_mode));
+  const bool a_mn = p.a_mode >= OP_MN_FLAT, b_mn = p.b_mode >= OP_MN_FLAT;
+  // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  // canonical SWIZZLE_128B layouts: K-major: 8-row groups 1024 B apart (SBO), LBO unused;
+  // MN-major: 8-r groups 1024 B apart (SBO), 64-wide MN atoms TC_BK*128 B apart (LBO)
+  p.a_sbo = 1024; p.a_lbo = a_mn ? TC_BK * 128 : 16; p.a_kstep = a_mn ? 16 * 128 : 32;
+  p.b_sbo = 1024; p.b_lbo = b_mn ? TC_BK * 128 : 16; p.b_kstep = b_mn ? 16 * 128 : 32;
+  if (g_tc_debug[0] == 1) {  // debug variant: swap LBO/SBO roles of MN-major operands
+    if (a_mn) { p.a_sbo = TC_BK * 128; p.a_lbo = 1024; }
+    if (b_mn) { p.b_sbo = TC_BK * 128; p.b_lbo = 1024; }
+  }
+  p.n_tiles_m = (pr.I + TC_BM - 1) / TC_BM;
+  p.n_tiles_n = pr.J / BN;
+  p.kb_total = (pr.R + TC_BK - 1) / TC_BK;
+  const int tiles = p.n_tiles_m * p.n_tiles_n;
+  const int sms = sm_count();
+  int splits = 1;
+  if (pr.ep.mode == E_ACCUM) {
+    splits = (sms + tiles - 1) / tiles;                    // fill the machine at least once
+    if (splits > p.kb_total / 4) splits = p.kb_total / 4;  // keep >= 4 k-blocks per item
+    if (splits < 1) splits = 1;
+    if (g_tc_debug[1] > 0) splits = g_tc_debug[1];
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.ep = pr.ep;
+  const int n_items = tiles * p.splits;
+  const int grid = n_items < sms ? n_items : sms;
+  gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(map_a, map_b, p);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
+  VITK_CHECK_ARG(pr.I > 0 && pr.J > 0 && pr.R > 0 && pr.A && pr.B && pr.ep.out);
+  if (pr.in_dtype != VITK_BF16) { set_error("gemm_tc: bf16 operands only"); return VITK_ERR_UNSUPPORTED; }
+  if (pr.ep.mode != E_STORE && pr.ep.mode != E_ACCUM && pr.ep.mode != E_BIAS_RESIDUAL && pr.ep.mode != E_PATCH &&
+      pr.ep.out_dtype != VITK_BF16) { set_error("gemm_tc: epilogue expects bf16 output"); return VITK_ERR_UNSUPPORTED; }
+  if (pr.J % 128 != 0 || pr.ep.ldc % 8 != 0) { set_error("gemm_tc: J must be a multiple of 128 (got %d)", pr.J); return VITK_ERR_UNSUPPORTED; }
+  if (pr.J % 256 == 0 && g_tc_debug[2] != 128) return launch_tc<256>(pr, st);
+  return launch_tc<128>(pr, st);
+}
+
+}  // namespace vitk
+
+extern "C" int vitk_debug_set(int key, int value) {
+  if (key < 0 || key >= 8) return VITK_ERR_ARG;
+  vitk::g_tc_debug[key] = value;
+  return VITK_OK;
+}

@@ -1,0 +1,209 @@
+// LayerNorm(768) forward / backward -- HBM-bound, one warp per row, row held in registers.
+// Replaces ATen native_layer_norm reached from timm Block.norm1/.norm2, vit.norm (eps 1e-6) and
+// classifier[0] (eps 1e-5; /root/reference/train_advanced.py:194).
+//
+// Algorithmic bytes per row: fwd 768*(4 in + sizeof(T) out) (+8 stats); bwd 768*(sizeof(T) dy + 4 x
+// + 4 dres + 4 dx [+2 dx16]).
+#include "common.cuh"
+
+namespace vitk {
+
+constexpr int LN_COLS = VITK_DIM;        // 768
+constexpr int LN_VEC = LN_COLS / 128;    // 6 float4 per lane
+constexpr int LN_WARPS = 8;
+constexpr int LN_BWD_MAX_CTAS = 296;     // 2 per SM
+
+template <typename T> struct Vec4IO;
+template <> struct Vec4IO<float> {
+  static __device__ __forceinline__ float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4IO<bf16> {
+  static __device__ __forceinline__ float4 load(const bf16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void store(bf16* p, float4 v) {
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ gamma,
+              const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, int rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + (int64_t)row * x_stride;
+  float4 v[LN_VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_VEC; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / LN_COLS);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_VEC; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float var = warp_sum(q) * (1.0f / LN_COLS);
+  const float rstd = 1.0f / sqrtf(var + eps);
+  T* yr = y + (int64_t)row * LN_COLS;
+#pragma unroll
+  for (int i = 0; i < LN_VEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 b = *reinterpret_cast<const float4*>(beta + c);
+    float4 o;
+    o.x = v[i].x * rstd * g.x + b.x;
+    o.y = v[i].y * rstd * g.y + b.y;
+    o.z = v[i].z * rstd * g.z + b.z;
+    o.w = v[i].w * rstd * g.w + b.w;
+    Vec4IO<T>::store(yr + c, o);
+  }
+  if (lane == 0 && mean_out) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+// Persistent over rows; per-lane register partials of dgamma/dbeta, one [2][768] partial per CTA.
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_stride,
+              const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+              const float* dres, float* dx, bf16* __restrict__ dx16,  // dres may alias dx (in-place residual-grad update)
+              float* __restrict__ partial, int rows) {
+  __shared__ float red[LN_WARPS][LN_COLS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 g[LN_VEC], dg[LN_VEC], db[LN_VEC];
+#pragma unroll
+  for (int i = 0; i < LN_VEC; ++i) {
+    g[i] = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+    const float* xr = x + (int64_t)row * x_stride;
+    const T* dyr = dy + (int64_t)row * LN_COLS;
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[LN_VEC], gy[LN_VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      const float4 d = Vec4IO<T>::load(dyr + c);
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      gy[i] = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+      s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+      s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+    }
+    const float c1 = warp_sum(s1) * (1.0f / LN_COLS);
+    const float c2 = warp_sum(s2) * (1.0f / LN_COLS);
+#pragma unroll
+    for (int i = 0; i < LN_VEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 o;
+      o.x = rs * (gy[i].x - c1 - xh[i].x * c2);
+      o.y = rs * (gy[i].y - c1 - xh[i].y * c2);
+      o.z = rs * (gy[i].z - c1 - xh[i].z * c2);
+      o.w = rs * (gy[i].w - c1 - xh[i].w * c2);
+      if (dres) {
+        const float4 r = *reinterpret_cast<const float4*>(dres + (int64_t)row * LN_COLS + c);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      *reinterpret_cast<float4*>(dx + (int64_t)row * LN_COLS + c) = o;
+      if (dx16) Vec4IO<bf16>::store(dx16 + (int64_t)row * LN_COLS + c, o);
+    }
+  }
+  // CTA reduction of the per-warp partials: dgamma then dbeta
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < LN_VEC; ++i)
+      *reinterpret_cast<float4*>(&red[warp][(i * 32 + lane) * 4]) = pass == 0 ? dg[i] : db[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < LN_COLS; c += LN_WARPS * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
+      partial[((int64_t)blockIdx.x * 2 + pass) * LN_COLS + c] = s;
+    }
+  }
+}
+
+__global__ void ln_bwd_reduce_kernel(const float* __restrict__ partial, int nparts,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2*768
+  if (c >= 2 * LN_COLS) return;
+  const int pass = c / LN_COLS, col = c % LN_COLS;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[((int64_t)p * 2 + pass) * LN_COLS + col];
+  float* dst = pass == 0 ? dgamma : dbeta;
+  if (dst) dst[col] += s;
+}
+
+}  // namespace vitk
+
+using namespace vitk;
+
+extern "C" size_t vitk_layernorm_bwd_scratch_floats(void) { return (size_t)LN_BWD_MAX_CTAS * 2 * LN_COLS; }
+
+extern "C" int vitk_layernorm_fwd(const float* x, int64_t x_stride, const float* gamma, const float* beta,
+                                  void* y, int y_dtype, float* mean, float* rstd, int rows, float eps,
+                                  void* stream) {
+  VITK_CHECK_ARG(x && gamma && beta && y && rows >= 0);
+  VITK_CHECK_ARG((mean == nullptr) == (rstd == nullptr));
+  VITK_CHECK_ARG(x_stride % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0);
+  if (rows == 0) return VITK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  if (y_dtype == VITK_F32)
+    ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, st>>>(x, x_stride, gamma, beta, (float*)y, mean, rstd, rows, eps);
+  else if (y_dtype == VITK_BF16)
+    ln_fwd_kernel<bf16><<<grid, LN_WARPS * 32, 0, st>>>(x, x_stride, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
+  else
+    VITK_CHECK_ARG(!"bad dtype");
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, int64_t x_stride,
+                                  const float* gamma, const float* mean, const float* rstd, const float* dres,
+                                  float* dx, void* dx16, float* dgamma, float* dbeta, float* partial, int rows,
+                                  void* stream) {
+  VITK_CHECK_ARG(dy && x && gamma && mean && rstd && dx && partial && rows >= 0);
+  VITK_CHECK_ARG(x_stride % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)dx % 16) == 0);
+  if (rows == 0) return VITK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int cap = sm_count() * 2 < LN_BWD_MAX_CTAS ? sm_count() * 2 : LN_BWD_MAX_CTAS;
+  if (grid > cap) grid = cap;
+  if (dy_dtype == VITK_F32)
+    ln_bwd_kernel<float><<<grid, LN_WARPS * 32, 0, st>>>((const float*)dy, x, x_stride, gamma, mean, rstd, dres, dx,
+                                                        (bf16*)dx16, partial, rows);
+  else if (dy_dtype == VITK_BF16)
+    ln_bwd_kernel<bf16><<<grid, LN_WARPS * 32, 0, st>>>((const bf16*)dy, x, x_stride, gamma, mean, rstd, dres, dx,
+                                                       (bf16*)dx16, partial, rows);
+  else
+    VITK_CHECK_ARG(!"bad dtype");
+  VITK_LAUNCH_CHECK();
+  if (dgamma || dbeta) {
+    ln_bwd_reduce_kernel<<<(2 * LN_COLS + 255) / 256, 256, 0, st>>>(partial, grid, dgamma, dbeta);
+    VITK_LAUNCH_CHECK();
+  }
+  return VITK_OK;
+}

@@ -1,0 +1,192 @@
+// nn.Linear forward / dgrad / wgrad and the patch-embedding GEMM: builds GemmProblems and
+// dispatches them to the tcgen05 engine (bf16) or the SIMT engine (fp32-validate / cross-check).
+// Reference call sites: timm Attention.qkv / .proj, Mlp.fc1 / .fc2 and PatchEmbed.proj reached from
+// /root/reference/train_advanced.py:203 (self.vit(x)); backward from loss.backward() at :330.
+#include <atomic>
+
+#include "gemm.cuh"
+
+namespace vitk {
+
+static std::atomic<int> g_engine{VITK_ENGINE_AUTO};
+int default_engine() { return g_engine.load(); }
+
+static int run_gemm(const GemmProblem& p, int engine, int simt_splits, cudaStream_t st) {
+  if (engine == VITK_ENGINE_AUTO) engine = default_engine();
+  if (p.in_dtype == VITK_F32) engine = VITK_ENGINE_SIMT;  // fp32 products only exist on the FFMA pipe
+  if (engine == VITK_ENGINE_AUTO) engine = VITK_ENGINE_TCGEN05;
+  if (engine == VITK_ENGINE_TCGEN05) return gemm_tc(p, st);
+  return gemm_simt(p, simt_splits, st);
+}
+
+// db[c] += sum_m dy(m, c)      (bias gradient; dy row-major [M][C] or head-major)
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ dy, MatLayout l, int M, int C, int rows_per_block, float* __restrict__ db) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float s = 0.f;
+  if (c < C)
+    for (int m = m0 + ty; m < m1; m += 8) s += to_f32(dy[l.at(m, c)]);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += red[w][tx];
+    atomicAdd(db + c, s);
+  }
+}
+
+static int colsum(const void* dy, int dtype, MatLayout l, int M, int C, float* db, cudaStream_t st) {
+  const int rows_per_block = 512;
+  dim3 grid((C + 31) / 32, (M + rows_per_block - 1) / rows_per_block);
+  if (dtype == VITK_BF16) colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, l, M, C, rows_per_block, db);
+  else colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, l, M, C, rows_per_block, db);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+// patches[(b*197 + t)][c*256 + i*16 + j] = image[b][c][py*16+i][px*16+j], t = 1 + py*14 + px; row t=0 zero.
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ img, T* __restrict__ patches, int batch) {
+  const int64_t total = (int64_t)batch * VITK_NTOK * (VITK_DIM / 4);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k4 = (int)(idx % (VITK_DIM / 4));
+    const int64_t row = idx / (VITK_DIM / 4);
+    const int t = (int)(row % VITK_NTOK), b = (int)(row / VITK_NTOK);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t > 0) {
+      const int p = t - 1, py = p / 14, px = p % 14;
+      const int k = k4 * 4, c = k >> 8, i = (k >> 4) & 15, j = k & 15;
+      v = *reinterpret_cast<const float4*>(img + (((int64_t)b * 3 + c) * VITK_IMG + py * 16 + i) * VITK_IMG + px * 16 + j);
+    }
+    T* dst = patches + row * VITK_DIM + k4 * 4;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(dst) = v;
+    } else {
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(dst) = u;
+    }
+  }
+}
+
+// dpos[t][j] += sum_b dx0[b][t][j]; dcls[j] += that at t = 0; dbpe[j] += sum over t >= 1
+__global__ void __launch_bounds__(256)
+embed_param_grads_kernel(const float* __restrict__ dx0, int batch, float* __restrict__ dpos,
+                         float* __restrict__ dcls, float* __restrict__ dbpe) {
+  const int t = blockIdx.x;
+  for (int j = threadIdx.x; j < VITK_DIM; j += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < batch; ++b) s += dx0[((int64_t)b * VITK_NTOK + t) * VITK_DIM + j];
+    dpos[(int64_t)t * VITK_DIM + j] += s;
+    if (t == 0) dcls[j] += s;
+    else atomicAdd(dbpe + j, s);
+  }
+}
+
+}  // namespace vitk
+
+using namespace vitk;
+
+extern "C" int vitk_set_gemm_engine(int engine) { return g_engine.exchange(engine); }
+
+extern "C" int vitk_linear_fwd(const void* x, int x_layout, const void* w, const float* bias, void* y, void* aux,
+                               int M, int N, int K, int epilogue, int dtype, int engine, void* stream) {
+  VITK_CHECK_ARG(x && w && bias && y && M > 0 && N > 0 && K > 0);
+  VITK_CHECK_ARG(dtype == VITK_F32 || dtype == VITK_BF16);
+  GemmProblem p{};
+  p.I = M; p.J = N; p.R = K;
+  p.A = x; p.B = w; p.in_dtype = dtype;
+  p.la = x_layout == VITK_LAYOUT_HEADMAJOR ? layout_headmajor_rows_m(M) : layout_rowmajor(K);
+  p.lb = layout_rowmajor(K);
+  p.ep.out = y; p.ep.bias = bias; p.ep.ldc = N; p.ep.out_dtype = dtype;
+  switch (epilogue) {
+    case VITK_EPI_BIAS: p.ep.mode = E_STORE; break;
+    case VITK_EPI_BIAS_GELU: p.ep.mode = E_BIAS_GELU; p.ep.aux = aux; break;  // aux == NULL: eval, u not kept
+    case VITK_EPI_BIAS_RESIDUAL:
+      VITK_CHECK_ARG(aux);
+      p.ep.mode = E_BIAS_RESIDUAL; p.ep.residual = (const float*)aux; p.ep.out_dtype = VITK_F32;
+      break;
+    case VITK_EPI_QKV_SCATTER: VITK_CHECK_ARG(N % 64 == 0); p.ep.mode = E_QKV_SCATTER; p.ep.hm_rows = M; break;
+    default: VITK_CHECK_ARG(!"bad epilogue");
+  }
+  return run_gemm(p, engine, 1, (cudaStream_t)stream);
+}
+
+extern "C" int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, const void* gelu_u,
+                                 int M, int N, int K, int dtype, int engine, void* stream) {
+  VITK_CHECK_ARG(dy && w && dx && M > 0 && N > 0 && K > 0);
+  VITK_CHECK_ARG(dtype == VITK_F32 || dtype == VITK_BF16);
+  VITK_CHECK_ARG(dy_layout != VITK_LAYOUT_HEADMAJOR || N % 64 == 0);
+  GemmProblem p{};
+  p.I = M; p.J = K; p.R = N;
+  p.A = dy; p.B = w; p.in_dtype = dtype;
+  p.la = dy_layout == VITK_LAYOUT_HEADMAJOR ? layout_headmajor_rows_m(M) : layout_rowmajor(N);
+  p.lb = layout_transposed(K);  // B(j=k, r=n) = w[n*K + k]
+  p.ep.out = dx; p.ep.ldc = K; p.ep.out_dtype = dtype;
+  p.ep.mode = gelu_u ? E_GELU_BWD : E_STORE;
+  p.ep.aux = const_cast<void*>(gelu_u);
+  return run_gemm(p, engine, 1, (cudaStream_t)stream);
+}
+
+extern "C" int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, float* dw, float* db, int M, int N,
+                                 int K, int dtype, int engine, void* stream) {
+  VITK_CHECK_ARG(dy && x && dw && M > 0 && N > 0 && K > 0);
+  VITK_CHECK_ARG(dtype == VITK_F32 || dtype == VITK_BF16);
+  VITK_CHECK_ARG(dy_layout != VITK_LAYOUT_HEADMAJOR || N % 64 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmProblem p{};
+  p.I = N; p.J = K; p.R = M;
+  p.A = dy; p.B = x; p.in_dtype = dtype;
+  p.la = dy_layout == VITK_LAYOUT_HEADMAJOR ? layout_headmajor_rows_c(M) : layout_transposed(N);
+  p.lb = layout_transposed(K);
+  p.ep.mode = E_ACCUM; p.ep.out = dw; p.ep.ldc = K; p.ep.out_dtype = VITK_F32;
+  // split the token reduction so small weight tiles still fill the machine
+  const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
+  int splits = (4 * sm_count() + tiles - 1) / tiles;
+  if (splits > (M + 255) / 256) splits = (M + 255) / 256;
+  VITK_TRY(run_gemm(p, engine, splits, st));
+  if (db) {
+    const MatLayout l = dy_layout == VITK_LAYOUT_HEADMAJOR ? layout_headmajor_rows_m(M) : layout_rowmajor(N);
+    VITK_TRY(colsum(dy, dtype, l, M, N, db, st));
+  }
+  return VITK_OK;
+}
+
+extern "C" int vitk_patch_embed_fwd(const float* images, const void* wpe, const float* bpe, const float* cls,
+                                    const float* pos, void* patches, float* x0, int batch, int dtype, int engine,
+                                    void* stream) {
+  VITK_CHECK_ARG(images && wpe && bpe && cls && pos && patches && x0 && batch > 0);
+  VITK_CHECK_ARG(dtype == VITK_F32 || dtype == VITK_BF16);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)batch * VITK_NTOK * (VITK_DIM / 4);
+  const int grid = (int)((total + 255) / 256 < (int64_t)sm_count() * 16 ? (total + 255) / 256 : (int64_t)sm_count() * 16);
+  if (dtype == VITK_BF16) im2col_kernel<bf16><<<grid, 256, 0, st>>>(images, (bf16*)patches, batch);
+  else im2col_kernel<float><<<grid, 256, 0, st>>>(images, (float*)patches, batch);
+  VITK_LAUNCH_CHECK();
+  GemmProblem p{};
+  p.I = batch * VITK_NTOK; p.J = VITK_DIM; p.R = VITK_DIM;
+  p.A = patches; p.B = wpe; p.in_dtype = dtype;
+  p.la = layout_rowmajor(VITK_DIM); p.lb = layout_rowmajor(VITK_DIM);
+  p.ep.mode = E_PATCH; p.ep.out = x0; p.ep.out_dtype = VITK_F32; p.ep.bias = bpe; p.ep.residual = pos;
+  p.ep.aux = const_cast<float*>(cls); p.ep.ldc = VITK_DIM;
+  return run_gemm(p, engine, 1, st);
+}
+
+extern "C" int vitk_patch_embed_wgrad(const float* dx0, const void* dx0_act, const void* patches, float* dwpe,
+                                      float* dbpe, float* dcls, float* dpos, int batch, int dtype, int engine,
+                                      void* stream) {
+  VITK_CHECK_ARG(dx0 && dx0_act && patches && dwpe && dbpe && dcls && dpos && batch > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  // CLS rows of `patches` are zero, so the plain token-row wgrad is exact (no row remap needed)
+  VITK_TRY(vitk_linear_wgrad(dx0_act, VITK_LAYOUT_ROWMAJOR, patches, dwpe, nullptr, batch * VITK_NTOK, VITK_DIM,
+                             VITK_DIM, dtype, engine, stream));
+  embed_param_grads_kernel<<<VITK_NTOK, 256, 0, st>>>(dx0, batch, dpos, dcls, dbpe);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}

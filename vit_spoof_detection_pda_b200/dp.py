@@ -1,0 +1,107 @@
+"""Batch-sharded data parallelism: one process per GPU, bucketed gradient all-reduce over NCCL
+(NVLink 5 / NVSwitch) overlapped with backward.
+
+The reference is single-GPU (no torch.distributed call site); this is the new
+functionality BASELINE config #5 asks for.  Backward runs in stages (module.stage_ranges()); the flat
+gradient range a stage finalises is contiguous and adjacent to the previous stage's range, so buckets
+are plain slices of the flat gradient buffer -- no packing copies.  Each full bucket is all-reduced
+asynchronously on the process group's communication stream while the next stage computes; the last
+bucket's wait is the only exposed communication.  Inference shards by batch with no collective.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+class GradBucketer:
+    """Greedy merge of consecutive (descending, adjacent) flat ranges into buckets of >= bucket_elems,
+    all-reduced (average) as soon as they close.  Device- and backend-agnostic (tested with gloo on CPU)."""
+
+    def __init__(self, bucket_elems: int, group=None):
+        self.bucket_elems = int(bucket_elems)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._open: Optional[Tuple[int, int]] = None
+        self._works: List = []
+        self.launched: List[Tuple[int, int]] = []   # for tests / introspection
+
+    def reset(self):
+        self._open = None
+        self._works = []
+        self.launched = []
+
+    def _launch(self, flat: torch.Tensor, lo: int, hi: int):
+        self.launched.append((lo, hi))
+        if self.world == 1:
+            return
+        view = flat[lo:hi]
+        backend = dist.get_backend(self.group)
+        if backend == "nccl":
+            self._works.append((dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True), None))
+        else:  # gloo has no AVG
+            self._works.append((dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True), view))
+
+    def add(self, flat: torch.Tensor, lo: int, hi: int):
+        """Register that flat[lo:hi] is final. Ranges must arrive adjacent and descending (or be disjoint)."""
+        if self._open is None:
+            self._open = (lo, hi)
+        elif hi == self._open[0]:
+            self._open = (lo, self._open[1])
+        elif lo == self._open[1]:
+            self._open = (self._open[0], hi)
+        else:  # not adjacent: close what we have
+            self._launch(flat, *self._open)
+            self._open = (lo, hi)
+        if self._open[1] - self._open[0] >= self.bucket_elems:
+            self._launch(flat, *self._open)
+            self._open = None
+
+    def finish(self, flat: torch.Tensor):
+        if self._open is not None:
+            self._launch(flat, *self._open)
+            self._open = None
+        for work, view in self._works:
+            work.wait()   # stream-ordered for NCCL (no host block), blocking for gloo
+            if view is not None:
+                view.div_(self.world)
+        self._works = []
+
+
+class DataParallel(nn.Module):
+    """``DataParallel(ViTFaceAntiSpoofing(...).cuda())``: identical replicas, local batch per rank,
+    gradients averaged over ranks during backward."""
+
+    def __init__(self, module: nn.Module, process_group=None, bucket_mb: float = 50.0, broadcast: bool = True):
+        super().__init__()
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (one process per GPU, backend 'nccl')")
+        self.module = module
+        self.group = process_group
+        self.bucketer = GradBucketer(int(bucket_mb * 1e6 / 4), process_group)
+        if broadcast:
+            flat = module.flat_params()
+            dist.broadcast(flat, src=0, group=process_group)
+        module._bucket_hook = self._on_stage
+        module._finish_hook = self._on_finish
+        self._first = True
+
+    def _on_stage(self, stage: int, lo: int, hi: int, flat_grad: torch.Tensor):
+        if stage == 0:
+            self.bucketer.reset()
+        self.bucketer.add(flat_grad, lo, hi)
+
+    def _on_finish(self, flat_grad: torch.Tensor):
+        self.bucketer.finish(flat_grad)
+
+    def forward(self, x):
+        return self.module(x)
+
+    def state_dict(self, *a, **k):
+        return self.module.state_dict(*a, **k)
+
+    def load_state_dict(self, *a, **k):
+        return self.module.load_state_dict(*a, **k)

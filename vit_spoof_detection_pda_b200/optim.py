@@ -1,0 +1,163 @@
+"""Fused Adam / AdamW + fused global-norm clipping over the module's flat parameter / gradient buffers.
+
+Reference call sites (/root/reference/train_advanced.py): ``torch.optim.AdamW(lr=3e-4, weight_decay=0.05,
+betas=(0.9, 0.999))`` :592-597; ``clip_grad_norm_(model.parameters(), 1.0)`` :334; ``optimizer.step()``
+via ``scaler.step`` :335; ``optimizer.zero_grad(set_to_none=True)`` :337; README.md:140-147 names Adam with
+weight_decay 1e-4 (L2), which is ``adamw=False`` here.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def _owner_of(params):
+    params = list(params)
+    if not params:
+        raise ValueError("no parameters")
+    ref = getattr(params[0], "_vitk_owner", None)
+    owner = ref() if ref is not None else None
+    if owner is None:
+        raise RuntimeError("parameters do not belong to a CUDA-resident vitk ViTFaceAntiSpoofing "
+                           "(move the model to CUDA before constructing the optimizer)")
+    return owner, params
+
+
+def _gather_flat_grads(owner, params):
+    """Return the flat gradient buffer; zero-copy when .grad tensors are the views backward produced."""
+    g = owner.flat_grads()
+    base = g.data_ptr()
+    alt = owner._flat_grad_alt
+    for p, off, n in zip(owner._param_list(), owner._offsets, owner._sizes):
+        if p.grad is None:
+            if p.requires_grad:
+                g[off:off + n].zero_()
+            continue
+        if p.grad.data_ptr() != base + 4 * off:
+            g[off:off + n].copy_(p.grad.reshape(-1))   # foreign gradient tensor (cloned / accumulated elsewhere)
+    return g
+
+
+def clip_grad_norm_(parameters, max_norm: float):
+    """Drop-in for ``torch.nn.utils.clip_grad_norm_`` on a vitk model: one deterministic sum-of-squares
+    reduction over the flat gradient buffer; the scaling itself is folded into the next FusedAdam.step().
+    Returns the total norm (0-dim tensor)."""
+    owner, params = _owner_of(parameters)
+    g = _gather_flat_grads(owner, params)
+    lib = L.load()
+    if getattr(owner, "_sumsq_scratch", None) is None:
+        owner._sumsq_scratch = torch.empty(lib.vitk_grad_sumsq_scratch_floats(), dtype=torch.float32, device=g.device)
+        owner._sumsq = torch.zeros(1, dtype=torch.float32, device=g.device)
+    L.call("vitk_grad_sumsq", L.ptr(g), g.numel(), L.ptr(owner._sumsq_scratch), L.ptr(owner._sumsq), L.stream_ptr())
+    owner._pending_clip = (owner._sumsq, float(max_norm))
+    return owner._sumsq.sqrt().reshape(())
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """One kernel over the flat buffers: (optional) clip scale -> Adam/AdamW update -> bf16 shadow write."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, adamw=True,
+                 max_grad_norm=None, grad_mult: float = 1.0):
+        params = list(params)
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, adamw=adamw)
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedAdam supports a single param group (the reference uses one)")
+        self._owner, _ = _owner_of(self.param_groups[0]["params"])
+        self.max_grad_norm = max_grad_norm
+        self.grad_mult = grad_mult
+        self._step = 0
+        self._m = None
+        self._v = None
+
+    def _ensure_state(self, flat):
+        if self._m is None or self._m.device != flat.device or self._m.numel() != flat.numel():
+            self._m = torch.zeros_like(flat)
+            self._v = torch.zeros_like(flat)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        owner = self._owner
+        grp = self.param_groups[0]
+        flat = owner.flat_params()
+        self._ensure_state(flat)
+        g = _gather_flat_grads(owner, grp["params"])
+        sumsq, max_norm = None, 0.0
+        if owner._pending_clip is not None:
+            sumsq, max_norm = owner._pending_clip
+            owner._pending_clip = None
+        elif self.max_grad_norm is not None:
+            clip_grad_norm_(grp["params"], self.max_grad_norm)
+            sumsq, max_norm = owner._pending_clip
+            owner._pending_clip = None
+        # frozen parameters must not move: zero their gradient AND skip decay by masking ranges
+        frozen = [(off, n) for p, off, n in zip(owner._param_list(), owner._offsets, owner._sizes) if not p.requires_grad]
+        self._step += 1
+        p16 = owner._flat16 if owner.precision == "bf16" else None
+        b1, b2 = grp["betas"]
+        if not frozen:
+            self._launch(flat, g, p16, 0, flat.numel(), grp, b1, b2, sumsq, max_norm)
+        else:
+            live = _complement(frozen, flat.numel())
+            for lo, hi in live:
+                self._launch(flat, g, p16, lo, hi, grp, b1, b2, sumsq, max_norm)
+        if p16 is not None:
+            owner.mark_shadow_fresh()
+        return loss
+
+    def _launch(self, flat, g, p16, lo, hi, grp, b1, b2, sumsq, max_norm):
+        n = hi - lo
+        if n <= 0:
+            return
+        L.call("vitk_adam_step", flat.data_ptr() + 4 * lo, g.data_ptr() + 4 * lo, self._m.data_ptr() + 4 * lo,
+               self._v.data_ptr() + 4 * lo, (p16.data_ptr() + 2 * lo) if p16 is not None else None, n,
+               float(grp["lr"]), float(b1), float(b2), float(grp["eps"]), float(grp["weight_decay"]),
+               1 if grp["adamw"] else 0, self._step, float(self.grad_mult), L.ptr(sumsq), float(max_norm), L.stream_ptr())
+
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none=set_to_none)
+
+    # torch.optim.AdamW-compatible state layout so save_checkpoint (train_advanced.py:475-489) round-trips
+    def state_dict(self):
+        owner = self._owner
+        state = {}
+        if self._m is not None:
+            for i, (p, off, n) in enumerate(zip(owner._param_list(), owner._offsets, owner._sizes)):
+                state[i] = {"step": torch.tensor(float(self._step)),
+                            "exp_avg": self._m[off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": self._v[off:off + n].view(p.shape).clone()}
+        grp = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        grp["params"] = list(range(len(owner._param_list())))
+        return {"state": state, "param_groups": [grp]}
+
+    def load_state_dict(self, sd):
+        owner = self._owner
+        flat = owner.flat_params()
+        self._ensure_state(flat)
+        for k, v in sd["param_groups"][0].items():
+            if k != "params":
+                self.param_groups[0][k] = v
+        for i, (p, off, n) in enumerate(zip(owner._param_list(), owner._offsets, owner._sizes)):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            self._m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self._v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            self._step = int(float(st["step"]))
+
+
+def _complement(ranges, total):
+    out, cur = [], 0
+    for off, n in sorted(ranges):
+        if off > cur:
+            out.append((cur, off))
+        cur = max(cur, off + n)
+    if cur < total:
+        out.append((cur, total))
+    # launches need 16-byte aligned starts: offsets are multiples of 64 elements by construction
+    return out
