@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- ViT-B/16 PAD fine-tune throughput on B200 (BASELINE.json metric), one JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+
+A "step" is the reference's optimisation step (/root/reference/train_advanced.py:322-346): forward,
+focal loss, backward, global-norm clip 1.0, Adam step, zero_grad, LR-schedule step, accuracy -- on one
+synthetic batch of 64 images per GPU (BASELINE.json configs[1]; weak scaling for N > 1 = configs[4]).
+
+  value      img/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public API with pinned HOST inputs: H2D of images+labels and the
+             D2H of loss/accuracy (.item()) inside the timed region every step
+  roofline   the dominant kernel (tcgen05 GEMM): algorithmic FLOPs of every GEMM launch / its CUDA-event
+             duration, recorded live inside real steps (vitk_prof_*), against MEASURED_PEAKS.json
+  cpu_baseline  the oracle (timm-semantics restatement of the reference, fp32) on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ViT-B/16 fine-tune img/s"
+TRAIN_FLOP_PER_IMG = 105.150e9
+FWD_FLOP_PER_IMG = 35.127e9
+PER_GPU_BATCH = 64
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU every 100 ms while running (pynvml)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the oracle (restated reference) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps: int, warmup: int, batch: int = 8, budget_s: float = 150.0):
+    import torch
+    from oracle import vit_oracle as vo   # the one place bench.py executes oracle/: the CPU baseline
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = vo.OracleViTFaceAntiSpoofing(dropout=0.1, depth=12)
+    vo.seeded_init_(model, seed=42)
+    opt = vo.make_optimizer(model.parameters(), "adam", lr=1e-5, weight_decay=1e-4)
+    crit = vo.OracleFocalLoss(0.25, 2.0)
+    images, labels = vo.synthetic_batch(batch, seed=42)
+    t0 = time.perf_counter()
+    vo.oracle_train_step(model, crit, opt, images, labels, 1.0)
+    first = time.perf_counter() - t0
+    # keep the whole run inside the budget: shrink the step count, never the work per image
+    total = max(1, warmup - 1) + steps
+    if first * total > budget_s:
+        steps = max(2, int(budget_s / first) - max(0, warmup - 1))
+    for _ in range(max(0, warmup - 1)):
+        vo.oracle_train_step(model, crit, opt, images, labels, 1.0)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        vo.oracle_train_step(model, crit, opt, images, labels, 1.0)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"img_s": batch / med, "s_per_step": med, "cores": cores, "steps_timed": steps, "batch": batch}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_steps(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["img_s"], "unit": "img/s", "n_gpus": args.gpus,
+        "steps": r["steps_timed"], "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": train_config(args.gpus),
+        "cpu_baseline": {"value": r["img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
+                         "sample": f"{r['steps_timed']} timed steps of batch {r['batch']} (fwd+focal+bwd+clip+Adam, fp32, "
+                                   "oracle port of the reference: timm is not installable here)"},
+        "e2e": {"value": r["img_s"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def train_config(n_gpus):
+    return {"workload": "ViT-B/16 224x224 binary PAD head full fine-tune step (fwd + focal loss + bwd + clip 1.0 + Adam "
+                        "wd 1e-4), bf16, batch 64 per GPU, synthetic data (BASELINE configs[1]; N>1 = configs[4])",
+            "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus, "img": 224, "depth": 12,
+            "dropout": 0.1, "optimizer": "Adam(lr 1e-5, wd 1e-4) + clip_grad_norm 1.0 + cosine LR",
+            "parallelism": f"dp{n_gpus}",
+            "l2": "per-step working set (~5 GB activations + 1 GB params/grads/moments) >> 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import vit_spoof_detection_pda_b200 as pkg
+    from vit_spoof_detection_pda_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()   # fails loudly when libvitk.so is missing
+
+    torch.manual_seed(42)
+    model = pkg.ViTFaceAntiSpoofing(dropout=0.1, depth=12, precision="bf16").to(dev)
+    model.train()
+    net = pkg.DataParallel(model) if world > 1 else model
+    crit = pkg.FocalLoss(alpha=0.25, gamma=2.0)
+    opt = pkg.FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4, adamw=False)
+    total_sched_steps = 2 * (args.warmup + args.steps) + 64
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=total_sched_steps, eta_min=1e-6)
+
+    B = PER_GPU_BATCH
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_pool = 4
+    host_imgs = [torch.randn(B, 3, 224, 224, generator=g).pin_memory() for _ in range(n_pool)]
+    host_lbls = [torch.randint(0, 2, (B,), generator=g).pin_memory() for _ in range(n_pool)]
+    dev_imgs = [t.to(dev) for t in host_imgs]
+    dev_lbls = [t.to(dev) for t in host_lbls]
+
+    def step(images, labels):
+        out = net(images)
+        loss, met = crit(out, labels, with_metrics=True)
+        loss.backward()
+        pkg.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        sched.step()
+        return loss, met
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.vitk_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.vitk_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    # ---- device-resident throughput ("value")
+    for i in range(args.warmup):
+        step(dev_imgs[i % n_pool], dev_lbls[i % n_pool])
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total, launches = timed(lambda i: step(dev_imgs[i % n_pool], dev_lbls[i % n_pool]), args.steps)
+    sampler.stop()
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public API with host buffers ("e2e")
+    def e2e_step(i):
+        images = host_imgs[i % n_pool].to(dev, non_blocking=True)
+        labels = host_lbls[i % n_pool].to(dev, non_blocking=True)
+        loss, met = step(images, labels)
+        return loss.item(), met["ncorrect"].item()   # the reference's two per-step host syncs (train_advanced.py:345-346)
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = B * 3 * 224 * 224 * 4 + B * 8
+    d2h = 4 + 4
+
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        # ---- live per-launch GEMM timing inside real steps -> roofline of the dominant kernel
+        import ctypes as C
+        lib.vitk_prof_enable(1)
+        for i in range(2):
+            step(dev_imgs[i % n_pool], dev_lbls[i % n_pool])
+        torch.cuda.synchronize()
+        maxn = 4096
+        ms_arr = (C.c_float * maxn)()
+        info = (C.c_int * (5 * maxn))()
+        n = lib.vitk_prof_read(ms_arr, info, maxn)
+        lib.vitk_prof_enable(0)
+        fl, tt, fam = 0.0, 0.0, {}
+        for k in range(n):
+            I, J, R, mode, eng = info[5 * k:5 * k + 5]
+            if eng != L.ENGINE_TCGEN05:
+                continue
+            f = 2.0 * I * J * R
+            fl += f
+            tt += ms_arr[k] * 1e-3
+            key = f"{I}x{J}x{R}/epi{mode}"
+            a = fam.setdefault(key, [0, 0.0, 0.0])
+            a[0] += 1; a[1] += f; a[2] += ms_arr[k] * 1e-3
+        achieved = fl / tt / 1e12 if tt > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "vitk::gemm_tc_kernel (tcgen05.mma kind::f16, all GEMM launches of a step)",
+                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] +
+                " (sustained cuBLAS bf16: kernel timed inside a long step)", "gemm_launches_per_step": n // 2,
+                "gemm_share_of_step": (tt / 2) / (ms_total / args.steps / 1e3)}
+        fam_sorted = sorted(fam.items(), key=lambda kv: -kv[1][2])
+        sys.stderr.write("GEMM families (2 profiled steps): shape IxJxR/epilogue  launches  TFLOP/s  ms total\n")
+        for key, (cnt, f, t) in fam_sorted:
+            sys.stderr.write(f"  {key:32s} {cnt:4d} {f / t / 1e12:8.1f} {t * 1e3:8.3f}\n")
+
+        # ---- batch-1 latency (CUDA-graph replay) and batch-256 throughput of the eval path (config 3)
+        extra = {}
+        try:
+            model.eval()
+            x1 = dev_imgs[0][:1].clone()
+            with torch.no_grad():
+                for _ in range(3):
+                    model(x1)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    y1 = model(x1)
+                lat = []
+                for _ in range(300):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); graph.replay(); e1.record(); e1.synchronize()
+                    lat.append(e0.elapsed_time(e1))
+                lat.sort()
+                extra["bs1_latency_ms_p50"] = lat[len(lat) // 2]
+                extra["bs1_latency_ms_p99"] = lat[int(len(lat) * 0.99)]
+                x256 = torch.randn(256, 3, 224, 224, device=dev)
+                for _ in range(2):
+                    model(x256)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    model(x256)
+                e1.record(); torch.cuda.synchronize()
+                extra["bs256_infer_img_s"] = 256 * 5 / (e0.elapsed_time(e1) / 1e3)
+            model.train()
+        except Exception as e:  # noqa: BLE001 -- extras never invalidate the headline line
+            extra["eval_extra_error"] = repr(e)
+
+        per_gpu = value / world
+        extra.update({
+            "tflops_per_gpu": per_gpu * TRAIN_FLOP_PER_IMG / 1e12,
+            "mfu_vs_measured_sustained": per_gpu * TRAIN_FLOP_PER_IMG / 1e12 / peaks["bf16_tflops_sustained"],
+            "mfu_vs_measured_burst": per_gpu * TRAIN_FLOP_PER_IMG / 1e12 / peaks["bf16_tflops"],
+            "mfu_vs_spec_2250": per_gpu * TRAIN_FLOP_PER_IMG / 1e12 / 2250.0,
+        })
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_steps(steps=3, warmup=1, budget_s=60.0)
+            cpu = {"value": r["img_s"], "unit": "img/s", "cores": r["cores"], "kind": "port",
+                   "sample": f"{r['steps_timed']} timed steps of batch {r['batch']} (BASELINE configs[0]: fwd+focal+bwd+clip+Adam, fp32)"}
+
+        line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": train_config(world), "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "extra": extra}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch ourselves under torchrun
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__), "--gpus", str(args.gpus),
+               "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

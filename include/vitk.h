@@ -218,6 +218,13 @@ int vitk_model_num_bwd_stages(int depth);
 /* debug knobs of the tcgen05 engine (tests only): key 0 = swap LBO/SBO of MN-major operands,
  * key 1 = force split-K count, key 2 = force BLOCK_N (128) */
 int vitk_debug_set(int key, int value);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long vitk_launch_count(void);
+/* per-launch GEMM timing with CUDA events on the launching stream (bench.py's live roofline):
+ * enable(1) clears and starts recording, read() synchronises and returns up to `max` records:
+ * ms[i] and info[5*i..5*i+4] = I, J, R (C[I][J] += over R), epilogue mode, engine. */
+int vitk_prof_enable(int on);
+int vitk_prof_read(float* ms, int* info, int max);
 
 #ifdef __cplusplus
 }

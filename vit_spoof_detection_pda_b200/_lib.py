@@ -60,6 +60,9 @@ PROTOTYPES = {
     "vitk_model_bwd_stage": (i32, [C.POINTER(VitkModel), i32, vp]),
     "vitk_model_num_bwd_stages": (i32, [i32]),
     "vitk_debug_set": (i32, [i32, i32]),
+    "vitk_launch_count": (C.c_longlong, []),
+    "vitk_prof_enable": (i32, [i32]),
+    "vitk_prof_read": (i32, [C.POINTER(C.c_float), C.POINTER(i32), i32]),
 }
 
 _lib = None

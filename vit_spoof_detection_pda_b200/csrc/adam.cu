@@ -53,7 +53,7 @@ sumsq_final_kernel(const float* __restrict__ partial, int nparts, float* __restr
 }
 
 struct AdamArgs {
-  float lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, decay, grad_mult, max_norm;
+  float lr, beta1, beta2, omb1, omb2, eps, wd, step_size, bc2_sqrt, decay, grad_mult, max_norm;
   int mode;
 };
 
@@ -61,8 +61,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   g *= gm;
   if (a.mode == 1) p *= a.decay;
   else if (a.wd != 0.f) g = fmaf(a.wd, p, g);
-  m = m + (g - m) * (1.0f - a.beta1);
-  v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+  m = m + (g - m) * a.omb1;
+  v = fmaf(a.omb2, g * g, v * a.beta2);  // addcmul_(g, g, value = 1-b2): value is rounded from double
   const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
   p = p - a.step_size * (m / denom);
 }
@@ -151,6 +151,7 @@ extern "C" int vitk_adam_step(float* p, const float* g, float* m, float* v, void
   AdamArgs a;
   a.lr = (float)lr; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps; a.wd = (float)weight_decay;
   a.mode = mode;
+  a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
   a.grad_mult = grad_mult; a.max_norm = max_norm;
   // python-double scalar math, as torch does for the non-capturable path
   const double bc1 = 1.0 - pow(beta1, (double)step);

@@ -1,5 +1,6 @@
 // libvitk: version, error reporting, device query.
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -12,6 +13,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(); }
 int sm_count() {
   static int cached = 0;
   if (cached) return cached;
@@ -25,6 +29,7 @@ int sm_count() {
 
 extern "C" {
 int vitk_version(void) { return VITK_VERSION; }
+long long vitk_launch_count(void) { return vitk::launches(); }
 const char* vitk_last_error_string(void) { return vitk::g_err; }
 int vitk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

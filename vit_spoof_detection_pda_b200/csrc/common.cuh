@@ -16,6 +16,7 @@ namespace vitk {
 typedef __nv_bfloat16 bf16;
 
 void set_error(const char* fmt, ...);
+void count_launch();
 int sm_count();
 int default_engine();  // process-wide GEMM/attention engine (VITK_ENGINE_*)
 
@@ -36,7 +37,12 @@ int default_engine();  // process-wide GEMM/attention engine (VITK_ENGINE_*)
     }                                                                                          \
   } while (0)
 
-#define VITK_LAUNCH_CHECK() VITK_CUDA(cudaPeekAtLastError())
+// every kernel launch in the library goes through this macro: it also counts launches (bench.py "gpu_launches")
+#define VITK_LAUNCH_CHECK()                 \
+  do {                                      \
+    vitk::count_launch();                   \
+    VITK_CUDA(cudaPeekAtLastError());       \
+  } while (0)
 
 #define VITK_TRY(expr)          \
   do {                          \
@@ -67,6 +73,31 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
   return cdf + x * pdf;
+}
+
+// Fast GELU / GELU' for the bf16 tensor-core epilogues (outputs are rounded to bf16, rel. step 2^-8):
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), one MUFU.EX2 + one MUFU.RCP per element; the
+// same exponential e^{-x^2/2} serves erf(x/sqrt2) and the normal pdf.  The fp32-validate path keeps erff.
+__device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  e = __expf(-z * z);  // = exp(-x^2/2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, e;
+  gelu_fast_parts(x, cdf, e);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  float cdf, e;
+  gelu_fast_parts(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

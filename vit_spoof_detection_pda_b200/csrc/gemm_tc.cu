@@ -2,11 +2,12 @@
 //
 //   C[i][j] = sum_r A(i,r) * B(j,r)  + fused epilogue (gemm.cuh)
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM, 320 threads:
 //   warp 0        TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier expect_tx)
 //   warp 1        MMA issuer     (one elected lane: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16,
 //                                 accumulators double-buffered in TMEM; tcgen05.commit -> mbarriers)
-//   warps 2..5    epilogue       (tcgen05.ld 32x32b -> registers -> bias/GELU/residual/scatter -> global)
+//   warps 2..9    epilogue       (tcgen05.ld 32x32b -> registers -> swizzled smem transpose -> coalesced
+//                                 bias/GELU/residual/scatter global IO; two warps per TMEM lane quarter)
 // Both operands may be K-major (reduction index contiguous: forward X W^T) or MN-major (row index
 // contiguous: dgrad's W, wgrad's dY^T and X) -- the major-ness is a bit in the instruction descriptor
 // plus the canonical 128B-swizzle shared-memory layout the TMA boxes are written in -- and may be stored
@@ -23,7 +24,8 @@ namespace vitk {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;              // 64 bf16 = 128 B = one swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;            // two warps per TMEM lane quarter, interleaved over 32-column chunks
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_EPI_WARP0 = 2;
 constexpr uint32_t TC_A_STAGE_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 
@@ -108,106 +110,62 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // ------------------------------------------------------------------------------------------------
-// vectorised epilogue: one thread owns row i, 32 consecutive columns j0..j0+31
+// epilogue on 4 consecutive columns (j..j+3) of row i.  The accumulator chunk is transposed through a
+// small swizzled shared-memory buffer first, so that 8 consecutive lanes cover 32 consecutive columns of
+// ONE row: every global load/store below is a fully used 64/128-byte segment (coalesced), instead of the
+// row-per-thread pattern tcgen05.ld hands out.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-    u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-    u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-    u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-    reinterpret_cast<uint4*>(dst)[q] = u;
-  }
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) { return make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)); }
+__device__ __forceinline__ float4 unpack_bf16x4(uint2 u) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
 }
-__device__ __forceinline__ void load_bf16x32(const bf16* src, float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint4 u = reinterpret_cast<const uint4*>(src)[q];
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    v[q * 8 + 0] = a.x; v[q * 8 + 1] = a.y; v[q * 8 + 2] = b.x; v[q * 8 + 3] = b.y;
-    v[q * 8 + 4] = c.x; v[q * 8 + 5] = c.y; v[q * 8 + 6] = d.x; v[q * 8 + 7] = d.y;
-  }
-}
-__device__ __forceinline__ void add_bias32(const float* __restrict__ bias, float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
-    v[q * 4 + 0] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
-  }
-}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-__device__ __forceinline__ void epilogue_row32(const EpiParams& ep, int i, int j0, float (&v)[32]) {
+__device__ __forceinline__ void epilogue_quad(const EpiParams& ep, int i, int j, float4 v) {
   switch (ep.mode) {
     case E_STORE: {
-      if (ep.bias) add_bias32(ep.bias + j0, v);
-      if (ep.out_dtype == VITK_BF16) {
-        store_bf16x32(reinterpret_cast<bf16*>(ep.out) + (int64_t)i * ep.ldc + j0, v);
-      } else {
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-      }
+      if (ep.bias) v = f4_add(v, __ldg(reinterpret_cast<const float4*>(ep.bias + j)));
+      const int64_t o = (int64_t)i * ep.ldc + j;
+      if (ep.out_dtype == VITK_BF16) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) = pack_bf16x4(v);
+      else *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o) = v;
     } break;
     case E_BIAS_GELU: {
-      add_bias32(ep.bias + j0, v);
-      const int64_t o = (int64_t)i * ep.ldc + j0;
-      if (ep.aux) store_bf16x32(reinterpret_cast<bf16*>(ep.aux) + o, v);
-#pragma unroll
-      for (int q = 0; q < 32; ++q) v[q] = gelu_erf(__bfloat162float(__float2bfloat16_rn(v[q])));
-      store_bf16x32(reinterpret_cast<bf16*>(ep.out) + o, v);
+      v = f4_add(v, __ldg(reinterpret_cast<const float4*>(ep.bias + j)));
+      const int64_t o = (int64_t)i * ep.ldc + j;
+      const uint2 u16 = pack_bf16x4(v);
+      if (ep.aux) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.aux) + o) = u16;
+      const float4 ur = unpack_bf16x4(u16);  // GELU acts on the 16-bit fc1 output (autocast semantics)
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) =
+          pack_bf16x4(make_float4(gelu_fast(ur.x), gelu_fast(ur.y), gelu_fast(ur.z), gelu_fast(ur.w)));
     } break;
     case E_BIAS_RESIDUAL: {
-      add_bias32(ep.bias + j0, v);
-      const int64_t o = (int64_t)i * ep.ldc + j0;
-      const float4* r = reinterpret_cast<const float4*>(ep.residual + o);
-      float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 rv = r[q];
-        d[q] = make_float4(rv.x + v[q * 4], rv.y + v[q * 4 + 1], rv.z + v[q * 4 + 2], rv.w + v[q * 4 + 3]);
-      }
+      v = f4_add(v, __ldg(reinterpret_cast<const float4*>(ep.bias + j)));
+      const int64_t o = (int64_t)i * ep.ldc + j;
+      const float4 r = *reinterpret_cast<const float4*>(ep.residual + o);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o) = f4_add(r, v);
     } break;
     case E_QKV_SCATTER: {
-      add_bias32(ep.bias + j0, v);
-      const int64_t o = (int64_t)(j0 >> 6) * ep.hm_rows * 64 + (int64_t)i * 64 + (j0 & 63);
-      store_bf16x32(reinterpret_cast<bf16*>(ep.out) + o, v);
+      v = f4_add(v, __ldg(reinterpret_cast<const float4*>(ep.bias + j)));
+      const int64_t o = (int64_t)(j >> 6) * ep.hm_rows * 64 + (int64_t)i * 64 + (j & 63);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) = pack_bf16x4(v);
     } break;
     case E_GELU_BWD: {
-      const int64_t o = (int64_t)i * ep.ldc + j0;
-      float u[32];
-      load_bf16x32(reinterpret_cast<const bf16*>(ep.aux) + o, u);
-#pragma unroll
-      for (int q = 0; q < 32; ++q) v[q] *= gelu_erf_grad(u[q]);
-      store_bf16x32(reinterpret_cast<bf16*>(ep.out) + o, v);
+      const int64_t o = (int64_t)i * ep.ldc + j;
+      const float4 u = unpack_bf16x4(*reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + o));
+      v.x *= gelu_fast_grad(u.x); v.y *= gelu_fast_grad(u.y); v.z *= gelu_fast_grad(u.z); v.w *= gelu_fast_grad(u.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) = pack_bf16x4(v);
     } break;
     case E_ACCUM: {
-      float* d = reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + q * 4), "f"(v[q * 4]), "f"(v[q * 4 + 1]),
-                     "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3]) : "memory");
+      float* d = reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
     } break;
     case E_PATCH: {
       const int t = i % VITK_NTOK;
-      const float4* pe = reinterpret_cast<const float4*>(ep.residual + (int64_t)t * ep.ldc + j0);
-      float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j0);
-      if (t == 0) {
-        const float4* c = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.aux) + j0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 a = c[q], p = pe[q];
-          d[q] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
-        }
-      } else {
-        add_bias32(ep.bias + j0, v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 p = pe[q];
-          d[q] = make_float4(v[q * 4] + p.x, v[q * 4 + 1] + p.y, v[q * 4 + 2] + p.z, v[q * 4 + 3] + p.w);
-        }
-      }
+      const float4 pe = __ldg(reinterpret_cast<const float4*>(ep.residual + (int64_t)t * ep.ldc + j));
+      if (t == 0) v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.aux) + j));
+      else v = f4_add(v, __ldg(reinterpret_cast<const float4*>(ep.bias + j)));
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j) = f4_add(v, pe);
     } break;
     default: break;
   }
@@ -221,7 +179,8 @@ template <int BN> struct TcCfg {
   static constexpr uint32_t STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (256 or 512: powers of two)
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+  static constexpr uint32_t EPI_OFF = STAGES * STAGE_BYTES + 256;  // TC_EPI_WARPS x 4 KB transpose buffers after the barriers
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)EPI_OFF + TC_EPI_WARPS * 4096;
 };
 
 __device__ __forceinline__ void tc_issue_operand_loads(const CUtensorMap* map, int mode, uint32_t dst, uint32_t bar,
@@ -264,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -335,6 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int half = (warp - TC_EPI_WARP0) >> 2;  // which interleaved set of column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -342,18 +302,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int i0 = (tile / p.n_tiles_n) * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int i = i0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const uint32_t tbuf = smem_base + Cfg::EPI_OFF + (uint32_t)(warp - TC_EPI_WARP0) * 4096u;
+      const int sub_row = lane >> 3, c4 = lane & 7;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
         uint32_t raw[32];
         tc_ld32(taddr + c * 32, raw);
-        if (i < p.I) {
-          float v[32];
+        // row `lane` of the 32x32 chunk -> swizzled smem (16-byte column group cg at cg ^ (row & 7))
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
-          epilogue_row32(p.ep, i, j0 + c * 32, v);
+        for (int cg = 0; cg < 8; ++cg)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbuf + lane * 128 + ((cg ^ (lane & 7)) << 4)),
+                       "r"(raw[cg * 4]), "r"(raw[cg * 4 + 1]), "r"(raw[cg * 4 + 2]), "r"(raw[cg * 4 + 3]) : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + sub_row;
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                       : "r"(tbuf + r * 128 + ((c4 ^ (r & 7)) << 4)));
+          const int i = i0 + q * 32 + r;
+          if (i < p.I) epilogue_quad(p.ep, i, j0 + c * 32 + c4 * 4, v);
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

@@ -76,21 +76,26 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __rest
   }
 }
 
-// Persistent over rows; per-lane register partials of dgamma/dbeta, one [2][768] partial per CTA.
+// Persistent over rows.  dgamma/dbeta partials live in per-warp shared-memory accumulators (only the owning
+// warp touches its slice, so no synchronisation until the end) instead of 48 registers per lane: the kernel
+// then fits 2 co-resident CTAs (16 warps, ~9 KB of loads in flight per warp) per SM in one persistent wave.
+// Final cross-warp sum -> one fp32 atomicAdd per column per CTA into dgamma/dbeta.
+constexpr int LN_BWD_SMEM = LN_WARPS * 2 * LN_COLS * (int)sizeof(float);  // 48 KB
+
 template <typename T>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_stride,
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* dres, float* dx, bf16* __restrict__ dx16,  // dres may alias dx (in-place residual-grad update)
-              float* __restrict__ partial, int rows) {
-  __shared__ float red[LN_WARPS][LN_COLS];
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows) {
+  extern __shared__ float ln_acc[];  // [warp][2][768]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 g[LN_VEC], dg[LN_VEC], db[LN_VEC];
+  float* acc_g = ln_acc + (size_t)warp * 2 * LN_COLS;
+  float* acc_b = acc_g + LN_COLS;
 #pragma unroll
   for (int i = 0; i < LN_VEC; ++i) {
-    g[i] = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
-    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(acc_g + (i * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(acc_b + (i * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
     const float* xr = x + (int64_t)row * x_stride;
@@ -103,12 +108,16 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_s
       const int c = (i * 32 + lane) * 4;
       const float4 xv = *reinterpret_cast<const float4*>(xr + c);
       const float4 d = Vec4IO<T>::load(dyr + c);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      gy[i] = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+      gy[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
       s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
       s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
-      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
-      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      float4 ag = *reinterpret_cast<float4*>(acc_g + c), ab = *reinterpret_cast<float4*>(acc_b + c);
+      ag.x += d.x * xh[i].x; ag.y += d.y * xh[i].y; ag.z += d.z * xh[i].z; ag.w += d.w * xh[i].w;
+      ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+      *reinterpret_cast<float4*>(acc_g + c) = ag;
+      *reinterpret_cast<float4*>(acc_b + c) = ab;
     }
     const float c1 = warp_sum(s1) * (1.0f / LN_COLS);
     const float c2 = warp_sum(s2) * (1.0f / LN_COLS);
@@ -128,32 +137,16 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_s
       if (dx16) Vec4IO<bf16>::store(dx16 + (int64_t)row * LN_COLS + c, o);
     }
   }
-  // CTA reduction of the per-warp partials: dgamma then dbeta
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < LN_VEC; ++i)
-      *reinterpret_cast<float4*>(&red[warp][(i * 32 + lane) * 4]) = pass == 0 ? dg[i] : db[i];
-    __syncthreads();
-    for (int c = threadIdx.x; c < LN_COLS; c += LN_WARPS * 32) {
+  __syncthreads();
+  if (dgamma || dbeta) {
+    for (int c = threadIdx.x; c < 2 * LN_COLS; c += LN_WARPS * 32) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
-      partial[((int64_t)blockIdx.x * 2 + pass) * LN_COLS + c] = s;
+      for (int w = 0; w < LN_WARPS; ++w) s += ln_acc[(size_t)w * 2 * LN_COLS + c];
+      float* dst = c < LN_COLS ? dgamma : dbeta;
+      if (dst) atomicAdd(dst + (c % LN_COLS), s);
     }
   }
-}
-
-__global__ void ln_bwd_reduce_kernel(const float* __restrict__ partial, int nparts,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2*768
-  if (c >= 2 * LN_COLS) return;
-  const int pass = c / LN_COLS, col = c % LN_COLS;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[((int64_t)p * 2 + pass) * LN_COLS + col];
-  float* dst = pass == 0 ? dgamma : dbeta;
-  if (dst) dst[col] += s;
 }
 
 }  // namespace vitk
@@ -185,25 +178,28 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, 
                                   const float* gamma, const float* mean, const float* rstd, const float* dres,
                                   float* dx, void* dx16, float* dgamma, float* dbeta, float* partial, int rows,
                                   void* stream) {
-  VITK_CHECK_ARG(dy && x && gamma && mean && rstd && dx && partial && rows >= 0);
+  (void)partial;  // kept in the ABI; the reduction now finishes with per-CTA atomics
+  VITK_CHECK_ARG(dy && x && gamma && mean && rstd && dx && rows >= 0);
   VITK_CHECK_ARG(x_stride % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)dx % 16) == 0);
   if (rows == 0) return VITK_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {
+    VITK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_BWD_SMEM));
+    VITK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_BWD_SMEM));
+    configured = true;
+  }
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  const int cap = sm_count() * 2 < LN_BWD_MAX_CTAS ? sm_count() * 2 : LN_BWD_MAX_CTAS;
+  const int cap = sm_count() * 2;  // 2 CTAs per SM are co-resident (launch bounds): one persistent wave
   if (grid > cap) grid = cap;
   if (dy_dtype == VITK_F32)
-    ln_bwd_kernel<float><<<grid, LN_WARPS * 32, 0, st>>>((const float*)dy, x, x_stride, gamma, mean, rstd, dres, dx,
-                                                        (bf16*)dx16, partial, rows);
+    ln_bwd_kernel<float><<<grid, LN_WARPS * 32, LN_BWD_SMEM, st>>>((const float*)dy, x, x_stride, gamma, mean, rstd, dres,
+                                                                  dx, (bf16*)dx16, dgamma, dbeta, rows);
   else if (dy_dtype == VITK_BF16)
-    ln_bwd_kernel<bf16><<<grid, LN_WARPS * 32, 0, st>>>((const bf16*)dy, x, x_stride, gamma, mean, rstd, dres, dx,
-                                                       (bf16*)dx16, partial, rows);
+    ln_bwd_kernel<bf16><<<grid, LN_WARPS * 32, LN_BWD_SMEM, st>>>((const bf16*)dy, x, x_stride, gamma, mean, rstd, dres,
+                                                                 dx, (bf16*)dx16, dgamma, dbeta, rows);
   else
     VITK_CHECK_ARG(!"bad dtype");
   VITK_LAUNCH_CHECK();
-  if (dgamma || dbeta) {
-    ln_bwd_reduce_kernel<<<(2 * LN_COLS + 255) / 256, 256, 0, st>>>(partial, grid, dgamma, dbeta);
-    VITK_LAUNCH_CHECK();
-  }
   return VITK_OK;
 }

@@ -3,6 +3,8 @@
 // Reference call sites: timm Attention.qkv / .proj, Mlp.fc1 / .fc2 and PatchEmbed.proj reached from
 // /root/reference/train_advanced.py:203 (self.vit(x)); backward from loss.backward() at :330.
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "gemm.cuh"
 
@@ -11,12 +13,34 @@ namespace vitk {
 static std::atomic<int> g_engine{VITK_ENGINE_AUTO};
 int default_engine() { return g_engine.load(); }
 
+// ---- optional per-launch GEMM timing (bench.py's live roofline measurement) ----------------------
+// When enabled, every GEMM launch is bracketed by CUDA events on the launching stream; the list of
+// (I, J, R, epilogue, engine, ms) is read back after a synchronize.  Off by default (no events recorded).
+struct ProfRec { cudaEvent_t e0, e1; int I, J, R, mode, engine; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+static int run_gemm_impl(const GemmProblem& p, int engine, int simt_splits, cudaStream_t st) {
+  if (engine == VITK_ENGINE_TCGEN05) return gemm_tc(p, st);
+  return gemm_simt(p, simt_splits, st);
+}
+
 static int run_gemm(const GemmProblem& p, int engine, int simt_splits, cudaStream_t st) {
   if (engine == VITK_ENGINE_AUTO) engine = default_engine();
   if (p.in_dtype == VITK_F32) engine = VITK_ENGINE_SIMT;  // fp32 products only exist on the FFMA pipe
   if (engine == VITK_ENGINE_AUTO) engine = VITK_ENGINE_TCGEN05;
-  if (engine == VITK_ENGINE_TCGEN05) return gemm_tc(p, st);
-  return gemm_simt(p, simt_splits, st);
+  if (!g_prof_on.load()) return run_gemm_impl(p, engine, simt_splits, st);
+  ProfRec r{};
+  r.I = p.I; r.J = p.J; r.R = p.R; r.mode = p.ep.mode; r.engine = engine;
+  VITK_CUDA(cudaEventCreate(&r.e0));
+  VITK_CUDA(cudaEventCreate(&r.e1));
+  VITK_CUDA(cudaEventRecord(r.e0, st));
+  const int rc = run_gemm_impl(p, engine, simt_splits, st);
+  VITK_CUDA(cudaEventRecord(r.e1, st));
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  return rc;
 }
 
 // db[c] += sum_m dy(m, c)      (bias gradient; dy row-major [M][C] or head-major)
@@ -39,7 +63,58 @@ colsum_kernel(const T* __restrict__ dy, MatLayout l, int M, int C, int rows_per_
   }
 }
 
+// bf16 fast path: every thread owns 8 consecutive columns (one 16-byte load per row), CHUNKS threads cover a
+// row slab of 8*CHUNKS columns, 256/CHUNKS rows are in flight per iteration -> fully coalesced, HBM-bound.
+// Matrix is [M][ld] with the slab starting at column blockIdx.x*8*CHUNKS; blockIdx.z selects a [M][64] head
+// block (head-major storage, block stride M*64).
+template <int CHUNKS>
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const bf16* __restrict__ dy, int64_t ld, int64_t blk_stride, int M, int rows_per_block,
+                   float* __restrict__ db, int db_blk_stride) {
+  constexpr int RL = 256 / CHUNKS;
+  __shared__ float red[RL][CHUNKS * 8 + 1];
+  const int ch = threadIdx.x % CHUNKS, rl = threadIdx.x / CHUNKS;
+  const bf16* base = dy + (int64_t)blockIdx.z * blk_stride + (int64_t)blockIdx.x * (8 * CHUNKS) + ch * 8;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int m = m0 + rl; m < m1; m += RL) {
+    const uint4 u = *reinterpret_cast<const uint4*>(base + (int64_t)m * ld);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rl][ch * 8 + e] = acc[e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < CHUNKS * 8; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < RL; ++r) s += red[r][c];
+    atomicAdd(db + blockIdx.z * db_blk_stride + blockIdx.x * (8 * CHUNKS) + c, s);
+  }
+}
+
 static int colsum(const void* dy, int dtype, MatLayout l, int M, int C, float* db, cudaStream_t st) {
+  if (dtype == VITK_BF16 && C % 64 == 0) {
+    const int sms = sm_count();
+    if (l.split == 2) {  // head-major: C/64 blocks of [M][64]
+      const int nblk = C / 64;
+      int rows_per_block = (M + (4 * sms / nblk)) / (4 * sms / nblk + 1);
+      if (rows_per_block < 64) rows_per_block = 64;
+      dim3 grid(1, (M + rows_per_block - 1) / rows_per_block, nblk);
+      colsum_bf16_kernel<8><<<grid, 256, 0, st>>>((const bf16*)dy, 64, l.s_blk, M, rows_per_block, db, 64);
+      VITK_LAUNCH_CHECK();
+      return VITK_OK;
+    }
+    if (l.split == 0 && l.s_col == 1 && C % 256 == 0) {
+      const int slabs = C / 256;
+      int rows_per_block = (M + (4 * sms / slabs)) / (4 * sms / slabs + 1);
+      if (rows_per_block < 64) rows_per_block = 64;
+      dim3 grid(slabs, (M + rows_per_block - 1) / rows_per_block, 1);
+      colsum_bf16_kernel<32><<<grid, 256, 0, st>>>((const bf16*)dy, l.s_row, 0, M, rows_per_block, db, 0);
+      VITK_LAUNCH_CHECK();
+      return VITK_OK;
+    }
+  }
   const int rows_per_block = 512;
   dim3 grid((C + 31) / 32, (M + rows_per_block - 1) / rows_per_block);
   if (dtype == VITK_BF16) colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, l, M, C, rows_per_block, db);
@@ -94,6 +169,29 @@ embed_param_grads_kernel(const float* __restrict__ dx0, int batch, float* __rest
 using namespace vitk;
 
 extern "C" int vitk_set_gemm_engine(int engine) { return g_engine.exchange(engine); }
+
+extern "C" int vitk_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  return g_prof_on.exchange(on);
+}
+
+// Synchronises the recorded events and copies up to `max` records: info[5*i..] = I, J, R, epilogue mode, engine.
+extern "C" int vitk_prof_read(float* ms, int* info, int max) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (auto& r : g_prof) {
+    if (n >= max) break;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) break;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) break;
+    ms[n] = t;
+    info[5 * n + 0] = r.I; info[5 * n + 1] = r.J; info[5 * n + 2] = r.R; info[5 * n + 3] = r.mode; info[5 * n + 4] = r.engine;
+    ++n;
+  }
+  return n;
+}
 
 extern "C" int vitk_linear_fwd(const void* x, int x_layout, const void* w, const float* bias, void* y, void* aux,
                                int M, int N, int K, int epilogue, int dtype, int engine, void* stream) {

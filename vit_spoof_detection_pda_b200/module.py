@@ -145,6 +145,8 @@ class ViTFaceAntiSpoofing(nn.Module):
         self._finish_hook = None   # set by DataParallel: fn() before gradients are handed to autograd
         self._pending_clip = None  # (sumsq tensor, max_norm) left by clip_grad_norm_ for FusedAdam
         self.last_masks = None
+        for p in self.parameters():
+            p._vitk_owner = weakref.ref(self)
 
     # ------------------------------------------------------------------ flat storage management
     def _param_list(self):

@@ -19,8 +19,8 @@ def _owner_of(params):
     ref = getattr(params[0], "_vitk_owner", None)
     owner = ref() if ref is not None else None
     if owner is None:
-        raise RuntimeError("parameters do not belong to a CUDA-resident vitk ViTFaceAntiSpoofing "
-                           "(move the model to CUDA before constructing the optimizer)")
+        raise RuntimeError("parameters do not belong to a vitk ViTFaceAntiSpoofing module")
+    owner._ensure_flat()   # raises with a clear message when the model is not on CUDA yet
     return owner, params
 
 
