@@ -51,7 +51,7 @@ enum { VITK_PREC_FP32_VALIDATE = 0, VITK_PREC_BF16 = 1 };
 /* epilogues of the Linear forward (replaces cuBLASLt + ATen add/gelu call sites K4,K6,K7,K8) */
 enum {
   VITK_EPI_BIAS = 0,          /* y = x W^T + b                                 (out: act dtype)          */
-  VITK_EPI_BIAS_GELU = 1,     /* u = x W^T + b ; g = gelu_erf(u)               (out: u and g, act dtype) */
+  VITK_EPI_BIAS_GELU = 1,     /* u = x W^T + b ; y = gelu_erf(u) ; aux = gelu_erf'(u)   (both act dtype)   */
   VITK_EPI_BIAS_RESIDUAL = 2, /* y = res + x W^T + b                           (res, out: fp32)          */
   VITK_EPI_QKV_SCATTER = 3    /* y = x W^T + b written head-major [36][M][64]  (out: act dtype)          */
 };
@@ -89,16 +89,16 @@ size_t vitk_layernorm_bwd_scratch_floats(void);
 
 /* ---------------------------------------------------------------------------------------------
  * nn.Linear forward / backward (timm Attention.qkv, Attention.proj, Mlp.fc1, Mlp.fc2).
- *   fwd   : Y[M,N]  = X[M,K] W[N,K]^T + b, epilogue as above.   `aux` = u (pre-GELU) for BIAS_GELU,
- *           residual (fp32) for BIAS_RESIDUAL.
- *   dgrad : dX[M,K] = dY[M,N] W[N,K]   ; if gelu_u != NULL: dX *= gelu'(gelu_u)  (dX, gelu_u: [M,K])
+ *   fwd   : Y[M,N]  = X[M,K] W[N,K]^T + b, epilogue as above.   `aux` = gelu'(u) output for BIAS_GELU (saved
+ *           for backward instead of the pre-activation; may be NULL in eval), residual (fp32) for BIAS_RESIDUAL.
+ *   dgrad : dX[M,K] = dY[M,N] W[N,K]   ; if gelu_grad != NULL: dX *= gelu_grad  (the aux of the forward; [M,K])
  *   wgrad : dW[N,K] += dY[M,N]^T X[M,K]; db[N] += colsum(dY)   (dW, db fp32; += so autograd-style
  *           accumulation and split-K share one code path; caller zeroes the gradient buffer)
  * X/dY/W are `dtype` (VITK_F32 for FP32_VALIDATE, VITK_BF16 otherwise; W then is the bf16 shadow).
  * ------------------------------------------------------------------------------------------- */
 int vitk_linear_fwd(const void* x, int x_layout, const void* w, const float* bias, void* y, void* aux,
                     int M, int N, int K, int epilogue, int dtype, int engine, void* stream);
-int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, const void* gelu_u,
+int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, const void* gelu_grad,
                       int M, int N, int K, int dtype, int engine, void* stream);
 int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, float* dw, float* db,
                       int M, int N, int K, int dtype, int engine, void* stream);
@@ -216,7 +216,7 @@ int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream);
 int vitk_model_num_bwd_stages(int depth);
 
 /* debug knobs of the tcgen05 engine (tests only): key 0 = swap LBO/SBO of MN-major operands,
- * key 1 = force split-K count, key 2 = force BLOCK_N (128) */
+ * key 1 = 1 disables stream-K for accumulate (wgrad) GEMMs, key 2 = force BLOCK_N (128/192/256) */
 int vitk_debug_set(int key, int value);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long vitk_launch_count(void);

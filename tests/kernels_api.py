@@ -58,11 +58,11 @@ def linear_fwd(x, w, bias, epilogue, engine, x_layout=L.LAYOUT_ROWMAJOR, residua
     return (y, aux) if epilogue == L.EPI_BIAS_GELU else y
 
 
-def linear_dgrad(dy, w, engine, dy_layout=L.LAYOUT_ROWMAJOR, gelu_u=None):
+def linear_dgrad(dy, w, engine, dy_layout=L.LAYOUT_ROWMAJOR, gelu_grad=None):
     N, K = w.shape
     M = dy.shape[0] if dy_layout == L.LAYOUT_ROWMAJOR else dy.shape[1]
     dx = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
-    L.call("vitk_linear_dgrad", L.ptr(dy), dy_layout, L.ptr(w), L.ptr(dx), L.ptr(gelu_u), M, N, K, DT[dy.dtype], engine,
+    L.call("vitk_linear_dgrad", L.ptr(dy), dy_layout, L.ptr(w), L.ptr(dx), L.ptr(gelu_grad), M, N, K, DT[dy.dtype], engine,
            L.stream_ptr())
     return dx
 

@@ -91,9 +91,12 @@ def test_linear_fwd_epilogues(case, M, N, Kd):
     for eng in engines:
         y = K.linear_fwd(x, w, b, L.EPI_BIAS, eng)
         assert K.rel_err(y.float(), ref) < _tol(dtype), ("bias", eng)
-        g, u = K.linear_fwd(x, w, b, L.EPI_BIAS_GELU, eng)
-        assert K.rel_err(u.float(), ref) < _tol(dtype), ("gelu-u", eng)
-        assert K.rel_err(g.float(), F.gelu(u.float())) < _tol(dtype), ("gelu-g", eng)
+        g, dg = K.linear_fwd(x, w, b, L.EPI_BIAS_GELU, eng)
+        ur = ref.to(dtype).float().requires_grad_(True)      # GELU acts on the activation-dtype fc1 output
+        gr = F.gelu(ur)
+        gr.sum().backward()
+        assert K.rel_err(g.float(), gr) < _tol(dtype), ("gelu-g", eng)
+        assert K.rel_err(dg.float(), ur.grad) < _tol(dtype), ("gelu-dg", eng)
         y = K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, eng, residual=res)
         assert K.rel_err(y, ref + res) < _tol(dtype), ("residual", eng)
         y = K.linear_fwd(x, w, b, L.EPI_QKV_SCATTER, eng)
@@ -114,8 +117,8 @@ def test_linear_dgrad(case, M, N, Kd):
     for eng in engines:
         dx = K.linear_dgrad(dy, w, eng)
         assert K.rel_err(dx.float(), ref) < _tol(dtype), ("plain", eng)
-        dx = K.linear_dgrad(dy, w, eng, gelu_u=u)
-        assert K.rel_err(dx.float(), ref * uu.grad) < _tol(dtype), ("gelu_bwd", eng)
+        dx = K.linear_dgrad(dy, w, eng, gelu_grad=u)
+        assert K.rel_err(dx.float(), ref * u.float()) < _tol(dtype), ("gelu_bwd", eng)
         if N % 64 == 0:
             dx = K.linear_dgrad(K.to_headmajor(dy), w, eng, dy_layout=L.LAYOUT_HEADMAJOR)
             assert K.rel_err(dx.float(), ref) < _tol(dtype), ("headmajor", eng)
@@ -136,6 +139,30 @@ def test_linear_wgrad(case, M, N, Kd):
         dw, db = K.linear_wgrad(K.to_headmajor(dy), x, N, Kd, eng, dy_layout=L.LAYOUT_HEADMAJOR)
         assert K.rel_err(dw, ref_w) < _tol(dtype), ("headmajor", eng)
         assert K.rel_err(db, ref_b) < _tol(dtype)
+
+
+@pytest.mark.parametrize("bn", [128, 192, 256])
+def test_tcgen05_forced_block_n_and_streamk(bn):
+    """Every BLOCK_N instantiation of the tcgen05 kernel, with and without stream-K (tcgen05 engine only)."""
+    lib = L.load()
+    M, N, Kd = 1576, 768, 768
+    x = randn(M, Kd, seed=91).to(torch.bfloat16)
+    w = randn(N, Kd, seed=92, scale=0.05).to(torch.bfloat16)
+    b = randn(N, seed=93, scale=0.5)
+    dy = randn(M, N, seed=94).to(torch.bfloat16)
+    try:
+        lib.vitk_debug_set(2, bn)
+        y = K.linear_fwd(x, w, b, L.EPI_BIAS, L.ENGINE_TCGEN05)
+        assert K.rel_err(y.float(), x.float() @ w.float().t() + b) < BF16_TOL
+        dx = K.linear_dgrad(dy, w, L.ENGINE_TCGEN05)
+        assert K.rel_err(dx.float(), dy.float() @ w.float()) < BF16_TOL
+        for streamk_off in (0, 1):
+            lib.vitk_debug_set(1, streamk_off)
+            dw, _ = K.linear_wgrad(dy, x, N, Kd, L.ENGINE_TCGEN05)
+            assert K.rel_err(dw, dy.float().t() @ x.float()) < BF16_TOL
+    finally:
+        lib.vitk_debug_set(1, 0)
+        lib.vitk_debug_set(2, 0)
 
 
 # ------------------------------------------------------------------ attention

@@ -5,9 +5,9 @@ Public API mirrors the reference's own objects for this path (/root/reference/tr
 ``torch.optim.AdamW`` (:592-597) and ``torch.nn.utils.clip_grad_norm_`` (:334).
 """
 from . import _lib
-from .dp import DataParallel
+from .dp import DataParallel, DevicePrefetcher
 from .loss import FocalLoss, eval_postprocess
 from .module import ViTFaceAntiSpoofing
 from .optim import FusedAdam, clip_grad_norm_
 
-__all__ = ["ViTFaceAntiSpoofing", "FocalLoss", "FusedAdam", "clip_grad_norm_", "DataParallel", "eval_postprocess", "_lib"]
+__all__ = ["ViTFaceAntiSpoofing", "FocalLoss", "FusedAdam", "clip_grad_norm_", "DataParallel", "DevicePrefetcher", "eval_postprocess", "_lib"]

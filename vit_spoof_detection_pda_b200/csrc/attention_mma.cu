@@ -172,7 +172,7 @@ attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float*
   }
 }
 
-__global__ void __launch_bounds__(AM_THREADS)
+__global__ void __launch_bounds__(AM_THREADS, 2)
 attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
                     const float* __restrict__ lse, bf16* __restrict__ dqkv, int batch) {
   extern __shared__ __align__(1024) uint8_t am_smem[];
@@ -190,17 +190,27 @@ attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, 
   am_stage(sdO, dout + tok, VITK_DIM);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  for (int i = warp; i < AM_NP; i += AM_WARPS) {
-    float dl = 0.f;
+  // delta_i = dO_i . O_i : one thread per row, 16 independent 16-byte loads in flight per thread (a
+  // warp-per-row loop would serialise ~30 dependent global round trips per warp)
+  if (threadIdx.x < AM_NP) {
+    const int i = threadIdx.x;
+    float dl = 0.f, ls = 0.f;
     if (i < AM_N) {
-      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + tok + (int64_t)i * VITK_DIM + 2 * lane));
-      const float2 o = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(out + tok + (int64_t)i * VITK_DIM + 2 * lane));
-      dl = warp_sum(a.x * o.x + a.y * o.y);
+      const uint4* ap = reinterpret_cast<const uint4*>(dout + tok + (int64_t)i * VITK_DIM);
+      const uint4* op = reinterpret_cast<const uint4*>(out + tok + (int64_t)i * VITK_DIM);
+      uint4 av[8], ov[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { av[c] = ap[c]; ov[c] = op[c]; }
+      ls = lse[(int64_t)h * M + (int64_t)b * AM_N + i] * AM_LOG2E;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 a0 = unpack_bf16x2(av[c].x), a1 = unpack_bf16x2(av[c].y), a2 = unpack_bf16x2(av[c].z), a3 = unpack_bf16x2(av[c].w);
+        const float2 o0 = unpack_bf16x2(ov[c].x), o1 = unpack_bf16x2(ov[c].y), o2 = unpack_bf16x2(ov[c].z), o3 = unpack_bf16x2(ov[c].w);
+        dl += a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
+      }
     }
-    if (lane == 0) {
-      Ds[i] = dl;
-      Ls[i] = (i < AM_N) ? lse[(int64_t)h * M + (int64_t)b * AM_N + i] * AM_LOG2E : 0.f;
-    }
+    Ds[i] = dl;
+    Ls[i] = ls;
   }
   cp_async_wait_all();
   __syncthreads();

@@ -75,29 +75,24 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// Fast GELU / GELU' for the bf16 tensor-core epilogues (outputs are rounded to bf16, rel. step 2^-8):
-// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), one MUFU.EX2 + one MUFU.RCP per element; the
-// same exponential e^{-x^2/2} serves erf(x/sqrt2) and the normal pdf.  The fp32-validate path keeps erff.
-__device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& e) {
+// Fast GELU and GELU' together for the bf16 tensor-core epilogue (outputs are rounded to bf16, rel. step 2^-8):
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) with one MUFU.EX2 + one MUFU.RCP per element; the same
+// exponential e^{-x^2/2} serves erf(x/sqrt2) and the normal pdf.  ~17 instructions for both outputs.
+// The fp32-validate path keeps erff / expf.
+__device__ __forceinline__ void gelu_fast_both(float x, float& g, float& dg) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  e = __expf(-z * z);  // = exp(-x^2/2)
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));  // exp(-x^2/2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   const float erf_abs = fmaf(-poly * t, e, 1.0f);
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
-}
-__device__ __forceinline__ float gelu_fast(float x) {
-  float cdf, e;
-  gelu_fast_parts(x, cdf, e);
-  return x * cdf;
-}
-__device__ __forceinline__ float gelu_fast_grad(float x) {
-  float cdf, e;
-  gelu_fast_parts(x, cdf, e);
-  return fmaf(x * 0.39894228040143267794f, e, cdf);
+  const float cdf = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

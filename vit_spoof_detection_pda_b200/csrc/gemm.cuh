@@ -28,10 +28,10 @@ static inline MatLayout layout_headmajor_rows_c(int64_t M) { return MatLayout{1,
 
 enum EpiMode {
   E_STORE = 0,          // out[i][j] = acc (+ bias[j])                       out_dtype, row-major ldc
-  E_BIAS_GELU = 1,      // u = acc + bias[j]; aux = u; out = gelu(u)         out_dtype
+  E_BIAS_GELU = 1,      // u = acc + bias[j]; out = gelu(u); aux = gelu'(u)  out_dtype (aux kept for backward)
   E_BIAS_RESIDUAL = 2,  // out = residual[i][j] + acc + bias[j]             fp32
   E_QKV_SCATTER = 3,    // out_hm(i, j) = acc + bias[j]                      out_dtype, head-major
-  E_GELU_BWD = 4,       // out = acc * gelu'(aux[i][j])                      out_dtype
+  E_GELU_BWD = 4,       // out = acc * aux[i][j]   (aux = gelu'(u) saved by forward) out_dtype
   E_ACCUM = 5,          // atomicAdd(out_f32[i][j], acc)
   E_PATCH = 6           // rows are tokens (b*197+t): out_f32[i][j] = (t ? acc + bias[j] : cls[j]) + pos[t][j]  (aux = cls)
 };
@@ -40,7 +40,7 @@ struct EpiParams {
   int32_t mode;
   int32_t out_dtype;      // VITK_F32 / VITK_BF16
   void* out;
-  void* aux;              // u out (E_BIAS_GELU) / u in (E_GELU_BWD), same dtype+layout as out
+  void* aux;              // gelu'(u) out (E_BIAS_GELU) / in (E_GELU_BWD), same dtype+layout as out; cls (E_PATCH)
   const float* bias;      // [J] or nullptr
   const float* residual;  // fp32 [I][ldc] (E_BIAS_RESIDUAL) / pos_embed (E_PATCH)
   int64_t ldc;            // row stride of out / aux / residual (row-major modes)
@@ -72,10 +72,10 @@ __device__ __forceinline__ void epilogue_scalar(const EpiParams& ep, int i, int 
       store_as<TO>(ep.out, (int64_t)i * ep.ldc + j, acc);
     } break;
     case E_BIAS_GELU: {
-      const float u = acc + ep.bias[j];
-      if (ep.aux) store_as<TO>(ep.aux, (int64_t)i * ep.ldc + j, u);
       // the reference applies GELU to the 16-bit fc1 output under autocast: round first
-      store_as<TO>(ep.out, (int64_t)i * ep.ldc + j, gelu_erf(to_f32(from_f32<TO>(u))));
+      const float u = to_f32(from_f32<TO>(acc + ep.bias[j]));
+      if (ep.aux) store_as<TO>(ep.aux, (int64_t)i * ep.ldc + j, gelu_erf_grad(u));
+      store_as<TO>(ep.out, (int64_t)i * ep.ldc + j, gelu_erf(u));
     } break;
     case E_BIAS_RESIDUAL: {
       const int64_t o = (int64_t)i * ep.ldc + j;
@@ -87,7 +87,7 @@ __device__ __forceinline__ void epilogue_scalar(const EpiParams& ep, int i, int 
     } break;
     case E_GELU_BWD: {
       const int64_t o = (int64_t)i * ep.ldc + j;
-      store_as<TO>(ep.out, o, acc * gelu_erf_grad(load_as<TO>(ep.aux, o)));
+      store_as<TO>(ep.out, o, acc * load_as<TO>(ep.aux, o));
     } break;
     case E_ACCUM: {
       atomicAdd(reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j, acc);

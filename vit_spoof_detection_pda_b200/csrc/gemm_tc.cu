@@ -12,7 +12,9 @@
 // contiguous: dgrad's W, wgrad's dY^T and X) -- the major-ness is a bit in the instruction descriptor
 // plus the canonical 128B-swizzle shared-memory layout the TMA boxes are written in -- and may be stored
 // head-major ([C/64][M][64], q/k/v and their gradients), which is just a different 3-D tensor map.
-// Work items are (m-tile, n-tile, k-split); split-K items accumulate with fp32 atomics (wgrad).
+// Work: output tiles strided over the persistent CTAs; accumulate epilogues (wgrad) instead use stream-K --
+// the (tile, k-block) space is cut into one equal contiguous range per CTA and partial tiles are summed
+// with fp32 vector atomics, so 18..72-tile weight-gradient GEMMs still load all 148 SMs evenly.
 //
 // Replaces the cuBLASLt GEMMs behind timm's nn.Linear layers (SURVEY.md 2.1 K4,K6,K7,K8 and their
 // autograd backward), reached from /root/reference/train_advanced.py:327-330.
@@ -35,7 +37,9 @@ enum { OP_KM_FLAT = 0, OP_KM_SPLIT = 1, OP_MN_FLAT = 2, OP_MN_SPLIT = 3 };
 struct TcParams {
   int32_t I, J, R;
   int32_t a_mode, b_mode;
-  int32_t n_tiles_m, n_tiles_n, splits, kb_total, kb_per_split;
+  int32_t n_tiles_m, n_tiles_n, kb_total;
+  int32_t streamk;          // 0: tile-strided, full K per tile; 1: contiguous (tile, k-block) unit range per CTA
+  int64_t units_per_cta;    // stream-K: ceil(tiles * kb_total / gridDim.x)
   uint32_t idesc;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // bytes
   uint32_t a_kstep, b_kstep;            // bytes advanced per UMMA_K=16 step
@@ -122,50 +126,105 @@ __device__ __forceinline__ float4 unpack_bf16x4(uint2 u) {
 }
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-__device__ __forceinline__ void epilogue_quad(const EpiParams& ep, int i, int j, float4 v) {
+// 8 rows (i, i+4, ..., i+28) x 4 columns (j..j+3) per lane.  All global loads of the 8 rows are issued
+// before any dependent math/store so 8 requests per lane are in flight (no asm/memory-clobber fences here).
+__device__ __forceinline__ void epilogue_rows8(const EpiParams& ep, int i, int j, int I, float4 (&v)[8]) {
   switch (ep.mode) {
     case E_STORE: {
-      if (ep.bias) v = f4_add(v, __ldg(reinterpret_cast<const float4*>(ep.bias + j)));
-      const int64_t o = (int64_t)i * ep.ldc + j;
-      if (ep.out_dtype == VITK_BF16) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) = pack_bf16x4(v);
-      else *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o) = v;
+      if (ep.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + j));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) v[it] = f4_add(v[it], b);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = i + it * 4;
+        if (row >= I) continue;
+        const int64_t o = (int64_t)row * ep.ldc + j;
+        if (ep.out_dtype == VITK_BF16) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) = pack_bf16x4(v[it]);
+        else *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o) = v[it];
+      }
     } break;
     case E_BIAS_GELU: {
-      v = f4_add(v, __ldg(reinterpret_cast<const float4*>(ep.bias + j)));
-      const int64_t o = (int64_t)i * ep.ldc + j;
-      const uint2 u16 = pack_bf16x4(v);
-      if (ep.aux) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.aux) + o) = u16;
-      const float4 ur = unpack_bf16x4(u16);  // GELU acts on the 16-bit fc1 output (autocast semantics)
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) =
-          pack_bf16x4(make_float4(gelu_fast(ur.x), gelu_fast(ur.y), gelu_fast(ur.z), gelu_fast(ur.w)));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + j));
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = i + it * 4;
+        if (row >= I) continue;
+        const int64_t o = (int64_t)row * ep.ldc + j;
+        const float4 ur = unpack_bf16x4(pack_bf16x4(f4_add(v[it], b)));  // GELU acts on the 16-bit fc1 output (autocast)
+        float4 g, dg;
+        gelu_fast_both(ur.x, g.x, dg.x); gelu_fast_both(ur.y, g.y, dg.y);
+        gelu_fast_both(ur.z, g.z, dg.z); gelu_fast_both(ur.w, g.w, dg.w);
+        if (ep.aux) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.aux) + o) = pack_bf16x4(dg);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) = pack_bf16x4(g);
+      }
     } break;
     case E_BIAS_RESIDUAL: {
-      v = f4_add(v, __ldg(reinterpret_cast<const float4*>(ep.bias + j)));
-      const int64_t o = (int64_t)i * ep.ldc + j;
-      const float4 r = *reinterpret_cast<const float4*>(ep.residual + o);
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o) = f4_add(r, v);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + j));
+      float4 r[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = i + it * 4;
+        r[it] = (row < I) ? *reinterpret_cast<const float4*>(ep.residual + (int64_t)row * ep.ldc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = i + it * 4;
+        if (row < I) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldc + j) = f4_add(r[it], f4_add(v[it], b));
+      }
     } break;
     case E_QKV_SCATTER: {
-      v = f4_add(v, __ldg(reinterpret_cast<const float4*>(ep.bias + j)));
-      const int64_t o = (int64_t)(j >> 6) * ep.hm_rows * 64 + (int64_t)i * 64 + (j & 63);
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) = pack_bf16x4(v);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + j));
+      const int64_t base = (int64_t)(j >> 6) * ep.hm_rows * 64 + (j & 63);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = i + it * 4;
+        if (row < I) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + base + (int64_t)row * 64) = pack_bf16x4(f4_add(v[it], b));
+      }
     } break;
     case E_GELU_BWD: {
-      const int64_t o = (int64_t)i * ep.ldc + j;
-      const float4 u = unpack_bf16x4(*reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + o));
-      v.x *= gelu_fast_grad(u.x); v.y *= gelu_fast_grad(u.y); v.z *= gelu_fast_grad(u.z); v.w *= gelu_fast_grad(u.w);
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) = pack_bf16x4(v);
+      uint2 u[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = i + it * 4;
+        u[it] = (row < I) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + (int64_t)row * ep.ldc + j) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = i + it * 4;
+        if (row >= I) continue;
+        const float4 uu = unpack_bf16x4(u[it]);
+        float4 o = v[it];
+        o.x *= uu.x; o.y *= uu.y; o.z *= uu.z; o.w *= uu.w;   // aux = gelu'(u), saved by the forward epilogue
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + (int64_t)row * ep.ldc + j) = pack_bf16x4(o);
+      }
     } break;
     case E_ACCUM: {
-      float* d = reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j;
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = i + it * 4;
+        if (row >= I) continue;
+        float* d = reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldc + j;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v[it].x), "f"(v[it].y), "f"(v[it].z), "f"(v[it].w));
+      }
     } break;
     case E_PATCH: {
-      const int t = i % VITK_NTOK;
-      const float4 pe = __ldg(reinterpret_cast<const float4*>(ep.residual + (int64_t)t * ep.ldc + j));
-      if (t == 0) v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.aux) + j));
-      else v = f4_add(v, __ldg(reinterpret_cast<const float4*>(ep.bias + j)));
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)i * ep.ldc + j) = f4_add(v, pe);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + j));
+      const float4 cls = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.aux) + j));
+      float4 pe[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = i + it * 4;
+        pe[it] = (row < I) ? __ldg(reinterpret_cast<const float4*>(ep.residual + (int64_t)(row % VITK_NTOK) * ep.ldc + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = i + it * 4;
+        if (row >= I) continue;
+        const float4 val = (row % VITK_NTOK == 0) ? cls : f4_add(v[it], b);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldc + j) = f4_add(val, pe[it]);
+      }
     } break;
     default: break;
   }
@@ -177,8 +236,8 @@ __device__ __forceinline__ void epilogue_quad(const EpiParams& ep, int i, int j,
 template <int BN> struct TcCfg {
   static constexpr uint32_t B_STAGE_BYTES = BN * TC_BK * 2;
   static constexpr uint32_t STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (256 or 512: powers of two)
+  static constexpr int STAGES = (BN >= 192) ? 4 : 6;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // double-buffered accumulator, power of two
   static constexpr uint32_t EPI_OFF = STAGES * STAGE_BYTES + 256;  // TC_EPI_WARPS x 4 KB transpose buffers after the barriers
   static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)EPI_OFF + TC_EPI_WARPS * 4096;
 };
@@ -196,6 +255,41 @@ __device__ __forceinline__ void tc_issue_operand_loads(const CUtensorMap* map, i
     for (int a = 0; a < rows_in_tile / 64; ++a) tma_load_3d(dst + a * 8192, map, bar, 0, r0, (row0 >> 6) + a);
   }
 }
+
+// Work iterator shared by the three warp roles (they must walk identical sequences).
+struct TcWork {
+  int tile, kb0, kb1;
+};
+struct TcWorkIter {
+  int64_t cur, end;  // stream-K: unit cursor / end ; tile-strided: next tile / number of tiles
+  __device__ __forceinline__ void init(const TcParams& p) {
+    const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n;
+    if (p.streamk) {
+      const int64_t total = tiles * p.kb_total;
+      cur = (int64_t)blockIdx.x * p.units_per_cta;
+      end = cur + p.units_per_cta < total ? cur + p.units_per_cta : total;
+    } else {
+      cur = blockIdx.x;
+      end = tiles;
+    }
+  }
+  __device__ __forceinline__ bool next(const TcParams& p, TcWork& w) {
+    if (cur >= end) return false;
+    if (p.streamk) {
+      w.tile = (int)(cur / p.kb_total);
+      w.kb0 = (int)(cur % p.kb_total);
+      const int64_t left = end - cur;
+      w.kb1 = (int)((int64_t)(p.kb_total - w.kb0) < left ? p.kb_total : w.kb0 + left);
+      cur += w.kb1 - w.kb0;
+    } else {
+      w.tile = (int)cur;
+      w.kb0 = 0;
+      w.kb1 = p.kb_total;
+      cur += gridDim.x;
+    }
+    return true;
+  }
+};
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -237,18 +331,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int n_items = p.n_tiles_m * p.n_tiles_n * p.splits;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int tile = item % (p.n_tiles_m * p.n_tiles_n), split = item / (p.n_tiles_m * p.n_tiles_n);
+      TcWorkIter wi;
+      wi.init(p);
+      TcWork w;
+      while (wi.next(p, w)) {
+        const int tile = w.tile;
         const int i0 = (tile / p.n_tiles_n) * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int kb0 = w.kb0, kb1 = w.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -266,10 +361,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int split = item / (p.n_tiles_m * p.n_tiles_n);
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      TcWorkIter wi;
+      wi.init(p);
+      TcWork w;
+      while (wi.next(p, w)) {
+        const int kb0 = w.kb0, kb1 = w.kb1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -297,13 +393,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int half = (warp - TC_EPI_WARP0) >> 2;  // which interleaved set of column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int tile = item % (p.n_tiles_m * p.n_tiles_n);
+    TcWorkIter wi;
+    wi.init(p);
+    TcWork w;
+    while (wi.next(p, w)) {
+      const int tile = w.tile;
       const int i0 = (tile / p.n_tiles_n) * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
+      // While the MMAs of this tile still run: pull the epilogue's second operand (saved gelu' / fp32 residual)
+      // for this warp's 32 rows into L2, so the dependent loads below are L2 hits instead of HBM round trips.
+      if (p.ep.mode == E_GELU_BWD || p.ep.mode == E_BIAS_RESIDUAL) {
+        const int elt = p.ep.mode == E_GELU_BWD ? 2 : 4;
+        const char* src = p.ep.mode == E_GELU_BWD ? reinterpret_cast<const char*>(p.ep.aux)
+                                                  : reinterpret_cast<const char*>(p.ep.residual);
+        const int lines = BN * elt / 128;
+        for (int idx = half * 32 + lane; idx < 32 * lines; idx += 64) {
+          const int row = i0 + q * 32 + idx / lines;
+          if (row < p.I)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((int64_t)row * p.ep.ldc + j0) * elt + (idx % lines) * 128));
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      const uint32_t tbuf = smem_base + Cfg::EPI_OFF + (uint32_t)(warp - TC_EPI_WARP0) * 4096u;
+      float4* tb = reinterpret_cast<float4*>(smem + Cfg::EPI_OFF + (uint32_t)(warp - TC_EPI_WARP0) * 4096u);
       const int sub_row = lane >> 3, c4 = lane & 7;
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
@@ -312,19 +424,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // row `lane` of the 32x32 chunk -> swizzled smem (16-byte column group cg at cg ^ (row & 7))
 #pragma unroll
         for (int cg = 0; cg < 8; ++cg)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbuf + lane * 128 + ((cg ^ (lane & 7)) << 4)),
-                       "r"(raw[cg * 4]), "r"(raw[cg * 4 + 1]), "r"(raw[cg * 4 + 2]), "r"(raw[cg * 4 + 3]) : "memory");
+          tb[lane * 8 + (cg ^ (lane & 7))] = make_float4(__uint_as_float(raw[cg * 4]), __uint_as_float(raw[cg * 4 + 1]),
+                                                         __uint_as_float(raw[cg * 4 + 2]), __uint_as_float(raw[cg * 4 + 3]));
         __syncwarp();
+        float4 v[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + sub_row;
-          float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                       : "r"(tbuf + r * 128 + ((c4 ^ (r & 7)) << 4)));
-          const int i = i0 + q * 32 + r;
-          if (i < p.I) epilogue_quad(p.ep, i, j0 + c * 32 + c4 * 4, v);
+          v[it] = tb[r * 8 + (c4 ^ (r & 7))];
         }
         __syncwarp();
+        epilogue_rows8(p.ep, i0 + q * 32 + sub_row, j0 + c * 32 + c4 * 4, p.I, v);
       }
       tc_fence_before();
       __syncwarp();
@@ -438,18 +548,17 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
   p.kb_total = (pr.R + TC_BK - 1) / TC_BK;
   const int tiles = p.n_tiles_m * p.n_tiles_n;
   const int sms = sm_count();
-  int splits = 1;
-  if (pr.ep.mode == E_ACCUM) {
-    splits = (sms + tiles - 1) / tiles;                    // fill the machine at least once
-    if (splits > p.kb_total / 4) splits = p.kb_total / 4;  // keep >= 4 k-blocks per item
-    if (splits < 1) splits = 1;
-    if (g_tc_debug[1] > 0) splits = g_tc_debug[1];
+  int grid = tiles < sms ? tiles : sms;
+  p.streamk = 0;
+  p.units_per_cta = 0;
+  if (pr.ep.mode == E_ACCUM && g_tc_debug[1] != 1) {
+    const int64_t total = (int64_t)tiles * p.kb_total;
+    grid = total < sms ? (int)total : sms;
+    p.streamk = 1;
+    p.units_per_cta = (total + grid - 1) / grid;
+    grid = (int)((total + p.units_per_cta - 1) / p.units_per_cta);
   }
-  p.kb_per_split = (p.kb_total + splits - 1) / splits;
-  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.ep = pr.ep;
-  const int n_items = tiles * p.splits;
-  const int grid = n_items < sms ? n_items : sms;
   gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(map_a, map_b, p);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
@@ -461,7 +570,29 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
   if (pr.ep.mode != E_STORE && pr.ep.mode != E_ACCUM && pr.ep.mode != E_BIAS_RESIDUAL && pr.ep.mode != E_PATCH &&
       pr.ep.out_dtype != VITK_BF16) { set_error("gemm_tc: epilogue expects bf16 output"); return VITK_ERR_UNSUPPORTED; }
   if (pr.J % 128 != 0 || pr.ep.ldc % 8 != 0) { set_error("gemm_tc: J must be a multiple of 128 (got %d)", pr.J); return VITK_ERR_UNSUPPORTED; }
-  if (pr.J % 256 == 0 && g_tc_debug[2] != 128) return launch_tc<256>(pr, st);
+  // BLOCK_N: minimise (waves of the persistent grid) x (tile cost ~ BN + fixed per-tile overhead); with
+  // M = B*197 the tile count is rarely a multiple of 148 SMs, e.g. 12608x768: 297 tiles of 128x256 = 3 waves
+  // for 2.007 waves of work, 396 tiles of 128x192 = 3 waves of 3/4 the cost.
+  int bn = 0;
+  if (g_tc_debug[2] == 128 || g_tc_debug[2] == 192 || g_tc_debug[2] == 256) {
+    bn = g_tc_debug[2];
+  } else if (pr.ep.mode == E_ACCUM) {
+    bn = pr.J % 256 == 0 ? 256 : 128;  // stream-K balances by itself
+  } else {
+    const int sms = sm_count();
+    const long tiles_m = (pr.I + TC_BM - 1) / TC_BM;
+    long best = -1;
+    for (int cand : {256, 192, 128}) {
+      if (pr.J % cand != 0) continue;
+      const long tiles = tiles_m * (pr.J / cand);
+      const long waves = (tiles + sms - 1) / sms;
+      const long cost = waves * (cand + 32);
+      if (best < 0 || cost < best) { best = cost; bn = cand; }
+    }
+  }
+  if (bn == 0 || pr.J % bn != 0) { set_error("gemm_tc: no BLOCK_N divides J=%d", pr.J); return VITK_ERR_UNSUPPORTED; }
+  if (bn == 256) return launch_tc<256>(pr, st);
+  if (bn == 192) return launch_tc<192>(pr, st);
   return launch_tc<128>(pr, st);
 }
 

@@ -205,7 +205,7 @@ extern "C" int vitk_linear_fwd(const void* x, int x_layout, const void* w, const
   p.ep.out = y; p.ep.bias = bias; p.ep.ldc = N; p.ep.out_dtype = dtype;
   switch (epilogue) {
     case VITK_EPI_BIAS: p.ep.mode = E_STORE; break;
-    case VITK_EPI_BIAS_GELU: p.ep.mode = E_BIAS_GELU; p.ep.aux = aux; break;  // aux == NULL: eval, u not kept
+    case VITK_EPI_BIAS_GELU: p.ep.mode = E_BIAS_GELU; p.ep.aux = aux; break;  // aux == NULL: eval, gelu'(u) not kept
     case VITK_EPI_BIAS_RESIDUAL:
       VITK_CHECK_ARG(aux);
       p.ep.mode = E_BIAS_RESIDUAL; p.ep.residual = (const float*)aux; p.ep.out_dtype = VITK_F32;
@@ -216,7 +216,7 @@ extern "C" int vitk_linear_fwd(const void* x, int x_layout, const void* w, const
   return run_gemm(p, engine, 1, (cudaStream_t)stream);
 }
 
-extern "C" int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, const void* gelu_u,
+extern "C" int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, const void* gelu_grad,
                                  int M, int N, int K, int dtype, int engine, void* stream) {
   VITK_CHECK_ARG(dy && w && dx && M > 0 && N > 0 && K > 0);
   VITK_CHECK_ARG(dtype == VITK_F32 || dtype == VITK_BF16);
@@ -227,8 +227,8 @@ extern "C" int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, v
   p.la = dy_layout == VITK_LAYOUT_HEADMAJOR ? layout_headmajor_rows_m(M) : layout_rowmajor(N);
   p.lb = layout_transposed(K);  // B(j=k, r=n) = w[n*K + k]
   p.ep.out = dx; p.ep.ldc = K; p.ep.out_dtype = dtype;
-  p.ep.mode = gelu_u ? E_GELU_BWD : E_STORE;
-  p.ep.aux = const_cast<void*>(gelu_u);
+  p.ep.mode = gelu_grad ? E_GELU_BWD : E_STORE;
+  p.ep.aux = const_cast<void*>(gelu_grad);
   return run_gemm(p, engine, 1, (cudaStream_t)stream);
 }
 

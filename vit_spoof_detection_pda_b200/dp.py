@@ -105,3 +105,43 @@ class DataParallel(nn.Module):
 
     def load_state_dict(self, *a, **k):
         return self.module.load_state_dict(*a, **k)
+
+
+class DevicePrefetcher:
+    """Host->device input pipeline for the train / eval loops (the reference's
+    ``images.to(device, non_blocking=True)`` at train_advanced.py:323-324, made asynchronous): batch i+1 is
+    copied from pinned host memory on a side stream while step i computes, so the H2D transfer (38.5 MB per
+    64-image fp32 batch, ~1.5 ms over PCIe 5) leaves the critical path.  Iterate it like the loader::
+
+        for images, labels in DevicePrefetcher(loader, device): ...
+    """
+
+    def __init__(self, loader, device):
+        self.loader = loader
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def _issue(self, batch):
+        with torch.cuda.stream(self.stream):
+            out = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return out, ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._issue(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = self._issue(next(it))
+            except StopIteration:
+                nxt = None
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            for t in cur:
+                if torch.is_tensor(t):
+                    t.record_stream(torch.cuda.current_stream(self.device))
+            yield cur
