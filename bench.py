@@ -143,7 +143,7 @@ def run_reference(args):
         "e2e": {"value": r["img_s"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def train_config(n_gpus):
@@ -170,7 +170,11 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # SMs NCCL may take for the gradient all-reduce; DataParallel shrinks the persistent GEMM grids by the same
+        # number while a collective is in flight (see dp.py)
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     lib = L.load()   # fails loudly when libvitk.so is missing
 
     torch.manual_seed(42)
@@ -260,15 +264,18 @@ def run_ours(args):
     h2d = B * 3 * 224 * 224 * 4 + B * 8
     d2h = 4 + 4
 
+    # ---- live per-launch GEMM timing inside real steps -> roofline of the dominant kernel.  Every rank runs the two
+    # steps (they contain the gradient all-reduce); only rank 0 records and reads the events.
+    if rank == 0:
+        lib.vitk_prof_enable(1)
+    for i in range(2):
+        step(dev_imgs[i % n_pool], dev_lbls[i % n_pool])
+    barrier()
+
     line = None
     if rank == 0:
         peaks = load_peaks()
-        # ---- live per-launch GEMM timing inside real steps -> roofline of the dominant kernel
         import ctypes as C
-        lib.vitk_prof_enable(1)
-        for i in range(2):
-            step(dev_imgs[i % n_pool], dev_lbls[i % n_pool])
-        torch.cuda.synchronize()
         maxn = 4096
         ms_arr = (C.c_float * maxn)()
         info = (C.c_int * (5 * maxn))()
@@ -354,10 +361,30 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route everything libraries print to fd 1 (e.g. NCCL's version banner) to stderr, keeping the real stdout for
+    the single JSON line the driver parses."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -75,17 +75,18 @@ int vitk_set_gemm_engine(int engine);
  * Block.norm1/.norm2, vit.norm (eps 1e-6) and classifier[0] (eps 1e-5, train_advanced.py:194).
  *   x: fp32 [rows] with row stride x_stride (elements); y: y_dtype, dense [rows][768];
  *   mean/rstd: fp32 [rows] saved for backward (may be NULL in eval).
- * bwd: dx = (dres ? dres : 0) + LN'(dy) ; also written as bf16 to dx16 when non-NULL;
- *   dgamma/dbeta are ACCUMULATED (+=) into fp32 [768]; partial is caller scratch of
- *   vitk_layernorm_bwd_scratch_floats() floats.
+ * bwd: dx = (dres ? dres : 0) + LN'(dy) ; also written as bf16 to dx16 when non-NULL (dres may alias dx);
+ *   dgamma/dbeta are ACCUMULATED (+=) into fp32 [768];
+ *   dx_colsum (optional) += column sums of the dx written: dx is the gradient of the residual stream, i.e. the
+ *   dY of the Linear whose output was added into it, so this IS that Linear's bias gradient (proj / fc2) --
+ *   fused here instead of re-reading dY in a separate reduction.
  * ------------------------------------------------------------------------------------------- */
 int vitk_layernorm_fwd(const float* x, int64_t x_stride, const float* gamma, const float* beta,
                        void* y, int y_dtype, float* mean, float* rstd, int rows, float eps, void* stream);
 int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, int64_t x_stride,
                        const float* gamma, const float* mean, const float* rstd, const float* dres,
-                       float* dx, void* dx16, float* dgamma, float* dbeta, float* partial,
+                       float* dx, void* dx16, float* dgamma, float* dbeta, float* dx_colsum,
                        int rows, void* stream);
-size_t vitk_layernorm_bwd_scratch_floats(void);
 
 /* ---------------------------------------------------------------------------------------------
  * nn.Linear forward / backward (timm Attention.qkv, Attention.proj, Mlp.fc1, Mlp.fc2).
@@ -98,8 +99,10 @@ size_t vitk_layernorm_bwd_scratch_floats(void);
  * ------------------------------------------------------------------------------------------- */
 int vitk_linear_fwd(const void* x, int x_layout, const void* w, const float* bias, void* y, void* aux,
                     int M, int N, int K, int epilogue, int dtype, int engine, void* stream);
+/* dx_colsum (optional, only with gelu_grad): fp32 [K] += column sums of dX -- the bias gradient of the Linear in
+ * front of the GELU (fc1), fused into this GEMM's epilogue instead of a separate pass over dX. */
 int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, const void* gelu_grad,
-                      int M, int N, int K, int dtype, int engine, void* stream);
+                      float* dx_colsum, int M, int N, int K, int dtype, int engine, void* stream);
 int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, float* dw, float* db,
                       int M, int N, int K, int dtype, int engine, void* stream);
 
@@ -127,8 +130,9 @@ int vitk_patch_embed_wgrad(const float* dx0, const void* dx0_act, const void* pa
  *   bwd : dqkv head-major [36][M][64] from dout [M][768]
  * ------------------------------------------------------------------------------------------- */
 int vitk_attn_fwd(const void* qkv, void* out, float* lse, int batch, int dtype, void* stream);
+/* dqkv_colsum (optional): fp32 [2304] += column sums of dqkv (= the qkv bias gradient), fused into the kernel */
 int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                  int batch, int dtype, void* stream);
+                  float* dqkv_colsum, int batch, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Classifier head on the CLS feature (train_advanced.py:193-200, 204) -- fp32 always.
@@ -218,6 +222,10 @@ int vitk_model_num_bwd_stages(int depth);
 /* debug knobs of the tcgen05 engine (tests only): key 0 = swap LBO/SBO of MN-major operands,
  * key 1 = 1 disables stream-K for accumulate (wgrad) GEMMs, key 2 = force BLOCK_N (128/192/256) */
 int vitk_debug_set(int key, int value);
+/* Number of SMs the persistent kernels (GEMM, LayerNorm backward, ...) size their grids for; 0 = all.  The
+ * data-parallel wrapper lowers it during backward so the NCCL all-reduce CTAs and the persistent GEMM CTAs
+ * (one per SM, ~225 KB of shared memory each) can all be resident at once.  Returns the previous value. */
+int vitk_set_sm_budget(int n);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long vitk_launch_count(void);
 /* per-launch GEMM timing with CUDA events on the launching stream (bench.py's live roofline):

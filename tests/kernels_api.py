@@ -33,10 +33,10 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want16=False, x_stride=No
     dx16 = torch.empty(rows, 768, dtype=torch.bfloat16, device=dy.device) if want16 else None
     dg = torch.zeros(768, dtype=torch.float32, device=dy.device)
     db = torch.zeros_like(dg)
-    part = torch.empty(L.load().vitk_layernorm_bwd_scratch_floats(), dtype=torch.float32, device=dy.device)
+    cs = torch.zeros(768, dtype=torch.float32, device=dy.device)
     L.call("vitk_layernorm_bwd", L.ptr(dy), DT[dy.dtype], L.ptr(x), x_stride or 768, L.ptr(gamma), L.ptr(mean),
-           L.ptr(rstd), L.ptr(dres), L.ptr(dx), L.ptr(dx16), L.ptr(dg), L.ptr(db), L.ptr(part), rows, L.stream_ptr())
-    return dx, dx16, dg, db
+           L.ptr(rstd), L.ptr(dres), L.ptr(dx), L.ptr(dx16), L.ptr(dg), L.ptr(db), L.ptr(cs), rows, L.stream_ptr())
+    return dx, dx16, dg, db, cs
 
 
 def linear_fwd(x, w, bias, epilogue, engine, x_layout=L.LAYOUT_ROWMAJOR, residual=None, M=None):
@@ -58,13 +58,14 @@ def linear_fwd(x, w, bias, epilogue, engine, x_layout=L.LAYOUT_ROWMAJOR, residua
     return (y, aux) if epilogue == L.EPI_BIAS_GELU else y
 
 
-def linear_dgrad(dy, w, engine, dy_layout=L.LAYOUT_ROWMAJOR, gelu_grad=None):
+def linear_dgrad(dy, w, engine, dy_layout=L.LAYOUT_ROWMAJOR, gelu_grad=None, want_colsum=False):
     N, K = w.shape
     M = dy.shape[0] if dy_layout == L.LAYOUT_ROWMAJOR else dy.shape[1]
     dx = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
-    L.call("vitk_linear_dgrad", L.ptr(dy), dy_layout, L.ptr(w), L.ptr(dx), L.ptr(gelu_grad), M, N, K, DT[dy.dtype], engine,
-           L.stream_ptr())
-    return dx
+    cs = torch.zeros(K, dtype=torch.float32, device=dy.device) if (want_colsum and gelu_grad is not None) else None
+    L.call("vitk_linear_dgrad", L.ptr(dy), dy_layout, L.ptr(w), L.ptr(dx), L.ptr(gelu_grad), L.ptr(cs), M, N, K,
+           DT[dy.dtype], engine, L.stream_ptr())
+    return (dx, cs) if cs is not None else dx
 
 
 def linear_wgrad(dy, x, N, K, engine, dy_layout=L.LAYOUT_ROWMAJOR):
@@ -86,9 +87,10 @@ def attn_fwd(qkv_hm, batch):
 
 def attn_bwd(qkv_hm, out, dout, lse, batch):
     dqkv = torch.empty_like(qkv_hm)
-    L.call("vitk_attn_bwd", L.ptr(qkv_hm), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(dqkv), batch, DT[qkv_hm.dtype],
-           L.stream_ptr())
-    return dqkv
+    cs = torch.zeros(2304, dtype=torch.float32, device=qkv_hm.device)
+    L.call("vitk_attn_bwd", L.ptr(qkv_hm), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(dqkv), L.ptr(cs), batch,
+           DT[qkv_hm.dtype], L.stream_ptr())
+    return dqkv, cs
 
 
 def rel_err(a, b):

@@ -47,8 +47,9 @@ def test_layernorm_fwd_bwd(rows, out_dtype):
     dy = randn(rows, 768, seed=4).to(odt)
     dres = randn(rows, 768, seed=5)
     yr.backward(dy.float())
-    dx, dx16, dg, db = K.layernorm_bwd(dy, x, gamma, mean, rstd, dres=dres.clone(), want16=True)
+    dx, dx16, dg, db, cs = K.layernorm_bwd(dy, x, gamma, mean, rstd, dres=dres.clone(), want16=True)
     assert K.rel_err(dx, xr.grad + dres) < FP32_TOL
+    assert K.rel_err(cs, (xr.grad + dres).sum(0)) < FP32_TOL * 5
     assert K.rel_err(dx16.float(), xr.grad + dres) < BF16_TOL
     assert K.rel_err(dg, gr.grad) < FP32_TOL * 5
     assert K.rel_err(db, br.grad) < FP32_TOL * 5
@@ -117,8 +118,9 @@ def test_linear_dgrad(case, M, N, Kd):
     for eng in engines:
         dx = K.linear_dgrad(dy, w, eng)
         assert K.rel_err(dx.float(), ref) < _tol(dtype), ("plain", eng)
-        dx = K.linear_dgrad(dy, w, eng, gelu_grad=u)
+        dx, cs = K.linear_dgrad(dy, w, eng, gelu_grad=u, want_colsum=True)
         assert K.rel_err(dx.float(), ref * u.float()) < _tol(dtype), ("gelu_bwd", eng)
+        assert K.rel_err(cs, dx.float().sum(0)) < 1e-3, ("gelu_bwd fused bias-grad column sums", eng)
         if N % 64 == 0:
             dx = K.linear_dgrad(K.to_headmajor(dy), w, eng, dy_layout=L.LAYOUT_HEADMAJOR)
             assert K.rel_err(dx.float(), ref) < _tol(dtype), ("headmajor", eng)
@@ -185,9 +187,10 @@ def test_attention_fwd_bwd(dtype, B):
     lse_ref = torch.logsumexp(s, -1).permute(1, 0, 2).reshape(12, M)
     assert K.rel_err(lse, lse_ref) < _tol(dtype)
     o.backward(dout.float())
-    dqkv = K.attn_bwd(hm, out, dout, lse, B)
+    dqkv, cs = K.attn_bwd(hm, out, dout, lse, B)
     ref = t.grad.permute(1, 3, 0, 2, 4).reshape(M, 2304)
     assert K.rel_err(K.from_headmajor(dqkv).float(), ref) < _tol(dtype) * (1 if dtype == torch.float32 else 2)
+    assert K.rel_err(cs, K.from_headmajor(dqkv).float().sum(0)) < 1e-3     # fused qkv bias gradient
 
 
 # ------------------------------------------------------------------ head

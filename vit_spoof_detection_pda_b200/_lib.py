@@ -38,14 +38,13 @@ PROTOTYPES = {
     "vitk_set_gemm_engine": (i32, [i32]),
     "vitk_layernorm_fwd": (i32, [vp, i64, vp, vp, vp, i32, vp, vp, i32, f32, vp]),
     "vitk_layernorm_bwd": (i32, [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
-    "vitk_layernorm_bwd_scratch_floats": (sz, []),
     "vitk_linear_fwd": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
-    "vitk_linear_dgrad": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "vitk_linear_dgrad": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "vitk_linear_wgrad": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "vitk_patch_embed_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "vitk_patch_embed_wgrad": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "vitk_attn_fwd": (i32, [vp, vp, vp, i32, i32, vp]),
-    "vitk_attn_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
+    "vitk_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "vitk_head_save_floats": (sz, [i32]),
     "vitk_head_fwd": (i32, [vp] * 11 + [i32, i32, vp]),
     "vitk_head_bwd": (i32, [vp] * 14 + [i32, i32, vp]),
@@ -60,6 +59,7 @@ PROTOTYPES = {
     "vitk_model_bwd_stage": (i32, [C.POINTER(VitkModel), i32, vp]),
     "vitk_model_num_bwd_stages": (i32, [i32]),
     "vitk_debug_set": (i32, [i32, i32]),
+    "vitk_set_sm_budget": (i32, [i32]),
     "vitk_launch_count": (C.c_longlong, []),
     "vitk_prof_enable": (i32, [i32]),
     "vitk_prof_read": (i32, [C.POINTER(C.c_float), C.POINTER(i32), i32]),

@@ -16,7 +16,8 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(); }
-int sm_count() {
+static std::atomic<int> g_sm_budget{0};
+static int hw_sm_count() {
   static int cached = 0;
   if (cached) return cached;
   int dev = 0, n = 0;
@@ -25,10 +26,19 @@ int sm_count() {
   cached = n;
   return n;
 }
+// SMs the persistent kernels size their grids for: all of them, or the budget set while a communication
+// kernel (NCCL all-reduce) owns some SMs -- a persistent CTA that cannot become resident would stall its
+// statically assigned tiles until the collective finishes.
+int sm_count() {
+  const int hw = hw_sm_count(), b = g_sm_budget.load(std::memory_order_relaxed);
+  return (b > 0 && b < hw) ? b : hw;
+}
+int set_sm_budget(int n) { return g_sm_budget.exchange(n); }
 }  // namespace vitk
 
 extern "C" {
 int vitk_version(void) { return VITK_VERSION; }
+int vitk_set_sm_budget(int n) { return vitk::set_sm_budget(n); }
 long long vitk_launch_count(void) { return vitk::launches(); }
 const char* vitk_last_error_string(void) { return vitk::g_err; }
 int vitk_device_info(int* sm_count, int* cc_major, int* cc_minor) {

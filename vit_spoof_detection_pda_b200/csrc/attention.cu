@@ -6,18 +6,23 @@ int attn_fwd_simt(const void* qkv, void* out, float* lse, int batch, int dtype, 
 int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
                   int dtype, cudaStream_t st);
 int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t st);
-int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
-                 cudaStream_t st);
+int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum,
+                 int batch, cudaStream_t st);
+int colsum_headmajor(const void* x, int dtype, int M, int C, float* db, cudaStream_t st);
 
 int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dtype, cudaStream_t st) {
   if (dtype == VITK_BF16 && default_engine() != VITK_ENGINE_SIMT) return attn_fwd_mma(qkv, out, lse, batch, st);
   return attn_fwd_simt(qkv, out, lse, batch, dtype, st);
 }
-int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
-                      int dtype, cudaStream_t st) {
+// dqkv_colsum (optional): fp32 [2304] += column sums of dqkv = the qkv bias gradient; fused into the tensor-core
+// kernel, a separate reduction after the FFMA kernel.
+int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                      float* dqkv_colsum, int batch, int dtype, cudaStream_t st) {
   if (dtype == VITK_BF16 && default_engine() != VITK_ENGINE_SIMT)
-    return attn_bwd_mma(qkv, out, dout, lse, dqkv, batch, st);
-  return attn_bwd_simt(qkv, out, dout, lse, dqkv, batch, dtype, st);
+    return attn_bwd_mma(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, st);
+  VITK_TRY(attn_bwd_simt(qkv, out, dout, lse, dqkv, batch, dtype, st));
+  if (dqkv_colsum) VITK_TRY(colsum_headmajor(dqkv, dtype, batch * VITK_NTOK, 3 * VITK_DIM, dqkv_colsum, st));
+  return VITK_OK;
 }
 }  // namespace vitk
 
@@ -28,7 +33,7 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int batch, 
   return attn_fwd_dispatch(qkv, out, lse, batch, dtype, (cudaStream_t)stream);
 }
 extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                             int batch, int dtype, void* stream) {
+                             float* dqkv_colsum, int batch, int dtype, void* stream) {
   VITK_CHECK_ARG(qkv && out && dout && lse && dqkv && batch > 0 && (dtype == VITK_F32 || dtype == VITK_BF16));
-  return attn_bwd_dispatch(qkv, out, dout, lse, dqkv, batch, dtype, (cudaStream_t)stream);
+  return attn_bwd_dispatch(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, dtype, (cudaStream_t)stream);
 }

@@ -27,6 +27,8 @@ constexpr int AM_MAT_BYTES = AM_NP * 128;  // 26,624
 constexpr float AM_SCALE = 0.125f;
 constexpr float AM_LOG2E = 1.4426950408889634f;
 
+int attn_debug_variant();  // gemm_tc.cu: vitk_debug_set(3, v)
+
 __device__ __forceinline__ uint32_t am_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t am_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
@@ -172,13 +174,39 @@ attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float*
   }
 }
 
-__global__ void __launch_bounds__(AM_THREADS, 2)
+// Column sums of one 16 x 64 output tile held in mma accumulator layout (rows g / g+8, cols 8*dn + 2t, +1), of the
+// bf16-rounded scaled values actually stored, rows masked by validity: quad-stride shuffles over g, then lanes 0..3
+// add into the CTA's shared accumulator.  This is the qkv bias gradient, fused instead of re-reading dqkv.
+__device__ __forceinline__ void am_colsum_tile(float* cs, const float (&v)[8][4], float scale, bool valid0, bool valid1, int lane) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) {
+    const float2 lo = unpack_bf16x2(pack_bf16x2(v[dn][0] * scale, v[dn][1] * scale));
+    const float2 hi = unpack_bf16x2(pack_bf16x2(v[dn][2] * scale, v[dn][3] * scale));
+    float a = (valid0 ? lo.x : 0.f) + (valid1 ? hi.x : 0.f);
+    float b = (valid0 ? lo.y : 0.f) + (valid1 ? hi.y : 0.f);
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane < 4) {
+      atomicAdd(cs + dn * 8 + 2 * t, a);
+      atomicAdd(cs + dn * 8 + 2 * t + 1, b);
+    }
+  }
+}
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(AM_THREADS, MIN_CTAS)
 attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
-                    const float* __restrict__ lse, bf16* __restrict__ dqkv, int batch) {
+                    const float* __restrict__ lse, bf16* __restrict__ dqkv, float* __restrict__ dqkv_colsum, int batch) {
   extern __shared__ __align__(1024) uint8_t am_smem[];
   const uint32_t sQ = am_smem_u32(am_smem), sK = sQ + AM_MAT_BYTES, sV = sK + AM_MAT_BYTES, sdO = sV + AM_MAT_BYTES;
   float* Ls = reinterpret_cast<float*>(am_smem + 4 * AM_MAT_BYTES);  // lse * log2(e), padded rows 0
   float* Ds = Ls + AM_NP;                                            // delta_i = dO_i . O_i
+  float* Cs = Ds + AM_NP;                                            // [3][64] column sums of dq, dk, dv (qkv bias grad)
+  if (threadIdx.x < 3 * AM_D) Cs[threadIdx.x] = 0.f;
   const int b = blockIdx.x / VITK_HEADS, h = blockIdx.x % VITK_HEADS;
   const int64_t M = (int64_t)batch * AM_N;
   const int64_t hm = ((int64_t)h * M + (int64_t)b * AM_N) * AM_D;
@@ -256,6 +284,7 @@ attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, 
       if (i0 < AM_N) *reinterpret_cast<uint32_t*>(dqkv + hm + (int64_t)i0 * AM_D + d) = pack_bf16x2(dq[dn][0] * AM_SCALE, dq[dn][1] * AM_SCALE);
       if (i1 < AM_N) *reinterpret_cast<uint32_t*>(dqkv + hm + (int64_t)i1 * AM_D + d) = pack_bf16x2(dq[dn][2] * AM_SCALE, dq[dn][3] * AM_SCALE);
     }
+    if (dqkv_colsum) am_colsum_tile(Cs, dq, AM_SCALE, i0 < AM_N, i1 < AM_N, lane);
   }
 
   // ---------------- phase B: dK, dV for 16 key rows per warp iteration ----------------
@@ -312,11 +341,22 @@ attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, 
         *reinterpret_cast<uint32_t*>(dvg + (int64_t)j1 * AM_D + d) = pack_bf16x2(dv[dn][2], dv[dn][3]);
       }
     }
+    if (dqkv_colsum) {
+      am_colsum_tile(Cs + AM_D, dk, AM_SCALE, j0 < AM_N, j1 < AM_N, lane);
+      am_colsum_tile(Cs + 2 * AM_D, dv, 1.0f, j0 < AM_N, j1 < AM_N, lane);
+    }
+  }
+  if (dqkv_colsum) {
+    __syncthreads();
+    if (threadIdx.x < 3 * AM_D) {
+      const int sec = threadIdx.x / AM_D, d = threadIdx.x % AM_D;
+      atomicAdd(dqkv_colsum + (sec * VITK_HEADS + h) * AM_D + d, Cs[threadIdx.x]);
+    }
   }
 }
 
 constexpr size_t AM_FWD_SMEM = 3 * AM_MAT_BYTES;
-constexpr size_t AM_BWD_SMEM = 4 * AM_MAT_BYTES + 2 * AM_NP * sizeof(float);
+constexpr size_t AM_BWD_SMEM = 4 * AM_MAT_BYTES + (2 * AM_NP + 3 * AM_D) * sizeof(float);
 
 int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t st) {
   static bool configured = false;
@@ -329,15 +369,21 @@ int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t
   return VITK_OK;
 }
 
-int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
-                 cudaStream_t st) {
+int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum,
+                 int batch, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AM_BWD_SMEM));
+    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AM_BWD_SMEM));
+    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AM_BWD_SMEM));
     configured = true;
   }
-  attn_bwd_mma_kernel<<<batch * VITK_HEADS, AM_THREADS, AM_BWD_SMEM, st>>>((const bf16*)qkv, (const bf16*)out,
-                                                                           (const bf16*)dout, lse, (bf16*)dqkv, batch);
+  // variant 1 (debug knob 3): cap registers so two CTAs share an SM (load of one overlaps compute of the other)
+  if (attn_debug_variant() == 1)
+    attn_bwd_mma_kernel<2><<<batch * VITK_HEADS, AM_THREADS, AM_BWD_SMEM, st>>>(
+        (const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, dqkv_colsum, batch);
+  else
+    attn_bwd_mma_kernel<1><<<batch * VITK_HEADS, AM_THREADS, AM_BWD_SMEM, st>>>(
+        (const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, dqkv_colsum, batch);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

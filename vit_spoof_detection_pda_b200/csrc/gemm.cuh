@@ -45,6 +45,7 @@ struct EpiParams {
   const float* residual;  // fp32 [I][ldc] (E_BIAS_RESIDUAL) / pos_embed (E_PATCH)
   int64_t ldc;            // row stride of out / aux / residual (row-major modes)
   int64_t hm_rows;        // M of the head-major output (E_QKV_SCATTER)
+  float* colsum;          // optional (E_GELU_BWD, tcgen05 engine): += column sums of the output (bias gradient of fc1)
 };
 
 struct GemmProblem {

@@ -190,6 +190,7 @@ __device__ __forceinline__ void epilogue_rows8(const EpiParams& ep, int i, int j
         const int row = i + it * 4;
         u[it] = (row < I) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + (int64_t)row * ep.ldc + j) : make_uint2(0u, 0u);
       }
+      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int row = i + it * 4;
@@ -197,7 +198,18 @@ __device__ __forceinline__ void epilogue_rows8(const EpiParams& ep, int i, int j
         const float4 uu = unpack_bf16x4(u[it]);
         float4 o = v[it];
         o.x *= uu.x; o.y *= uu.y; o.z *= uu.z; o.w *= uu.w;   // aux = gelu'(u), saved by the forward epilogue
-        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + (int64_t)row * ep.ldc + j) = pack_bf16x4(o);
+        const uint2 ob = pack_bf16x4(o);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + (int64_t)row * ep.ldc + j) = ob;
+        cs = f4_add(cs, unpack_bf16x4(ob));   // bias gradient sums the values the wgrad GEMM will read
+      }
+      if (ep.colsum) {
+        // column sums of this 32x32 chunk: lanes l, l^8, l^16, l^24 hold the same 4 columns (different rows)
+        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8);  cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8);  cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+        if ((threadIdx.x & 31) < 8)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ep.colsum + j), "f"(cs.x), "f"(cs.y), "f"(cs.z), "f"(cs.w));
       }
     } break;
     case E_ACCUM: {
@@ -517,6 +529,7 @@ static int make_operand_map(const void* base, const MatLayout& l, int rows, int 
 }
 
 static int g_tc_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int attn_debug_variant() { return g_tc_debug[3]; }
 
 template <int BN>
 static int launch_tc(const GemmProblem& pr, cudaStream_t st) {

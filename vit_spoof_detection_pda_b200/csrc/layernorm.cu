@@ -11,7 +11,6 @@ namespace vitk {
 constexpr int LN_COLS = VITK_DIM;        // 768
 constexpr int LN_VEC = LN_COLS / 128;    // 6 float4 per lane
 constexpr int LN_WARPS = 8;
-constexpr int LN_BWD_MAX_CTAS = 296;     // 2 per SM
 
 template <typename T> struct Vec4IO;
 template <> struct Vec4IO<float> {
@@ -80,22 +79,24 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __rest
 // warp touches its slice, so no synchronisation until the end) instead of 48 registers per lane: the kernel
 // then fits 2 co-resident CTAs (16 warps, ~9 KB of loads in flight per warp) per SM in one persistent wave.
 // Final cross-warp sum -> one fp32 atomicAdd per column per CTA into dgamma/dbeta.
-constexpr int LN_BWD_SMEM = LN_WARPS * 2 * LN_COLS * (int)sizeof(float);  // 48 KB
+constexpr int LN_BWD_SMEM = LN_WARPS * 3 * LN_COLS * (int)sizeof(float);  // 72 KB: dgamma, dbeta, colsum(dx)
 
 template <typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32, 2)
 ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_stride,
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* dres, float* dx, bf16* __restrict__ dx16,  // dres may alias dx (in-place residual-grad update)
-              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows) {
-  extern __shared__ float ln_acc[];  // [warp][2][768]
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx_colsum, int rows) {
+  extern __shared__ float ln_acc[];  // [warp][3][768]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* acc_g = ln_acc + (size_t)warp * 2 * LN_COLS;
+  float* acc_g = ln_acc + (size_t)warp * 3 * LN_COLS;
   float* acc_b = acc_g + LN_COLS;
+  float* acc_c = acc_b + LN_COLS;  // column sums of the dx this kernel writes (= bias gradient of the Linear that produced x)
 #pragma unroll
   for (int i = 0; i < LN_VEC; ++i) {
     *reinterpret_cast<float4*>(acc_g + (i * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(acc_b + (i * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(acc_c + (i * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
     const float* xr = x + (int64_t)row * x_stride;
@@ -135,17 +136,21 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_s
       }
       *reinterpret_cast<float4*>(dx + (int64_t)row * LN_COLS + c) = o;
       if (dx16) Vec4IO<bf16>::store(dx16 + (int64_t)row * LN_COLS + c, o);
+      if (dx_colsum) {
+        float4 ac = *reinterpret_cast<float4*>(acc_c + c);
+        ac.x += o.x; ac.y += o.y; ac.z += o.z; ac.w += o.w;
+        *reinterpret_cast<float4*>(acc_c + c) = ac;
+      }
     }
   }
   __syncthreads();
-  if (dgamma || dbeta) {
-    for (int c = threadIdx.x; c < 2 * LN_COLS; c += LN_WARPS * 32) {
-      float s = 0.f;
+  for (int c = threadIdx.x; c < 3 * LN_COLS; c += LN_WARPS * 32) {
+    float* dst = c < LN_COLS ? dgamma : (c < 2 * LN_COLS ? dbeta : dx_colsum);
+    if (!dst) continue;
+    float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < LN_WARPS; ++w) s += ln_acc[(size_t)w * 2 * LN_COLS + c];
-      float* dst = c < LN_COLS ? dgamma : dbeta;
-      if (dst) atomicAdd(dst + (c % LN_COLS), s);
-    }
+    for (int w = 0; w < LN_WARPS; ++w) s += ln_acc[(size_t)w * 3 * LN_COLS + c];
+    atomicAdd(dst + (c % LN_COLS), s);
   }
 }
 
@@ -153,7 +158,6 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_s
 
 using namespace vitk;
 
-extern "C" size_t vitk_layernorm_bwd_scratch_floats(void) { return (size_t)LN_BWD_MAX_CTAS * 2 * LN_COLS; }
 
 extern "C" int vitk_layernorm_fwd(const float* x, int64_t x_stride, const float* gamma, const float* beta,
                                   void* y, int y_dtype, float* mean, float* rstd, int rows, float eps,
@@ -176,9 +180,8 @@ extern "C" int vitk_layernorm_fwd(const float* x, int64_t x_stride, const float*
 
 extern "C" int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, int64_t x_stride,
                                   const float* gamma, const float* mean, const float* rstd, const float* dres,
-                                  float* dx, void* dx16, float* dgamma, float* dbeta, float* partial, int rows,
+                                  float* dx, void* dx16, float* dgamma, float* dbeta, float* dx_colsum, int rows,
                                   void* stream) {
-  (void)partial;  // kept in the ABI; the reduction now finishes with per-CTA atomics
   VITK_CHECK_ARG(dy && x && gamma && mean && rstd && dx && rows >= 0);
   VITK_CHECK_ARG(x_stride % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)dx % 16) == 0);
   if (rows == 0) return VITK_OK;
@@ -194,10 +197,10 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, 
   if (grid > cap) grid = cap;
   if (dy_dtype == VITK_F32)
     ln_bwd_kernel<float><<<grid, LN_WARPS * 32, LN_BWD_SMEM, st>>>((const float*)dy, x, x_stride, gamma, mean, rstd, dres,
-                                                                  dx, (bf16*)dx16, dgamma, dbeta, rows);
+                                                                  dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
   else if (dy_dtype == VITK_BF16)
     ln_bwd_kernel<bf16><<<grid, LN_WARPS * 32, LN_BWD_SMEM, st>>>((const bf16*)dy, x, x_stride, gamma, mean, rstd, dres,
-                                                                 dx, (bf16*)dx16, dgamma, dbeta, rows);
+                                                                 dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
   else
     VITK_CHECK_ARG(!"bad dtype");
   VITK_LAUNCH_CHECK();

@@ -123,6 +123,11 @@ static int colsum(const void* dy, int dtype, MatLayout l, int M, int C, float* d
   return VITK_OK;
 }
 
+// column sums of a head-major [C/64][M][64] matrix (used by the attention backward's FFMA path for the qkv bias grad)
+int colsum_headmajor(const void* x, int dtype, int M, int C, float* db, cudaStream_t st) {
+  return colsum(x, dtype, layout_headmajor_rows_m(M), M, C, db, st);
+}
+
 // patches[(b*197 + t)][c*256 + i*16 + j] = image[b][c][py*16+i][px*16+j], t = 1 + py*14 + px; row t=0 zero.
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -217,10 +222,11 @@ extern "C" int vitk_linear_fwd(const void* x, int x_layout, const void* w, const
 }
 
 extern "C" int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, const void* gelu_grad,
-                                 int M, int N, int K, int dtype, int engine, void* stream) {
+                                 float* dx_colsum, int M, int N, int K, int dtype, int engine, void* stream) {
   VITK_CHECK_ARG(dy && w && dx && M > 0 && N > 0 && K > 0);
   VITK_CHECK_ARG(dtype == VITK_F32 || dtype == VITK_BF16);
   VITK_CHECK_ARG(dy_layout != VITK_LAYOUT_HEADMAJOR || N % 64 == 0);
+  VITK_CHECK_ARG(dx_colsum == nullptr || gelu_grad != nullptr);
   GemmProblem p{};
   p.I = M; p.J = K; p.R = N;
   p.A = dy; p.B = w; p.in_dtype = dtype;
@@ -229,7 +235,16 @@ extern "C" int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, v
   p.ep.out = dx; p.ep.ldc = K; p.ep.out_dtype = dtype;
   p.ep.mode = gelu_grad ? E_GELU_BWD : E_STORE;
   p.ep.aux = const_cast<void*>(gelu_grad);
-  return run_gemm(p, engine, 1, (cudaStream_t)stream);
+  // column sums of dX (= bias gradient of the Linear in front of the GELU): fused into the tcgen05 epilogue;
+  // the SIMT engine (fp32-validate) runs the reduction kernel on the finished output instead
+  int eng = engine == VITK_ENGINE_AUTO ? default_engine() : engine;
+  if (dtype == VITK_F32) eng = VITK_ENGINE_SIMT;
+  if (eng == VITK_ENGINE_AUTO) eng = VITK_ENGINE_TCGEN05;
+  p.ep.colsum = (eng == VITK_ENGINE_TCGEN05) ? dx_colsum : nullptr;
+  VITK_TRY(run_gemm(p, eng, 1, (cudaStream_t)stream));
+  if (dx_colsum && eng != VITK_ENGINE_TCGEN05)
+    VITK_TRY(colsum(dx, dtype, layout_rowmajor(K), M, K, dx_colsum, (cudaStream_t)stream));
+  return VITK_OK;
 }
 
 extern "C" int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, float* dw, float* db, int M, int N,

@@ -6,8 +6,8 @@
 namespace vitk {
 
 int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dtype, cudaStream_t st);
-int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
-                      int dtype, cudaStream_t st);
+int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                      float* dqkv_colsum, int batch, int dtype, cudaStream_t st);
 
 constexpr int D = VITK_DIM, NT = VITK_NTOK, MLP = VITK_MLP, HID = VITK_HEAD_HIDDEN;
 
@@ -60,7 +60,7 @@ struct Plan {
   size_t x_stride, act768_stride, qkv_stride, act3072_stride, stat_stride, lse_stride;
   size_t meanf, rstdf, feat, head_save;
   // backward transients
-  size_t dx, dx16, du, dh, dqkv, dfeat, dxc, ln_partial;
+  size_t dx, dx16, du, dh, dqkv, dfeat, dxc;
 };
 
 static void make_plan(int B, int depth, int precision, int training, int frozen, Plan* p) {
@@ -93,7 +93,6 @@ static void make_plan(int B, int depth, int precision, int training, int frozen,
   p->head_save = take(vitk_head_save_floats(B) * 4);
   p->dfeat = take((size_t)B * D * 4);
   p->dxc = take((size_t)B * D * 4);
-  p->ln_partial = take(vitk_layernorm_bwd_scratch_floats() * 4);
   if (save) {
     p->dx = take(M * D * 4);
     p->dx16 = take(M * D * T);
@@ -109,13 +108,20 @@ static void make_plan(int B, int depth, int precision, int training, int frozen,
 // dx[m][:] = (m % 197 == 0) ? dxc[m / 197][:] : 0 ; act copy alongside
 template <typename T>
 __global__ void __launch_bounds__(256)
-scatter_cls_grad_kernel(const float* __restrict__ dxc, float* __restrict__ dx, T* __restrict__ dx16, int64_t M) {
+scatter_cls_grad_kernel(const float* __restrict__ dxc, float* __restrict__ dx, T* __restrict__ dx16, int64_t M,
+                        float* __restrict__ colsum) {
   const int64_t total = M * (D / 4);
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = idx / (D / 4);
     const int c4 = (int)(idx % (D / 4));
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m % NT == 0) v = *reinterpret_cast<const float4*>(dxc + (m / NT) * D + c4 * 4);
+    if (m % NT == 0) {
+      v = *reinterpret_cast<const float4*>(dxc + (m / NT) * D + c4 * 4);
+      if (colsum) {  // bias gradient of the last block's fc2 (its dY is this scattered gradient)
+        atomicAdd(colsum + c4 * 4 + 0, v.x); atomicAdd(colsum + c4 * 4 + 1, v.y);
+        atomicAdd(colsum + c4 * 4 + 2, v.z); atomicAdd(colsum + c4 * 4 + 3, v.w);
+      }
+    }
     *reinterpret_cast<float4*>(dx + m * D + c4 * 4) = v;
     if (dx16) {
       uint2 u;
@@ -250,7 +256,6 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   float* dx = (float*)(ws + pl.dx);
   void* dxa = dt == VITK_BF16 ? (void*)(ws + pl.dx16) : (void*)dx;   // dx in the activation dtype
   void* dx16 = dt == VITK_BF16 ? (void*)(ws + pl.dx16) : nullptr;
-  float* part = (float*)(ws + pl.ln_partial);
 
   if (stage == 0) {
     float* dfeat = (float*)(ws + pl.dfeat);
@@ -261,11 +266,11 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
     float* xl = (float*)(ws + pl.x_in + pl.x_stride * (size_t)m->depth);
     float* dxc = (float*)(ws + pl.dxc);
     VITK_TRY(vitk_layernorm_bwd(dfeat, VITK_F32, xl, (int64_t)NT * D, c.P(po.normw), (float*)(ws + pl.meanf),
-                                (float*)(ws + pl.rstdf), nullptr, dxc, nullptr, c.G(po.normw), c.G(po.normb), part,
+                                (float*)(ws + pl.rstdf), nullptr, dxc, nullptr, c.G(po.normw), c.G(po.normb), nullptr,
                                 m->batch, st));
     const int64_t total = (int64_t)M * (D / 4);
     const int grid = (int)((total + 255) / 256 < (int64_t)sm_count() * 8 ? (total + 255) / 256 : (int64_t)sm_count() * 8);
-    scatter_cls_grad_kernel<bf16><<<grid, 256, 0, c.st>>>(dxc, dx, (bf16*)dx16, M);
+    scatter_cls_grad_kernel<bf16><<<grid, 256, 0, c.st>>>(dxc, dx, (bf16*)dx16, M, c.G(po.blk[m->depth - 1].fc2b));
     VITK_LAUNCH_CHECK();
     return VITK_OK;
   }
@@ -289,19 +294,25 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   void* dqkv = ws + pl.dqkv;
 
   // MLP:  x_out = x_mid + fc2(gelu(fc1(ln2(x_mid))))
-  VITK_TRY(vitk_linear_wgrad(dxa, VITK_LAYOUT_ROWMAJOR, g, c.G(b.fc2w), c.G(b.fc2b), M, D, MLP, dt, eng, st));
-  VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.fc2w), du, u, M, D, MLP, dt, eng, st));
-  VITK_TRY(vitk_linear_wgrad(du, VITK_LAYOUT_ROWMAJOR, ln2, c.G(b.fc1w), c.G(b.fc1b), M, MLP, D, dt, eng, st));
-  VITK_TRY(vitk_linear_dgrad(du, VITK_LAYOUT_ROWMAJOR, c.W(b.fc1w), dh, nullptr, M, MLP, D, dt, eng, st));
+  // (fc2 / proj bias gradients = column sums of the residual-stream gradient: produced by the kernel that wrote
+  //  it -- the LayerNorm backward below, or the CLS scatter for the last block)
+  VITK_TRY(vitk_linear_wgrad(dxa, VITK_LAYOUT_ROWMAJOR, g, c.G(b.fc2w), nullptr, M, D, MLP, dt, eng, st));
+  // fc1's bias gradient = column sums of du: fused into the epilogue of the GEMM that produces du
+  VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.fc2w), du, u, c.G(b.fc1b), M, D, MLP, dt, eng, st));
+  VITK_TRY(vitk_linear_wgrad(du, VITK_LAYOUT_ROWMAJOR, ln2, c.G(b.fc1w), nullptr, M, MLP, D, dt, eng, st));
+  VITK_TRY(vitk_linear_dgrad(du, VITK_LAYOUT_ROWMAJOR, c.W(b.fc1w), dh, nullptr, nullptr, M, MLP, D, dt, eng, st));
   VITK_TRY(vitk_layernorm_bwd(dh, dt, xmid, D, c.P(b.n2w), (float*)c.at(pl.mean2, pl.stat_stride, l),
-                              (float*)c.at(pl.rstd2, pl.stat_stride, l), dx, dx, dx16, c.G(b.n2w), c.G(b.n2b), part, M, st));
+                              (float*)c.at(pl.rstd2, pl.stat_stride, l), dx, dx, dx16, c.G(b.n2w), c.G(b.n2b), c.G(b.projb), M, st));
   // attention:  x_mid = x + proj(attn(qkv(ln1(x))))
-  VITK_TRY(vitk_linear_wgrad(dxa, VITK_LAYOUT_ROWMAJOR, ao, c.G(b.projw), c.G(b.projb), M, D, D, dt, eng, st));
-  VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.projw), dh, nullptr, M, D, D, dt, eng, st));
-  VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, m->batch, dt, c.st));
+  VITK_TRY(vitk_linear_wgrad(dxa, VITK_LAYOUT_ROWMAJOR, ao, c.G(b.projw), nullptr, M, D, D, dt, eng, st));
+  VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.projw), dh, nullptr, nullptr, M, D, D, dt, eng, st));
+  // (the qkv bias gradient stays a separate coalesced column-sum pass inside wgrad: fusing it into the mma.sync
+  //  attention kernel measured +48 us per layer against 16 us for the stand-alone reduction)
+  VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, nullptr, m->batch, dt, c.st));
   VITK_TRY(vitk_linear_wgrad(dqkv, VITK_LAYOUT_HEADMAJOR, ln1, c.G(b.qkvw), c.G(b.qkvb), M, 3 * D, D, dt, eng, st));
-  VITK_TRY(vitk_linear_dgrad(dqkv, VITK_LAYOUT_HEADMAJOR, c.W(b.qkvw), dh, nullptr, M, 3 * D, D, dt, eng, st));
+  VITK_TRY(vitk_linear_dgrad(dqkv, VITK_LAYOUT_HEADMAJOR, c.W(b.qkvw), dh, nullptr, nullptr, M, 3 * D, D, dt, eng, st));
   VITK_TRY(vitk_layernorm_bwd(dh, dt, x, D, c.P(b.n1w), (float*)c.at(pl.mean1, pl.stat_stride, l),
-                              (float*)c.at(pl.rstd1, pl.stat_stride, l), dx, dx, dx16, c.G(b.n1w), c.G(b.n1b), part, M, st));
+                              (float*)c.at(pl.rstd1, pl.stat_stride, l), dx, dx, dx16, c.G(b.n1w), c.G(b.n1b),
+                              l > 0 ? c.G(po.blk[l - 1].fc2b) : nullptr, M, st));
   return VITK_OK;
 }

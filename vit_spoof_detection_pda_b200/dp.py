@@ -10,6 +10,7 @@ bucket's wait is the only exposed communication.  Inference shards by batch with
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -75,13 +76,21 @@ class DataParallel(nn.Module):
     """``DataParallel(ViTFaceAntiSpoofing(...).cuda())``: identical replicas, local batch per rank,
     gradients averaged over ranks during backward."""
 
-    def __init__(self, module: nn.Module, process_group=None, bucket_mb: float = 50.0, broadcast: bool = True):
+    def __init__(self, module: nn.Module, process_group=None, bucket_mb: float = 50.0, broadcast: bool = True,
+                 comm_sms: Optional[int] = None):
         super().__init__()
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU, backend 'nccl')")
         self.module = module
         self.group = process_group
         self.bucketer = GradBucketer(int(bucket_mb * 1e6 / 4), process_group)
+        # SMs left to the NCCL all-reduce kernels while backward runs.  The persistent GEMM CTAs need a whole SM
+        # each (~225 KB smem); if NCCL's CTAs hold some SMs the GEMM grid must shrink by that many, or the CTAs
+        # that cannot become resident stall their tiles until the collective ends.  Set NCCL_MAX_CTAS (before
+        # init_process_group) to the same number so NCCL does not take more.
+        if comm_sms is None:
+            comm_sms = int(os.environ.get("NCCL_MAX_CTAS", "16"))
+        self.comm_sms = comm_sms if dist.get_world_size(process_group) > 1 else 0
         if broadcast:
             flat = module.flat_params()
             dist.broadcast(flat, src=0, group=process_group)
@@ -93,9 +102,20 @@ class DataParallel(nn.Module):
         if stage == 0:
             self.bucketer.reset()
         self.bucketer.add(flat_grad, lo, hi)
+        if self.comm_sms and self.bucketer._works:
+            # a collective is (or may still be) in flight: later stages size their persistent grids for the SMs left
+            from . import _lib as L
+            lib = L.load()
+            import ctypes as C
+            n = C.c_int(0)
+            lib.vitk_device_info(C.byref(n), None, None)
+            lib.vitk_set_sm_budget(max(1, n.value - self.comm_sms))
 
     def _on_finish(self, flat_grad: torch.Tensor):
         self.bucketer.finish(flat_grad)
+        if self.comm_sms:
+            from . import _lib as L
+            L.load().vitk_set_sm_budget(0)
 
     def forward(self, x):
         return self.module(x)
@@ -120,28 +140,45 @@ class DevicePrefetcher:
         self.loader = loader
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self._bufs = [None, None]          # two preallocated device slots (no allocator traffic in steady state)
+        self._free = [None, None]          # compute-stream event after which slot k may be overwritten
 
-    def _issue(self, batch):
+    def _issue(self, batch, slot):
+        dst = self._bufs[slot]
+        if dst is None or any(torch.is_tensor(s) and (d is None or d.shape != s.shape or d.dtype != s.dtype)
+                              for s, d in zip(batch, dst)) or len(dst) != len(batch):
+            dst = [torch.empty(s.shape, dtype=s.dtype, device=self.device) if torch.is_tensor(s) else None for s in batch]
+            self._bufs[slot] = dst
+        if self._free[slot] is not None:
+            self.stream.wait_event(self._free[slot])   # the step that last read this slot has finished on the GPU
         with torch.cuda.stream(self.stream):
-            out = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+            for s, d in zip(batch, dst):
+                if torch.is_tensor(s):
+                    d.copy_(s, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(self.stream)
+        out = tuple(d if torch.is_tensor(s) else s for s, d in zip(batch, dst))
         return out, ev
 
     def __iter__(self):
         it = iter(self.loader)
+        slot = 0
         try:
-            nxt = self._issue(next(it))
+            nxt = self._issue(next(it), slot)
         except StopIteration:
             return
         while nxt is not None:
             cur, ev = nxt
+            cur_slot = slot
+            slot ^= 1
             try:
-                nxt = self._issue(next(it))
+                nxt = self._issue(next(it), slot)      # copy of batch i+1 overlaps the compute of batch i
             except StopIteration:
                 nxt = None
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            for t in cur:
-                if torch.is_tensor(t):
-                    t.record_stream(torch.cuda.current_stream(self.device))
+            compute = torch.cuda.current_stream(self.device)
+            compute.wait_event(ev)
             yield cur
+            # everything the consumer enqueued for this batch is now in the compute stream: mark the slot reusable
+            done = torch.cuda.Event()
+            done.record(compute)
+            self._free[cur_slot] = done
