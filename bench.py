@@ -403,7 +403,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__), "--gpus", str(args.gpus),
                "--steps", str(args.steps), "--warmup", str(args.warmup)]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     run_ours(args)
 
 
