@@ -143,28 +143,47 @@ def test_linear_wgrad(case, M, N, Kd):
         assert K.rel_err(db, ref_b) < _tol(dtype)
 
 
+@pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("bn", [128, 192, 256])
-def test_tcgen05_forced_block_n_and_streamk(bn):
-    """Every BLOCK_N instantiation of the tcgen05 kernel, with and without stream-K (tcgen05 engine only)."""
+def test_tcgen05_forced_block_n_and_streamk(bn, cg):
+    """Every (BLOCK_N, CTA-group) instantiation of the tcgen05 kernel -- single CTAs (cta_group::1) and CTA pairs
+    (cta_group::2, 256-row tiles) -- with and without stream-K, all epilogues that touch a second operand."""
     lib = L.load()
-    M, N, Kd = 1576, 768, 768
+    M, N, Kd = 1576, 768, 768     # 6.16 tiles of 256 rows: partial last tile, second CTA of the last pair fully out of range
     x = randn(M, Kd, seed=91).to(torch.bfloat16)
     w = randn(N, Kd, seed=92, scale=0.05).to(torch.bfloat16)
     b = randn(N, seed=93, scale=0.5)
     dy = randn(M, N, seed=94).to(torch.bfloat16)
+    res = randn(M, N, seed=95)
+    u = randn(M, Kd, seed=96).to(torch.bfloat16)
     try:
         lib.vitk_debug_set(2, bn)
+        lib.vitk_debug_set(4, cg)
+        ref = x.float() @ w.float().t() + b
         y = K.linear_fwd(x, w, b, L.EPI_BIAS, L.ENGINE_TCGEN05)
-        assert K.rel_err(y.float(), x.float() @ w.float().t() + b) < BF16_TOL
+        assert K.rel_err(y.float(), ref) < BF16_TOL
+        y = K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, L.ENGINE_TCGEN05, residual=res)
+        assert K.rel_err(y, ref + res) < BF16_TOL
+        y = K.linear_fwd(x, w, b, L.EPI_QKV_SCATTER, L.ENGINE_TCGEN05)
+        assert K.rel_err(K.from_headmajor(y).float(), ref) < BF16_TOL
+        dref = dy.float() @ w.float()
         dx = K.linear_dgrad(dy, w, L.ENGINE_TCGEN05)
-        assert K.rel_err(dx.float(), dy.float() @ w.float()) < BF16_TOL
+        assert K.rel_err(dx.float(), dref) < BF16_TOL
+        dx, cs = K.linear_dgrad(dy, w, L.ENGINE_TCGEN05, gelu_grad=u, want_colsum=True)
+        assert K.rel_err(dx.float(), dref * u.float()) < BF16_TOL
+        assert K.rel_err(cs, dx.float().sum(0)) < 1e-3
+        dx = K.linear_dgrad(K.to_headmajor(dy), w, L.ENGINE_TCGEN05, dy_layout=L.LAYOUT_HEADMAJOR)
+        assert K.rel_err(dx.float(), dref) < BF16_TOL
         for streamk_off in (0, 1):
             lib.vitk_debug_set(1, streamk_off)
             dw, _ = K.linear_wgrad(dy, x, N, Kd, L.ENGINE_TCGEN05)
             assert K.rel_err(dw, dy.float().t() @ x.float()) < BF16_TOL
+            dw, _ = K.linear_wgrad(K.to_headmajor(dy), x, N, Kd, L.ENGINE_TCGEN05, dy_layout=L.LAYOUT_HEADMAJOR)
+            assert K.rel_err(dw, dy.float().t() @ x.float()) < BF16_TOL
     finally:
         lib.vitk_debug_set(1, 0)
         lib.vitk_debug_set(2, 0)
+        lib.vitk_debug_set(4, 0)
 
 
 # ------------------------------------------------------------------ attention
@@ -173,7 +192,7 @@ def _attn_ref(q, k, v):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B", [1, 3])
+@pytest.mark.parametrize("B", [1, 3, 26])   # 26: 312 (batch, head) items > 148 persistent CTAs -> prefetch path
 def test_attention_fwd_bwd(dtype, B):
     M = B * 197
     qkv = randn(M, 2304, seed=41).to(dtype)

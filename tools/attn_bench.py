@@ -37,12 +37,11 @@ def timeit(fn, n=20):
     return tot / n * 1e3
 
 
-fwd = timeit(lambda: lib.vitk_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, L.BF16, st))
-print(f"attn fwd  B={B}: {fwd:7.1f} us  ({B*12*4*197*197*64/fwd/1e6:.1f} TFLOP/s algorithmic)")
-for variant in (0, 1):
+for variant in (0, 2):   # 0: persistent 13-warp kernels, 2: first-generation kernels
     lib.vitk_debug_set(3, variant)
-    for with_cs in (False, True):
-        t = timeit(lambda: lib.vitk_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-                                             cs.data_ptr() if with_cs else None, B, L.BF16, st))
-        print(f"attn bwd  B={B} variant {variant} colsum {with_cs}: {t:7.1f} us  ({B*12*10*197*197*64/t/1e6:.1f} TFLOP/s algorithmic 10*N^2*d)")
+    fwd = timeit(lambda: lib.vitk_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, L.BF16, st))
+    print(f"variant {variant} attn fwd  B={B}: {fwd:7.1f} us  ({B*12*4*197*197*64/fwd/1e6:.1f} TFLOP/s algorithmic)")
+    t = timeit(lambda: lib.vitk_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                         None, B, L.BF16, st))
+    print(f"variant {variant} attn bwd  B={B}: {t:7.1f} us  ({B*12*10*197*197*64/t/1e6:.1f} TFLOP/s algorithmic 10*N^2*d)")
 lib.vitk_debug_set(3, 0)

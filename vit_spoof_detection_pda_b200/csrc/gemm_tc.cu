@@ -12,7 +12,12 @@
 // contiguous: dgrad's W, wgrad's dY^T and X) -- the major-ness is a bit in the instruction descriptor
 // plus the canonical 128B-swizzle shared-memory layout the TMA boxes are written in -- and may be stored
 // head-major ([C/64][M][64], q/k/v and their gradients), which is just a different 3-D tensor map.
-// Work: output tiles strided over the persistent CTAs; accumulate epilogues (wgrad) instead use stream-K --
+// CTA pairs (template CG = 2, the default for every shape with >= 2 x 128 rows): the two CTAs of a 2-cluster own
+// one 256 x BN tile -- each stages its own 128 rows of A and HALF of the B tile, the leader's elected lane issues
+// tcgen05.mma.cta_group::2 (M = 256) against both shared memories and multicasts its commits to both CTAs' barriers.
+// Per CTA and k-block that is 128 + BN/2 operand rows from L2 instead of 128 + BN: the kernel is bound by L2->SM
+// bandwidth (~6.3 KB/clk chip-wide), not by the tensor pipe, so this is what moves it.
+// Work: output tiles strided over the persistent CTAs (CTA pairs); accumulate epilogues (wgrad) instead use stream-K --
 // the (tile, k-block) space is cut into one equal contiguous range per CTA and partial tiles are summed
 // with fp32 vector atomics, so 18..72-tile weight-gradient GEMMs still load all 148 SMs evenly.
 //
@@ -75,6 +80,41 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// 2-CTA variant: the transaction bytes land on the mbarrier of the pair's leader CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -245,26 +285,34 @@ __device__ __forceinline__ void epilogue_rows8(const EpiParams& ep, int i, int j
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN> struct TcCfg {
-  static constexpr uint32_t B_STAGE_BYTES = BN * TC_BK * 2;
+template <int BN, int CG> struct TcCfg {
+  static constexpr int B_ROWS = BN / CG;                                   // rows of the B tile this CTA stages
+  static constexpr uint32_t B_STAGE_BYTES = B_ROWS * TC_BK * 2;
   static constexpr uint32_t STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 192) ? 4 : 6;
+  static constexpr int STAGES_FIT = (227 * 1024 - 1024 - 256 - TC_EPI_WARPS * 4096) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // double-buffered accumulator, power of two
   static constexpr uint32_t EPI_OFF = STAGES * STAGE_BYTES + 256;  // TC_EPI_WARPS x 4 KB transpose buffers after the barriers
   static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)EPI_OFF + TC_EPI_WARPS * 4096;
 };
 
+template <int CG>
+__device__ __forceinline__ void tc_tma(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  if constexpr (CG == 2) tma_load_3d_2cta(dst, map, bar, c0, c1, c2);
+  else tma_load_3d(dst, map, bar, c0, c1, c2);
+}
+template <int CG>
 __device__ __forceinline__ void tc_issue_operand_loads(const CUtensorMap* map, int mode, uint32_t dst, uint32_t bar,
                                                        int row0, int rows_in_tile, int r0) {
   // K-major: one box [rows_in_tile][64 r]; MN-major: rows_in_tile/64 boxes [64 r][64 rows], 8 KB apart
   if (mode == OP_KM_FLAT) {
-    tma_load_3d(dst, map, bar, r0, row0, 0);
+    tc_tma<CG>(dst, map, bar, r0, row0, 0);
   } else if (mode == OP_KM_SPLIT) {
-    tma_load_3d(dst, map, bar, 0, row0, r0 >> 6);
+    tc_tma<CG>(dst, map, bar, 0, row0, r0 >> 6);
   } else if (mode == OP_MN_FLAT) {
-    for (int a = 0; a < rows_in_tile / 64; ++a) tma_load_3d(dst + a * 8192, map, bar, row0 + a * 64, r0, 0);
+    for (int a = 0; a < rows_in_tile / 64; ++a) tc_tma<CG>(dst + a * 8192, map, bar, row0 + a * 64, r0, 0);
   } else {
-    for (int a = 0; a < rows_in_tile / 64; ++a) tma_load_3d(dst + a * 8192, map, bar, 0, r0, (row0 >> 6) + a);
+    for (int a = 0; a < rows_in_tile / 64; ++a) tc_tma<CG>(dst + a * 8192, map, bar, 0, r0, (row0 >> 6) + a);
   }
 }
 
@@ -274,14 +322,18 @@ struct TcWork {
 };
 struct TcWorkIter {
   int64_t cur, end;  // stream-K: unit cursor / end ; tile-strided: next tile / number of tiles
-  __device__ __forceinline__ void init(const TcParams& p) {
+  int stride;
+  // `cg` CTAs (one cluster) walk the same sequence
+  __device__ __forceinline__ void init(const TcParams& p, int cg) {
     const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n;
+    const int cluster = blockIdx.x / cg;
+    stride = gridDim.x / cg;
     if (p.streamk) {
       const int64_t total = tiles * p.kb_total;
-      cur = (int64_t)blockIdx.x * p.units_per_cta;
+      cur = (int64_t)cluster * p.units_per_cta;
       end = cur + p.units_per_cta < total ? cur + p.units_per_cta : total;
     } else {
-      cur = blockIdx.x;
+      cur = cluster;
       end = tiles;
     }
   }
@@ -297,16 +349,16 @@ struct TcWorkIter {
       w.tile = (int)cur;
       w.kb0 = 0;
       w.kb1 = p.kb_total;
-      cur += gridDim.x;
+      cur += stride;
     }
     return true;
   }
 };
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
@@ -319,6 +371,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA pair: rank 0 (leader) owns the barriers the pair shares -- `full` (TMA bytes of both CTAs) and `tmem_empty`
+  // (epilogue warps of both CTAs); `empty` and `tmem_full` exist in both CTAs and are signalled by multicast commits.
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -329,52 +384,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), TC_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), CG * TC_EPI_WARPS);  // one arrive per epilogue warp of every CTA of the pair
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
-                 "r"(Cfg::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                   "r"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                   "r"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // peer barriers initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A rows and its share of the B rows) ==========
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       TcWorkIter wi;
-      wi.init(p);
+      wi.init(p, CG);
       TcWork w;
       while (wi.next(p, w)) {
         const int tile = w.tile;
-        const int i0 = (tile / p.n_tiles_n) * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
+        const int i0 = (tile / p.n_tiles_n) * (TC_BM * CG) + (int)rank * TC_BM;
+        const int j0 = (tile % p.n_tiles_n) * BN + (int)rank * Cfg::B_ROWS;
         const int kb0 = w.kb0, kb1 = w.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), CG * Cfg::STAGE_BYTES);
+          const uint32_t fb = CG == 2 ? mapa_u32(full_bar(stage), 0) : full_bar(stage);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          tc_issue_operand_loads(&map_a, p.a_mode, sa, full_bar(stage), i0, TC_BM, kb * TC_BK);
-          tc_issue_operand_loads(&map_b, p.b_mode, sa + TC_A_STAGE_BYTES, full_bar(stage), j0, BN, kb * TC_BK);
+          tc_issue_operand_loads<CG>(&map_a, p.a_mode, sa, fb, i0, TC_BM, kb * TC_BK);
+          tc_issue_operand_loads<CG>(&map_b, p.b_mode, sa + TC_A_STAGE_BYTES, fb, j0, Cfg::B_ROWS, kb * TC_BK);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      if constexpr (CG == 2) {
+        // tail: the leader's last multicast commits must have landed in this CTA's `empty` barriers before it may exit
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       TcWorkIter wi;
-      wi.init(p);
+      wi.init(p, CG);
       TcWork w;
       while (wi.next(p, w)) {
         const int kb0 = w.kb0, kb1 = w.kb1;
@@ -390,12 +459,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * p.a_kstep, p.a_lbo, p.a_sbo);
             const uint64_t bdesc = make_smem_desc(sb + k * p.b_kstep, p.b_lbo, p.b_sbo);
-            tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2) tc_mma_bf16_2cta(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+          // smem slot free (in both CTAs) once these MMAs retire
+          if constexpr (CG == 2) tc_commit_2cta(empty_bar(stage)); else tc_commit(empty_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar(acc));      // accumulator complete
+        // accumulator complete (both CTAs' epilogues)
+        if constexpr (CG == 2) tc_commit_2cta(tfull_bar(acc)); else tc_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -406,11 +478,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     TcWorkIter wi;
-    wi.init(p);
+    wi.init(p, CG);
     TcWork w;
     while (wi.next(p, w)) {
       const int tile = w.tile;
-      const int i0 = (tile / p.n_tiles_n) * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
+      const int i0 = (tile / p.n_tiles_n) * (TC_BM * CG) + (int)rank * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
       // While the MMAs of this tile still run: pull the epilogue's second operand (saved gelu' / fp32 residual)
       // for this warp's 32 rows into L2, so the dependent loads below are L2 hits instead of HBM round trips.
       if (p.ep.mode == E_GELU_BWD || p.ep.mode == E_BIAS_RESIDUAL) {
@@ -429,37 +501,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       float4* tb = reinterpret_cast<float4*>(smem + Cfg::EPI_OFF + (uint32_t)(warp - TC_EPI_WARP0) * 4096u);
       const int sub_row = lane >> 3, c4 = lane & 7;
+      if (i0 + q * 32 < p.I) {   // warps whose 32 rows are all past the end of the matrix have nothing to write
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
-        uint32_t raw[32];
-        tc_ld32(taddr + c * 32, raw);
-        // row `lane` of the 32x32 chunk -> swizzled smem (16-byte column group cg at cg ^ (row & 7))
+        for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
+          uint32_t raw[32];
+          tc_ld32(taddr + c * 32, raw);
+          // row `lane` of the 32x32 chunk -> swizzled smem (16-byte column group cg at cg ^ (row & 7))
 #pragma unroll
-        for (int cg = 0; cg < 8; ++cg)
-          tb[lane * 8 + (cg ^ (lane & 7))] = make_float4(__uint_as_float(raw[cg * 4]), __uint_as_float(raw[cg * 4 + 1]),
-                                                         __uint_as_float(raw[cg * 4 + 2]), __uint_as_float(raw[cg * 4 + 3]));
-        __syncwarp();
-        float4 v[8];
+          for (int cg = 0; cg < 8; ++cg)
+            tb[lane * 8 + (cg ^ (lane & 7))] = make_float4(__uint_as_float(raw[cg * 4]), __uint_as_float(raw[cg * 4 + 1]),
+                                                           __uint_as_float(raw[cg * 4 + 2]), __uint_as_float(raw[cg * 4 + 3]));
+          __syncwarp();
+          float4 v[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + sub_row;
-          v[it] = tb[r * 8 + (c4 ^ (r & 7))];
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + sub_row;
+            v[it] = tb[r * 8 + (c4 ^ (r & 7))];
+          }
+          __syncwarp();
+          epilogue_rows8(p.ep, i0 + q * 32 + sub_row, j0 + c * 32 + c4 * 4, p.I, v);
         }
-        __syncwarp();
-        epilogue_rows8(p.ep, i0 + q * 32 + sub_row, j0 + c * 32 + c4 * 4, p.I, v);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0));
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody exits while its peer may still touch it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -531,23 +611,23 @@ static int make_operand_map(const void* base, const MatLayout& l, int rows, int 
 static int g_tc_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 int attn_debug_variant() { return g_tc_debug[3]; }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    VITK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     configured = true;
   }
   CUtensorMap map_a, map_b;
   TcParams p{};
   p.I = pr.I; p.J = pr.J; p.R = pr.R;
   VITK_TRY(make_operand_map(pr.A, pr.la, pr.I, pr.R, TC_BM, &map_a, &p.a_mode));
-  VITK_TRY(make_operand_map(pr.B, pr.lb, pr.J, pr.R, BN, &map_b, &p.b_mode));
+  VITK_TRY(make_operand_map(pr.B, pr.lb, pr.J, pr.R, Cfg::B_ROWS, &map_b, &p.b_mode));
   const bool a_mn = p.a_mode >= OP_MN_FLAT, b_mn = p.b_mode >= OP_MN_FLAT;
-  // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+  // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4 (M = 128 per CTA: 256 for a CTA pair)
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * CG) >> 4) << 24);
   // canonical SWIZZLE_128B layouts: K-major: 8-row groups 1024 B apart (SBO), LBO unused;
   // MN-major: 8-r groups 1024 B apart (SBO), 64-wide MN atoms TC_BK*128 B apart (LBO)
   p.a_sbo = 1024; p.a_lbo = a_mn ? TC_BK * 128 : 16; p.a_kstep = a_mn ? 16 * 128 : 32;
@@ -556,23 +636,33 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
     if (a_mn) { p.a_sbo = TC_BK * 128; p.a_lbo = 1024; }
     if (b_mn) { p.b_sbo = TC_BK * 128; p.b_lbo = 1024; }
   }
-  p.n_tiles_m = (pr.I + TC_BM - 1) / TC_BM;
+  p.n_tiles_m = (pr.I + TC_BM * CG - 1) / (TC_BM * CG);
   p.n_tiles_n = pr.J / BN;
   p.kb_total = (pr.R + TC_BK - 1) / TC_BK;
   const int tiles = p.n_tiles_m * p.n_tiles_n;
-  const int sms = sm_count();
-  int grid = tiles < sms ? tiles : sms;
+  const int slots = sm_count() / CG;            // persistent CTAs (CTA pairs)
+  int grid = tiles < slots ? tiles : slots;
   p.streamk = 0;
   p.units_per_cta = 0;
   if (pr.ep.mode == E_ACCUM && g_tc_debug[1] != 1) {
     const int64_t total = (int64_t)tiles * p.kb_total;
-    grid = total < sms ? (int)total : sms;
+    grid = total < slots ? (int)total : slots;
     p.streamk = 1;
     p.units_per_cta = (total + grid - 1) / grid;
     grid = (int)((total + p.units_per_cta - 1) / p.units_per_cta);
   }
   p.ep = pr.ep;
-  gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(map_a, map_b, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid * CG, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  VITK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, map_a, map_b, p));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -583,30 +673,47 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
   if (pr.ep.mode != E_STORE && pr.ep.mode != E_ACCUM && pr.ep.mode != E_BIAS_RESIDUAL && pr.ep.mode != E_PATCH &&
       pr.ep.out_dtype != VITK_BF16) { set_error("gemm_tc: epilogue expects bf16 output"); return VITK_ERR_UNSUPPORTED; }
   if (pr.J % 128 != 0 || pr.ep.ldc % 8 != 0) { set_error("gemm_tc: J must be a multiple of 128 (got %d)", pr.J); return VITK_ERR_UNSUPPORTED; }
-  // BLOCK_N: minimise (waves of the persistent grid) x (tile cost ~ BN + fixed per-tile overhead); with
-  // M = B*197 the tile count is rarely a multiple of 148 SMs, e.g. 12608x768: 297 tiles of 128x256 = 3 waves
-  // for 2.007 waves of work, 396 tiles of 128x192 = 3 waves of 3/4 the cost.
-  int bn = 0;
-  if (g_tc_debug[2] == 128 || g_tc_debug[2] == 192 || g_tc_debug[2] == 256) {
-    bn = g_tc_debug[2];
-  } else if (pr.ep.mode == E_ACCUM) {
-    bn = pr.J % 256 == 0 ? 256 : 128;  // stream-K balances by itself
+  // Tile shape: CTA pair (CG = 2, 256 x BN) or single CTA (128 x BN), BN in {256, 192, 128}.  The kernel is bound by
+  // L2->SM operand traffic long before the tensor pipe: per CTA and 64-deep k-block it pulls (128 + BN/CG) rows of
+  // 128 B at ~42.5 B/clk/SM (6.3 KB/clk chip-wide, B300_MICROARCH.md) while the MMAs need 2*BN clk.  Pick the
+  // candidate that minimises waves x k-blocks x max(L2, MMA) clocks; with M = B*197 the tile count is rarely a
+  // multiple of the slot count, so the wave term matters (12608 x 768 on 74 pairs: 150 tiles of 256x256 = 3 waves for
+  // 2.03 waves of work, 200 tiles of 256x192 = 3 waves of 3/4 the cost).
+  const bool b_mn = pr.lb.s_row == 1 && pr.lb.s_col != 1;   // MN-major B: staged in 64-row atoms
+  int cg = 0, bn = 0;
+  const int forced_bn = (g_tc_debug[2] == 128 || g_tc_debug[2] == 192 || g_tc_debug[2] == 256) ? g_tc_debug[2] : 0;
+  if (pr.ep.mode == E_ACCUM) {
+    bn = forced_bn ? forced_bn : (pr.J % 256 == 0 ? 256 : 128);  // stream-K balances by itself
+    cg = (pr.I > TC_BM && g_tc_debug[4] != 1 && !(b_mn && (bn / 2) % 64 != 0)) ? 2 : 1;
   } else {
-    const int sms = sm_count();
-    const long tiles_m = (pr.I + TC_BM - 1) / TC_BM;
-    long best = -1;
-    for (int cand : {256, 192, 128}) {
-      if (pr.J % cand != 0) continue;
-      const long tiles = tiles_m * (pr.J / cand);
-      const long waves = (tiles + sms - 1) / sms;
-      const long cost = waves * (cand + 32);
-      if (best < 0 || cost < best) { best = cost; bn = cand; }
+    const long kb = (pr.R + TC_BK - 1) / TC_BK;
+    double best = -1.0;
+    for (int c : {2, 1}) {
+      if (c == 2 && (pr.I <= TC_BM || g_tc_debug[4] == 1)) continue;
+      if (c == 1 && g_tc_debug[4] == 2 && best >= 0.0) continue;   // debug: pairs forced (when expressible)
+      const long slots = sm_count() / c;
+      const long tiles_m = (pr.I + TC_BM * c - 1) / (TC_BM * c);
+      for (int cand : {256, 192, 128}) {
+        if (pr.J % cand != 0) continue;
+        if (b_mn && (cand / c) % 64 != 0) continue;
+        if (forced_bn && forced_bn != cand) continue;
+        const long tiles = tiles_m * (pr.J / cand);
+        const long waves = (tiles + slots - 1) / slots;
+        const double l2 = (128.0 + cand / c) * 128.0 / 42.5, mma = 2.0 * cand;
+        const double cost = (double)waves * ((double)kb * (l2 > mma ? l2 : mma) + 600.0);
+        if (best < 0.0 || cost < best) { best = cost; bn = cand; cg = c; }
+      }
     }
   }
   if (bn == 0 || pr.J % bn != 0) { set_error("gemm_tc: no BLOCK_N divides J=%d", pr.J); return VITK_ERR_UNSUPPORTED; }
-  if (bn == 256) return launch_tc<256>(pr, st);
-  if (bn == 192) return launch_tc<192>(pr, st);
-  return launch_tc<128>(pr, st);
+  if (cg == 2) {
+    if (bn == 256) return launch_tc<256, 2>(pr, st);
+    if (bn == 192) return launch_tc<192, 2>(pr, st);
+    return launch_tc<128, 2>(pr, st);
+  }
+  if (bn == 256) return launch_tc<256, 1>(pr, st);
+  if (bn == 192) return launch_tc<192, 1>(pr, st);
+  return launch_tc<128, 1>(pr, st);
 }
 
 }  // namespace vitk
