@@ -39,9 +39,16 @@ constexpr uint32_t TC_A_STAGE_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 // operand addressing modes (see header comment)
 enum { OP_KM_FLAT = 0, OP_KM_SPLIT = 1, OP_MN_FLAT = 2, OP_MN_SPLIT = 3 };
 
+// Branch-free TMA coordinates of one operand: box `a` of k-block `kb` of the tile whose first row is `row0` is at
+//   c0 = row0*fr0 + kb*d0 + a*e0,  c1 = row0*fr1 + kb*d1,  c2 = (row0>>6)*fr2 + kb*d2 + a*e2     (boxes 8 KB apart in smem)
+struct OpCoord {
+  int32_t fr0, fr1, fr2, d0, d1, d2, e0, e2, nbox;
+};
+
 struct TcParams {
   int32_t I, J, R;
   int32_t a_mode, b_mode;
+  OpCoord ca, cb;
   int32_t n_tiles_m, n_tiles_n, kb_total;
   int32_t streamk;          // 0: tile-strided, full K per tile; 1: contiguous (tile, k-block) unit range per CTA
   int64_t units_per_cta;    // stream-K: ceil(tiles * kb_total / gridDim.x)
@@ -116,6 +123,40 @@ __device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t tmem_d, uint64_t adesc
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+// tcgen05.mma with the 64-bit descriptors assembled from a constant high word and a running low word
+__device__ __forceinline__ void tc_mma_desc(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accum, bool pair) {
+  if (pair)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum) : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -140,6 +181,45 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// TMA store / load of epilogue tiles (2-D row-major, 3-D head-major) and bulk-group bookkeeping
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
 // 64-bit shared-memory matrix descriptor (SWIZZLE_128B, version 1 = Blackwell)
@@ -285,15 +365,27 @@ __device__ __forceinline__ void epilogue_rows8(const EpiParams& ep, int i, int j
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+// Epilogue kinds (compile-time).  All but EK_LEGACY move the output through shared memory and TMA:
+// tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns); the lane applies the epilogue math,
+// writes its row into a swizzled 32 x 32 staging tile and one elected lane issues a cp.async.bulk.tensor store
+// (rows past the end of the matrix are clipped by the tensor map).  Second operands (fp32 residual, saved gelu')
+// arrive the same way: a TMA load into the staging tile issued BEFORE the accumulator is ready, combined in place.
+// No per-thread global loads/stores and no global-memory latency remain on the epilogue warps' critical path.
+enum { EK_LEGACY = 0, EK_STORE_BF16 = 1, EK_STORE_F32 = 2, EK_GELU = 3, EK_RESIDUAL = 4, EK_SCATTER = 5, EK_GELU_BWD = 6 };
+constexpr uint32_t TC_EPI_WARP_BYTES = 8192;   // per epilogue warp: 2 slots x 4 KB (fp32 tile) or 4 x 2 KB (bf16 tiles)
+
 template <int BN, int CG> struct TcCfg {
   static constexpr int B_ROWS = BN / CG;                                   // rows of the B tile this CTA stages
   static constexpr uint32_t B_STAGE_BYTES = B_ROWS * TC_BK * 2;
   static constexpr uint32_t STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES_FIT = (227 * 1024 - 1024 - 256 - TC_EPI_WARPS * 4096) / STAGE_BYTES;
+  static constexpr uint32_t TAIL_BYTES = TC_EPI_WARPS * TC_EPI_WARP_BYTES + TC_EPI_WARPS * 512 + 512;  // staging | bias | barriers
+  static constexpr int STAGES_FIT = (227 * 1024 - 1024 - (int)TAIL_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // double-buffered accumulator, power of two
-  static constexpr uint32_t EPI_OFF = STAGES * STAGE_BYTES + 256;  // TC_EPI_WARPS x 4 KB transpose buffers after the barriers
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)EPI_OFF + TC_EPI_WARPS * 4096;
+  static constexpr uint32_t EPI_OFF = STAGES * STAGE_BYTES;                                  // 1024-aligned staging tiles
+  static constexpr uint32_t BIAS_OFF = EPI_OFF + TC_EPI_WARPS * TC_EPI_WARP_BYTES;           // 512 B per epilogue warp
+  static constexpr uint32_t BAR_OFF = BIAS_OFF + TC_EPI_WARPS * 512;
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + TAIL_BYTES;
 };
 
 template <int CG>
@@ -355,20 +447,26 @@ struct TcWorkIter {
   }
 };
 
-template <int BN, int CG>
+// shared-memory offsets of lane `r`'s row inside a 32-row staging tile
+__device__ __forceinline__ uint32_t row_off_64(int r, int k4) { return (uint32_t)(r * 64 + ((k4 ^ ((r >> 1) & 3)) << 4)); }   // bf16, SWIZZLE_64B
+__device__ __forceinline__ uint32_t row_off_128(int r, int k8) { return (uint32_t)(r * 128 + ((k8 ^ (r & 7)) << 4)); }        // fp32, SWIZZLE_128B
+
+template <int BN, int CG, int EK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_d, const TcParams p) {
   using Cfg = TcCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  // barrier layout: full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  const uint32_t bar_base = smem_base + Cfg::BAR_OFF;
+  // barrier layout: full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | epi_load[8 warps][2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
+  auto eload_bar = [&](int we, int s) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + we * 2 + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Cfg::BAR_OFF + 8 * (2 * Cfg::STAGES + 4 + 2 * TC_EPI_WARPS));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA pair: rank 0 (leader) owns the barriers the pair shares -- `full` (TMA bytes of both CTAs) and `tmem_empty`
@@ -378,6 +476,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    if constexpr (EK != EK_LEGACY) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_d)) : "memory");
+    }
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -386,6 +488,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), CG * TC_EPI_WARPS);  // one arrive per epilogue warp of every CTA of the pair
     }
+    for (int s = 0; s < 2 * TC_EPI_WARPS; ++s) mbar_init(eload_bar(0, s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -406,24 +509,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of the B rows) ==========
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers); one elected
+    // lane arms the barrier and issues the copies.  Coordinates advance by additions only (OpCoord).
+    {
       int stage = 0;
       uint32_t phase = 0;
       TcWorkIter wi;
       wi.init(p, CG);
       TcWork w;
+      const bool leader = elect_one();
       while (wi.next(p, w)) {
         const int tile = w.tile;
         const int i0 = (tile / p.n_tiles_n) * (TC_BM * CG) + (int)rank * TC_BM;
         const int j0 = (tile % p.n_tiles_n) * BN + (int)rank * Cfg::B_ROWS;
         const int kb0 = w.kb0, kb1 = w.kb1;
+        int a0 = i0 * p.ca.fr0 + kb0 * p.ca.d0, a1 = i0 * p.ca.fr1 + kb0 * p.ca.d1, a2 = (i0 >> 6) * p.ca.fr2 + kb0 * p.ca.d2;
+        int b0 = j0 * p.cb.fr0 + kb0 * p.cb.d0, b1 = j0 * p.cb.fr1 + kb0 * p.cb.d1, b2 = (j0 >> 6) * p.cb.fr2 + kb0 * p.cb.d2;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          if (rank == 0) mbar_expect_tx(full_bar(stage), CG * Cfg::STAGE_BYTES);
-          const uint32_t fb = CG == 2 ? mapa_u32(full_bar(stage), 0) : full_bar(stage);
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          tc_issue_operand_loads<CG>(&map_a, p.a_mode, sa, fb, i0, TC_BM, kb * TC_BK);
-          tc_issue_operand_loads<CG>(&map_b, p.b_mode, sa + TC_A_STAGE_BYTES, fb, j0, Cfg::B_ROWS, kb * TC_BK);
+          if (leader) {
+            if (rank == 0) mbar_expect_tx(full_bar(stage), CG * Cfg::STAGE_BYTES);
+            const uint32_t fb = CG == 2 ? mapa_u32(full_bar(stage), 0) : full_bar(stage);
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+              if (a < p.ca.nbox) tc_tma<CG>(sa + a * 8192, &map_a, fb, a0 + a * p.ca.e0, a1, a2 + a * p.ca.e2);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              if (a < p.cb.nbox) tc_tma<CG>(sa + TC_A_STAGE_BYTES + a * 8192, &map_b, fb, b0 + a * p.cb.e0, b1, b2 + a * p.cb.e2);
+          }
+          __syncwarp();
+          a0 += p.ca.d0; a1 += p.ca.d1; a2 += p.ca.d2;
+          b0 += p.cb.d0; b1 += p.cb.d1; b2 += p.cb.d2;
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -437,7 +554,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    // One elected lane issues; the warp stays converged so descriptor arithmetic lives in uniform registers.  The
+    // 64-bit smem descriptors are a constant high word plus a low word that advances by (bytes >> 4) per UMMA_K step:
+    // the issue loop must stay far below the 2*BN tensor clocks one k-block takes, or it -- not the tensor pipe --
+    // bounds the kernel.
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -445,90 +566,242 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       TcWorkIter wi;
       wi.init(p, CG);
       TcWork w;
+      const bool leader = elect_one();
+      const uint32_t a_hi = ((p.a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+      const uint32_t b_hi = ((p.b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((smem_base >> 4) & 0x3FFFu) | (((p.a_lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t b_lo0 = (((smem_base + TC_A_STAGE_BYTES) >> 4) & 0x3FFFu) | (((p.b_lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t a_ks = p.a_kstep >> 4, b_ks = p.b_kstep >> 4;
       while (wi.next(p, w)) {
-        const int kb0 = w.kb0, kb1 = w.kb1;
+        const int nkb = w.kb1 - w.kb0;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sb = sa + TC_A_STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * p.a_kstep, p.a_lbo, p.a_sbo);
-            const uint64_t bdesc = make_smem_desc(sb + k * p.b_kstep, p.b_lbo, p.b_sbo);
-            if constexpr (CG == 2) tc_mma_bf16_2cta(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if (leader) {
+            const uint32_t so = (uint32_t)stage * (Cfg::STAGE_BYTES >> 4);
+            const uint32_t al = a_lo0 + so, bl = b_lo0 + so;
+            tc_mma_desc(d_tmem, al, a_hi, bl, b_hi, p.idesc, kb > 0 ? 1u : 0u, CG == 2);
+            tc_mma_desc(d_tmem, al + a_ks, a_hi, bl + b_ks, b_hi, p.idesc, 1u, CG == 2);
+            tc_mma_desc(d_tmem, al + 2 * a_ks, a_hi, bl + 2 * b_ks, b_hi, p.idesc, 1u, CG == 2);
+            tc_mma_desc(d_tmem, al + 3 * a_ks, a_hi, bl + 3 * b_ks, b_hi, p.idesc, 1u, CG == 2);
+            // smem slot free (in both CTAs) once these MMAs retire
+            if constexpr (CG == 2) tc_commit_2cta(empty_bar(stage)); else tc_commit(empty_bar(stage));
+            if (kb + 1 == nkb) {   // accumulator complete (both CTAs' epilogues)
+              if constexpr (CG == 2) tc_commit_2cta(tfull_bar(acc)); else tc_commit(tfull_bar(acc));
+            }
           }
-          // smem slot free (in both CTAs) once these MMAs retire
-          if constexpr (CG == 2) tc_commit_2cta(empty_bar(stage)); else tc_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete (both CTAs' epilogues)
-        if constexpr (CG == 2) tc_commit_2cta(tfull_bar(acc)); else tc_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may touch
-    const int half = (warp - TC_EPI_WARP0) >> 2;  // which interleaved set of column chunks
+    const int we = warp - TC_EPI_WARP0;
+    const int q = warp & 3;      // TMEM lane quarter this warp may touch
+    const int half = we >> 2;    // which interleaved set of 32-column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
     TcWorkIter wi;
     wi.init(p, CG);
     TcWork w;
-    while (wi.next(p, w)) {
-      const int tile = w.tile;
-      const int i0 = (tile / p.n_tiles_n) * (TC_BM * CG) + (int)rank * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
-      // While the MMAs of this tile still run: pull the epilogue's second operand (saved gelu' / fp32 residual)
-      // for this warp's 32 rows into L2, so the dependent loads below are L2 hits instead of HBM round trips.
-      if (p.ep.mode == E_GELU_BWD || p.ep.mode == E_BIAS_RESIDUAL) {
-        const int elt = p.ep.mode == E_GELU_BWD ? 2 : 4;
-        const char* src = p.ep.mode == E_GELU_BWD ? reinterpret_cast<const char*>(p.ep.aux)
-                                                  : reinterpret_cast<const char*>(p.ep.residual);
-        const int lines = BN * elt / 128;
-        for (int idx = half * 32 + lane; idx < 32 * lines; idx += 64) {
-          const int row = i0 + q * 32 + idx / lines;
-          if (row < p.I)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((int64_t)row * p.ep.ldc + j0) * elt + (idx % lines) * 128));
-        }
-      }
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      float4* tb = reinterpret_cast<float4*>(smem + Cfg::EPI_OFF + (uint32_t)(warp - TC_EPI_WARP0) * 4096u);
-      const int sub_row = lane >> 3, c4 = lane & 7;
-      if (i0 + q * 32 < p.I) {   // warps whose 32 rows are all past the end of the matrix have nothing to write
-#pragma unroll 1
-        for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
-          uint32_t raw[32];
-          tc_ld32(taddr + c * 32, raw);
-          // row `lane` of the 32x32 chunk -> swizzled smem (16-byte column group cg at cg ^ (row & 7))
-#pragma unroll
-          for (int cg = 0; cg < 8; ++cg)
-            tb[lane * 8 + (cg ^ (lane & 7))] = make_float4(__uint_as_float(raw[cg * 4]), __uint_as_float(raw[cg * 4 + 1]),
-                                                           __uint_as_float(raw[cg * 4 + 2]), __uint_as_float(raw[cg * 4 + 3]));
-          __syncwarp();
-          float4 v[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + sub_row;
-            v[it] = tb[r * 8 + (c4 ^ (r & 7))];
-          }
-          __syncwarp();
-          epilogue_rows8(p.ep, i0 + q * 32 + sub_row, j0 + c * 32 + c4 * 4, p.I, v);
-        }
-      }
+    auto release_tmem = [&]() {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0));
         else mbar_arrive(tempty_bar(acc));
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    };
+
+    if constexpr (EK == EK_LEGACY) {
+      while (wi.next(p, w)) {
+        const int tile = w.tile;
+        const int i0 = (tile / p.n_tiles_n) * (TC_BM * CG) + (int)rank * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+        const uint32_t tb = smem_base + Cfg::EPI_OFF + (uint32_t)we * TC_EPI_WARP_BYTES;   // 4 KB transpose buffer
+        const int sub_row = lane >> 3, c4 = lane & 7;
+        if (i0 + q * 32 < p.I) {   // warps whose 32 rows are all past the end of the matrix have nothing to write
+#pragma unroll 1
+          for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
+            uint32_t raw[32];
+            tc_ld32(taddr + c * 32, raw);
+            // row `lane` of the 32x32 chunk -> swizzled smem (16-byte column group cg at cg ^ (row & 7)), then 8 lanes
+            // re-read 32 consecutive columns of ONE row: coalesced global IO in epilogue_rows8
+#pragma unroll
+            for (int cg = 0; cg < 8; ++cg)
+              sts128(tb + row_off_128(lane, cg), raw[cg * 4], raw[cg * 4 + 1], raw[cg * 4 + 2], raw[cg * 4 + 3]);
+            __syncwarp();
+            float4 v[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + sub_row;
+              const uint4 u = lds128(tb + row_off_128(r, c4));
+              v[it] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+            }
+            __syncwarp();
+            epilogue_rows8(p.ep, i0 + q * 32 + sub_row, j0 + c * 32 + c4 * 4, p.I, v);
+          }
+        }
+        release_tmem();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else {
+      // ---------------- TMA epilogue ----------------
+      constexpr bool kLoads = (EK == EK_RESIDUAL || EK == EK_GELU_BWD);       // second operand TMA-loaded into the staging tile
+      constexpr bool kF32 = (EK == EK_STORE_F32 || EK == EK_RESIDUAL);         // fp32 tiles: 4 KB, 128-byte rows
+      constexpr uint32_t kTileBytes = kF32 ? 4096u : 2048u;
+      constexpr int NCH = BN / 64;                                             // 32-column chunks per warp and tile
+      const uint32_t stg = smem_base + Cfg::EPI_OFF + (uint32_t)we * TC_EPI_WARP_BYTES;   // slot s at stg + s * 4096
+      const uint32_t sbias = smem_base + Cfg::BIAS_OFF + (uint32_t)we * 512;
+      uint32_t eph = 0;            // phase bits of this warp's two load barriers
+      uint32_t slot = 0;           // staging slot of the next chunk (alternates across tiles too)
+      while (wi.next(p, w)) {
+        const int tile = w.tile;
+        const int i0 = (tile / p.n_tiles_n) * (TC_BM * CG) + (int)rank * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
+        const int row0 = i0 + q * 32;
+        const bool active = row0 < p.I;   // warps whose 32 rows are all past the end of the matrix have nothing to do
+        // ---- before the accumulator is ready: bias values of this warp's columns, and the first second-operand tile
+        float bv[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) bv[k] = p.ep.bias ? __ldg(p.ep.bias + j0 + (half + 2 * k) * 32 + lane) : 0.f;
+        auto issue_load = [&](int k, uint32_t s) {   // lane 0: second operand of chunk k -> staging slot s
+          mbar_expect_tx(eload_bar(we, s), kTileBytes);
+          tma_load_2d(stg + s * 4096, &map_d, eload_bar(we, s), j0 + (half + 2 * k) * 32, row0);
+        };
+        if constexpr (kLoads) {
+          if (active && lane == 0) {
+            bulk_wait_read<0>();       // the store that last read this slot has drained it
+            issue_load(0, slot);
+          }
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+        if (!active) {
+          release_tmem();
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + (k * 32 + lane) * 4), "f"(bv[k]) : "memory");
+        __syncwarp();
+        uint32_t raw[32];
+        tc_ld32_issue(taddr + half * 32, raw);
+#pragma unroll 1
+        for (int k = 0; k < NCH; ++k) {
+          const int col = j0 + (half + 2 * k) * 32;
+          const uint32_t s = slot;
+          slot ^= 1;
+          if constexpr (kLoads) {
+            if (k + 1 < NCH && lane == 0) {
+              bulk_wait_read<0>();     // chunk k-1's store (slot s^1) has been read out
+              issue_load(k + 1, s ^ 1);
+            }
+          }
+          tc_ld_wait();
+          if (k + 1 == NCH) release_tmem();   // accumulator fully in registers: the MMA warp may reuse this TMEM buffer
+          // ---- epilogue math on this lane's row: 32 columns
+          float v[32];
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 b;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sbias + (k * 32 + c4 * 4) * 4));
+            v[c4 * 4 + 0] = __uint_as_float(raw[c4 * 4 + 0]) + b.x;
+            v[c4 * 4 + 1] = __uint_as_float(raw[c4 * 4 + 1]) + b.y;
+            v[c4 * 4 + 2] = __uint_as_float(raw[c4 * 4 + 2]) + b.z;
+            v[c4 * 4 + 3] = __uint_as_float(raw[c4 * 4 + 3]) + b.w;
+          }
+          if (k + 1 < NCH) tc_ld32_issue(taddr + (half + 2 * (k + 1)) * 32, raw);   // next chunk's TMEM read overlaps the rest
+          const uint32_t t0 = stg + s * 4096;
+          if constexpr (kLoads) {
+            mbar_wait(eload_bar(we, s), (eph >> s) & 1u);
+            eph ^= 1u << s;
+          } else {
+            if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago (same slot) has been read out
+            __syncwarp();
+          }
+          if constexpr (EK == EK_STORE_BF16 || EK == EK_SCATTER) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              sts128(t0 + row_off_64(lane, k4), pack_bf16x2(v[k4 * 8 + 0], v[k4 * 8 + 1]), pack_bf16x2(v[k4 * 8 + 2], v[k4 * 8 + 3]),
+                     pack_bf16x2(v[k4 * 8 + 4], v[k4 * 8 + 5]), pack_bf16x2(v[k4 * 8 + 6], v[k4 * 8 + 7]));
+          } else if constexpr (EK == EK_STORE_F32) {
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8)
+              sts128(t0 + row_off_128(lane, k8), __float_as_uint(v[k8 * 4 + 0]), __float_as_uint(v[k8 * 4 + 1]),
+                     __float_as_uint(v[k8 * 4 + 2]), __float_as_uint(v[k8 * 4 + 3]));
+          } else if constexpr (EK == EK_GELU) {
+            // GELU acts on the 16-bit fc1 output (autocast); gelu'(u) is kept for the backward epilogue
+            uint32_t g[16], dg[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float2 ur = unpack_bf16x2(pack_bf16x2(v[2 * e], v[2 * e + 1]));
+              float g0, d0, g1, d1;
+              gelu_fast_both(ur.x, g0, d0);
+              gelu_fast_both(ur.y, g1, d1);
+              g[e] = pack_bf16x2(g0, g1);
+              dg[e] = pack_bf16x2(d0, d1);
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              sts128(t0 + row_off_64(lane, k4), g[k4 * 4], g[k4 * 4 + 1], g[k4 * 4 + 2], g[k4 * 4 + 3]);
+              sts128(t0 + 2048 + row_off_64(lane, k4), dg[k4 * 4], dg[k4 * 4 + 1], dg[k4 * 4 + 2], dg[k4 * 4 + 3]);
+            }
+          } else if constexpr (EK == EK_RESIDUAL) {
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const uint32_t a = t0 + row_off_128(lane, k8);
+              const uint4 r = lds128(a);
+              sts128(a, __float_as_uint(__uint_as_float(r.x) + v[k8 * 4 + 0]), __float_as_uint(__uint_as_float(r.y) + v[k8 * 4 + 1]),
+                     __float_as_uint(__uint_as_float(r.z) + v[k8 * 4 + 2]), __float_as_uint(__uint_as_float(r.w) + v[k8 * 4 + 3]));
+            }
+          } else if constexpr (EK == EK_GELU_BWD) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint32_t a = t0 + row_off_64(lane, k4);
+              const uint4 u = lds128(a);   // gelu'(u), saved by the forward epilogue
+              const float2 u0 = unpack_bf16x2(u.x), u1 = unpack_bf16x2(u.y), u2 = unpack_bf16x2(u.z), u3 = unpack_bf16x2(u.w);
+              sts128(a, pack_bf16x2(v[k4 * 8 + 0] * u0.x, v[k4 * 8 + 1] * u0.y), pack_bf16x2(v[k4 * 8 + 2] * u1.x, v[k4 * 8 + 3] * u1.y),
+                     pack_bf16x2(v[k4 * 8 + 4] * u2.x, v[k4 * 8 + 5] * u2.y), pack_bf16x2(v[k4 * 8 + 6] * u3.x, v[k4 * 8 + 7] * u3.y));
+            }
+            if (p.ep.colsum) {
+              // bias gradient of fc1 = column sums of the bf16 values just written (rows past the end are zero: their
+              // gelu' tile was zero-filled by the TMA load).  Lane = column; 32 conflict-free 2-byte reads.
+              __syncwarp();
+              float cs = 0.f;
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                uint16_t h;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(t0 + row_off_64(r, lane >> 3) + (lane & 7) * 2));
+                cs += __uint_as_float((uint32_t)h << 16);
+              }
+              atomicAdd(p.ep.colsum + col + lane, cs);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (EK == EK_SCATTER) {
+              tma_store_3d(&map_c, t0, col & 63, row0, col >> 6);
+            } else {
+              tma_store_2d(&map_c, t0, col, row0);
+              if constexpr (EK == EK_GELU) {
+                if (p.ep.aux) tma_store_2d(&map_d, t0 + 2048, col, row0);
+              }
+            }
+            bulk_commit();
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) bulk_wait_all();   // shared memory must outlive the last stores' reads; writes complete before exit
     }
   }
 
@@ -608,22 +881,85 @@ static int make_operand_map(const void* base, const MatLayout& l, int rows, int 
   return VITK_OK;
 }
 
+
 static int g_tc_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 int attn_debug_variant() { return g_tc_debug[3]; }
 
-template <int BN, int CG>
+// 32 x 32 element tile maps of the epilogue operands: row-major [rows][ld] (2-D) or head-major [C/64][rows][64] (3-D).
+// 4-byte elements -> 128-byte tile rows (SWIZZLE_128B), 2-byte -> 64-byte rows (SWIZZLE_64B).
+static int make_tile_map(const void* base, int dtype, int64_t cols, int64_t rows, int64_t ld, int64_t hm_rows, CUtensorMap* map) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return VITK_ERR_DRIVER; }
+  const cuuint64_t elt = dtype == VITK_BF16 ? 2 : 4;
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+  int rank = 2;
+  if (hm_rows > 0) {
+    rank = 3;
+    dims[0] = 64; dims[1] = (cuuint64_t)hm_rows; dims[2] = (cuuint64_t)(cols / 64);
+    strides[0] = 64 * elt; strides[1] = (cuuint64_t)hm_rows * 64 * elt;
+  } else {
+    dims[0] = (cuuint64_t)cols; dims[1] = (cuuint64_t)rows; dims[2] = 1;
+    strides[0] = (cuuint64_t)ld * elt; strides[1] = strides[0] * (cuuint64_t)rows;
+  }
+  if (((uintptr_t)base & 15) || (strides[0] & 15)) { set_error("gemm_tc: epilogue operand must be 16-byte aligned"); return VITK_ERR_ARG; }
+  const CUresult r = enc(map, dtype == VITK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         dtype == VITK_BF16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (epilogue tile) failed: CUresult %d", (int)r); return VITK_ERR_DRIVER; }
+  return VITK_OK;
+}
+
+static int epilogue_kind(const EpiParams& ep) {
+  if (g_tc_debug[5] == 1) return EK_LEGACY;   // debug: per-thread global IO epilogue for every mode
+  const bool ok16 = (((uintptr_t)ep.out & 15) == 0) && (ep.ldc % 8 == 0);
+  switch (ep.mode) {
+    case E_STORE: return !ok16 ? EK_LEGACY : (ep.out_dtype == VITK_BF16 ? EK_STORE_BF16 : EK_STORE_F32);
+    case E_BIAS_GELU: return (ok16 && ep.out_dtype == VITK_BF16 && (((uintptr_t)ep.aux & 15) == 0)) ? EK_GELU : EK_LEGACY;
+    case E_BIAS_RESIDUAL: return (ok16 && (((uintptr_t)ep.residual & 15) == 0)) ? EK_RESIDUAL : EK_LEGACY;
+    case E_QKV_SCATTER: return (ok16 && ep.out_dtype == VITK_BF16) ? EK_SCATTER : EK_LEGACY;
+    case E_GELU_BWD: return (ok16 && ep.out_dtype == VITK_BF16 && ep.aux && (((uintptr_t)ep.aux & 15) == 0)) ? EK_GELU_BWD : EK_LEGACY;
+    default: return EK_LEGACY;
+  }
+}
+
+template <int BN, int CG, int EK>
 static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
   using Cfg = TcCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    VITK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     configured = true;
   }
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_c, map_d;
   TcParams p{};
   p.I = pr.I; p.J = pr.J; p.R = pr.R;
   VITK_TRY(make_operand_map(pr.A, pr.la, pr.I, pr.R, TC_BM, &map_a, &p.a_mode));
   VITK_TRY(make_operand_map(pr.B, pr.lb, pr.J, pr.R, Cfg::B_ROWS, &map_b, &p.b_mode));
+  const EpiParams& ep = pr.ep;
+  if constexpr (EK == EK_LEGACY) {
+    map_c = map_a; map_d = map_a;   // unused
+  } else if constexpr (EK == EK_SCATTER) {
+    VITK_TRY(make_tile_map(ep.out, VITK_BF16, pr.J, pr.I, 0, ep.hm_rows, &map_c));
+    map_d = map_c;
+  } else {
+    const int odt = (EK == EK_STORE_F32 || EK == EK_RESIDUAL) ? VITK_F32 : VITK_BF16;
+    VITK_TRY(make_tile_map(ep.out, odt, pr.J, pr.I, ep.ldc, 0, &map_c));
+    if constexpr (EK == EK_RESIDUAL) VITK_TRY(make_tile_map(ep.residual, VITK_F32, pr.J, pr.I, ep.ldc, 0, &map_d));
+    else if constexpr (EK == EK_GELU_BWD) VITK_TRY(make_tile_map(ep.aux, VITK_BF16, pr.J, pr.I, ep.ldc, 0, &map_d));
+    else if constexpr (EK == EK_GELU) { if (ep.aux) VITK_TRY(make_tile_map(ep.aux, VITK_BF16, pr.J, pr.I, ep.ldc, 0, &map_d)); else map_d = map_c; }
+    else map_d = map_c;
+  }
+  auto fill_coord = [](int mode, int rows_in_tile, OpCoord* c) {
+    *c = OpCoord{0, 0, 0, 0, 0, 0, 0, 0, 1};
+    if (mode == OP_KM_FLAT) { c->fr1 = 1; c->d0 = TC_BK; }
+    else if (mode == OP_KM_SPLIT) { c->fr1 = 1; c->d2 = 1; }
+    else if (mode == OP_MN_FLAT) { c->fr0 = 1; c->d1 = TC_BK; c->e0 = 64; c->nbox = rows_in_tile / 64; }
+    else { c->fr2 = 1; c->d1 = TC_BK; c->e2 = 1; c->nbox = rows_in_tile / 64; }
+  };
+  fill_coord(p.a_mode, TC_BM, &p.ca);
+  fill_coord(p.b_mode, Cfg::B_ROWS, &p.cb);
   const bool a_mn = p.a_mode >= OP_MN_FLAT, b_mn = p.b_mode >= OP_MN_FLAT;
   // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4 (M = 128 per CTA: 256 for a CTA pair)
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -662,9 +998,22 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  VITK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, map_a, map_b, p));
+  VITK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, EK>, map_a, map_b, map_c, map_d, p));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
+}
+
+template <int BN, int CG>
+static int launch_tc_kind(const GemmProblem& pr, int ek, cudaStream_t st) {
+  switch (ek) {
+    case EK_STORE_BF16: return launch_tc<BN, CG, EK_STORE_BF16>(pr, st);
+    case EK_STORE_F32: return launch_tc<BN, CG, EK_STORE_F32>(pr, st);
+    case EK_GELU: return launch_tc<BN, CG, EK_GELU>(pr, st);
+    case EK_RESIDUAL: return launch_tc<BN, CG, EK_RESIDUAL>(pr, st);
+    case EK_SCATTER: return launch_tc<BN, CG, EK_SCATTER>(pr, st);
+    case EK_GELU_BWD: return launch_tc<BN, CG, EK_GELU_BWD>(pr, st);
+    default: return launch_tc<BN, CG, EK_LEGACY>(pr, st);
+  }
 }
 
 int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
@@ -673,12 +1022,10 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
   if (pr.ep.mode != E_STORE && pr.ep.mode != E_ACCUM && pr.ep.mode != E_BIAS_RESIDUAL && pr.ep.mode != E_PATCH &&
       pr.ep.out_dtype != VITK_BF16) { set_error("gemm_tc: epilogue expects bf16 output"); return VITK_ERR_UNSUPPORTED; }
   if (pr.J % 128 != 0 || pr.ep.ldc % 8 != 0) { set_error("gemm_tc: J must be a multiple of 128 (got %d)", pr.J); return VITK_ERR_UNSUPPORTED; }
-  // Tile shape: CTA pair (CG = 2, 256 x BN) or single CTA (128 x BN), BN in {256, 192, 128}.  The kernel is bound by
-  // L2->SM operand traffic long before the tensor pipe: per CTA and 64-deep k-block it pulls (128 + BN/CG) rows of
-  // 128 B at ~42.5 B/clk/SM (6.3 KB/clk chip-wide, B300_MICROARCH.md) while the MMAs need 2*BN clk.  Pick the
-  // candidate that minimises waves x k-blocks x max(L2, MMA) clocks; with M = B*197 the tile count is rarely a
-  // multiple of the slot count, so the wave term matters (12608 x 768 on 74 pairs: 150 tiles of 256x256 = 3 waves for
-  // 2.03 waves of work, 200 tiles of 256x192 = 3 waves of 3/4 the cost).
+  // Tile shape: CTA pair (CG = 2, 256 x BN) or single CTA (128 x BN), BN in {256, 192, 128}: minimise
+  // (waves of the persistent grid) x (k-blocks x 2*BN tensor clocks + per-tile overhead).  With M = B*197 the tile count
+  // is rarely a multiple of the slot count, so the wave term matters (12608 x 768 on 74 CTA pairs: 150 tiles of 256x256 =
+  // 3 waves for 2.03 waves of work, 200 tiles of 256x192 = 3 waves of 3/4 the cost).  Pairs win ties (half the B traffic).
   const bool b_mn = pr.lb.s_row == 1 && pr.lb.s_col != 1;   // MN-major B: staged in 64-row atoms
   int cg = 0, bn = 0;
   const int forced_bn = (g_tc_debug[2] == 128 || g_tc_debug[2] == 192 || g_tc_debug[2] == 256) ? g_tc_debug[2] : 0;
@@ -699,21 +1046,21 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
         if (forced_bn && forced_bn != cand) continue;
         const long tiles = tiles_m * (pr.J / cand);
         const long waves = (tiles + slots - 1) / slots;
-        const double l2 = (128.0 + cand / c) * 128.0 / 42.5, mma = 2.0 * cand;
-        const double cost = (double)waves * ((double)kb * (l2 > mma ? l2 : mma) + 600.0);
+        const double cost = (double)waves * ((double)kb * 2.0 * cand + 1200.0);
         if (best < 0.0 || cost < best) { best = cost; bn = cand; cg = c; }
       }
     }
   }
   if (bn == 0 || pr.J % bn != 0) { set_error("gemm_tc: no BLOCK_N divides J=%d", pr.J); return VITK_ERR_UNSUPPORTED; }
+  const int ek = epilogue_kind(pr.ep);
   if (cg == 2) {
-    if (bn == 256) return launch_tc<256, 2>(pr, st);
-    if (bn == 192) return launch_tc<192, 2>(pr, st);
-    return launch_tc<128, 2>(pr, st);
+    if (bn == 256) return launch_tc_kind<256, 2>(pr, ek, st);
+    if (bn == 192) return launch_tc_kind<192, 2>(pr, ek, st);
+    return launch_tc_kind<128, 2>(pr, ek, st);
   }
-  if (bn == 256) return launch_tc<256, 1>(pr, st);
-  if (bn == 192) return launch_tc<192, 1>(pr, st);
-  return launch_tc<128, 1>(pr, st);
+  if (bn == 256) return launch_tc_kind<256, 1>(pr, ek, st);
+  if (bn == 192) return launch_tc_kind<192, 1>(pr, ek, st);
+  return launch_tc_kind<128, 1>(pr, ek, st);
 }
 
 }  // namespace vitk
