@@ -58,19 +58,23 @@ def timeit(fn, n=6):
     return tot / n * 1e3
 
 
-print(f"{'case':38s} {'auto':>8s} | " + " ".join(f"cg{cg}/bn{bn:3d}" for cg in (1, 2) for bn in (128, 192, 256)))
+for kv in os.environ.get("VITK_KNOBS", "").split(","):   # e.g. VITK_KNOBS=7:1,5:1  -> vitk_debug_set(7, 1); vitk_debug_set(5, 1)
+    if kv:
+        lib.vitk_debug_set(int(kv.split(":")[0]), int(kv.split(":")[1]))
+print("knobs:", os.environ.get("VITK_KNOBS", ""))
+COMBOS = [(cg, bn) for cg in (1, 2) for bn in (128, 192, 256)] if os.environ.get("FULL") else [(2, 192), (2, 256)]
+print(f"{'case':38s} {'auto':>8s} | " + " ".join(f"cg{cg}/bn{bn:3d}" for cg, bn in COMBOS))
 for name, nk, fn in CASES:
     flops = 2.0 * M * nk
     lib.vitk_debug_set(2, 0); lib.vitk_debug_set(4, 0)
     t_auto = timeit(fn)
     cells = []
-    for cg in (1, 2):
-        for bn in (128, 192, 256):
-            lib.vitk_debug_set(2, bn); lib.vitk_debug_set(4, cg)
-            try:
-                t = timeit(fn)
-                cells.append(f"{t:6.1f}us ")
-            except Exception:  # noqa: BLE001
-                cells.append("    n/a  ")
+    for cg, bn in COMBOS:
+        lib.vitk_debug_set(2, bn); lib.vitk_debug_set(4, cg)
+        try:
+            t = timeit(fn)
+            cells.append(f"{t:6.1f}us ")
+        except Exception:  # noqa: BLE001
+            cells.append("    n/a  ")
     lib.vitk_debug_set(2, 0); lib.vitk_debug_set(4, 0)
     print(f"{name:38s} {t_auto:6.1f}us {flops / t_auto / 1e6:6.0f}TF | " + " ".join(cells), flush=True)

@@ -85,6 +85,8 @@ def load():
         fn.argtypes = args
     if lib.vitk_version() != 100:
         raise RuntimeError("libvitk.so version mismatch: rebuild")
+    if os.environ.get("VITK_NO_PDL") == "1":   # A/B timing: plain stream order instead of programmatic dependent launch
+        lib.vitk_debug_set(6, 1)
     _lib = lib
     return lib
 

@@ -17,6 +17,7 @@ constexpr int SUMSQ_MAX_CTAS = 1024;
 
 __global__ void __launch_bounds__(256)
 sumsq_partial_kernel(const float* __restrict__ g, size_t n, float* __restrict__ partial) {
+  pdl_sync();
   __shared__ float red[8];
   float s = 0.f;
   const size_t n4 = n / 4;
@@ -39,6 +40,7 @@ sumsq_partial_kernel(const float* __restrict__ g, size_t n, float* __restrict__ 
 
 __global__ void __launch_bounds__(256)
 sumsq_final_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ sumsq) {
+  pdl_sync();
   __shared__ float red[8];
   float s = 0.f;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
@@ -70,6 +72,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             bf16* __restrict__ p16, size_t n, AdamArgs a, const float* __restrict__ sumsq) {
+  pdl_sync();
   float gm = a.grad_mult;
   if (sumsq && a.max_norm > 0.f) {
     const float total = sqrtf(sumsq[0]) * a.grad_mult;
@@ -106,6 +109,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  pdl_sync();
   const size_t n4 = n / 4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(src)[i];
@@ -135,10 +139,8 @@ extern "C" int vitk_grad_sumsq(const float* g, size_t n, float* partial, float* 
   cudaStream_t st = (cudaStream_t)stream;
   int grid = stream_grid(n / 4);
   if (grid > SUMSQ_MAX_CTAS) grid = SUMSQ_MAX_CTAS;
-  sumsq_partial_kernel<<<grid, 256, 0, st>>>(g, n, partial);
-  VITK_LAUNCH_CHECK();
-  sumsq_final_kernel<<<1, 256, 0, st>>>(partial, grid, sumsq);
-  VITK_LAUNCH_CHECK();
+  VITK_LAUNCH((sumsq_partial_kernel), grid, 256, 0, st, g, n, partial);
+  VITK_LAUNCH((sumsq_final_kernel), 1, 256, 0, st, partial, grid, sumsq);
   return VITK_OK;
 }
 
@@ -159,14 +161,12 @@ extern "C" int vitk_adam_step(float* p, const float* g, float* m, float* v, void
   a.step_size = (float)(lr / bc1);
   a.bc2_sqrt = (float)sqrt(bc2);
   a.decay = (float)(1.0 - lr * weight_decay);
-  adam_kernel<<<stream_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)p16, n, a, sumsq);
-  VITK_LAUNCH_CHECK();
+  VITK_LAUNCH((adam_kernel), stream_grid(n / 4), 256, 0, (cudaStream_t)stream, p, g, m, v, (bf16*)p16, n, a, sumsq);
   return VITK_OK;
 }
 
 extern "C" int vitk_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
   VITK_CHECK_ARG(src && dst && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0);
-  cast_bf16_kernel<<<stream_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
-  VITK_LAUNCH_CHECK();
+  VITK_LAUNCH((cast_bf16_kernel), stream_grid(n / 4), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, n);
   return VITK_OK;
 }

@@ -34,6 +34,9 @@ int sm_count() {
   return (b > 0 && b < hw) ? b : hw;
 }
 int set_sm_budget(int n) { return g_sm_budget.exchange(n); }
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+void set_pdl(int on) { g_pdl.store(on); }
 }  // namespace vitk
 
 extern "C" {

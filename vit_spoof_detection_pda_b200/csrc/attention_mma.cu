@@ -97,6 +97,7 @@ __device__ __forceinline__ void am_mma_tn(float (&out)[8][4], const uint32_t (&a
 
 __global__ void __launch_bounds__(AM_THREADS)
 attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int batch) {
+  pdl_sync();
   extern __shared__ __align__(1024) uint8_t am_smem[];
   const uint32_t sQ = am_smem_u32(am_smem), sK = sQ + AM_MAT_BYTES, sV = sK + AM_MAT_BYTES;
   const int b = blockIdx.x / VITK_HEADS, h = blockIdx.x % VITK_HEADS;
@@ -201,6 +202,7 @@ template <int MIN_CTAS>
 __global__ void __launch_bounds__(AM_THREADS, MIN_CTAS)
 attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
                     const float* __restrict__ lse, bf16* __restrict__ dqkv, float* __restrict__ dqkv_colsum, int batch) {
+  pdl_sync();
   extern __shared__ __align__(1024) uint8_t am_smem[];
   const uint32_t sQ = am_smem_u32(am_smem), sK = sQ + AM_MAT_BYTES, sV = sK + AM_MAT_BYTES, sdO = sV + AM_MAT_BYTES;
   float* Ls = reinterpret_cast<float*>(am_smem + 4 * AM_MAT_BYTES);  // lse * log2(e), padded rows 0
@@ -426,6 +428,7 @@ attn_fwd_mma2_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float
   const int64_t hstride = (int64_t)VITK_HEADS * M * AM_D;
   const float sl2 = AM_SCALE * AM_LOG2E;
   for (int i = 0; i < 6; ++i) a2_zero_pad_rows(s0 + i * AM_MAT_BYTES);
+  pdl_sync();
   int item = blockIdx.x;
   if (item >= n_items) return;
   auto issue = [&](int it_, int buf) {
@@ -545,6 +548,7 @@ attn_bwd_mma2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
   const int64_t hstride = (int64_t)VITK_HEADS * M * AM_D;
   const float sl2 = AM_SCALE * AM_LOG2E;
   for (int i = 0; i < 5; ++i) a2_zero_pad_rows(sQ + i * AM_MAT_BYTES);
+  pdl_sync();
   int item = blockIdx.x;
   if (item >= n_items) return;
 
@@ -696,12 +700,11 @@ int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t
     configured = true;
   }
   if (attn_debug_variant() == 2) {   // debug knob 3 == 2: the first-generation kernel (one CTA per item)
-    attn_fwd_mma_kernel<<<batch * VITK_HEADS, AM_THREADS, AM_FWD_SMEM, st>>>((const bf16*)qkv, (bf16*)out, lse, batch);
+    VITK_LAUNCH((attn_fwd_mma_kernel), batch * VITK_HEADS, AM_THREADS, AM_FWD_SMEM, st, (const bf16*)qkv, (bf16*)out, lse, batch);
   } else {
     const int items = batch * VITK_HEADS, sms = sm_count();
-    attn_fwd_mma2_kernel<<<items < sms ? items : sms, A2_THREADS, A2_FWD_SMEM, st>>>((const bf16*)qkv, (bf16*)out, lse, batch, items);
+    VITK_LAUNCH((attn_fwd_mma2_kernel), (items < sms ? items : sms), A2_THREADS, A2_FWD_SMEM, st, (const bf16*)qkv, (bf16*)out, lse, batch, items);
   }
-  VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
 
@@ -714,15 +717,11 @@ int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float
     configured = true;
   }
   if (attn_debug_variant() == 2) {
-    attn_bwd_mma_kernel<1><<<batch * VITK_HEADS, AM_THREADS, AM_BWD_SMEM, st>>>(
-        (const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, dqkv_colsum, batch);
-    VITK_LAUNCH_CHECK();
+    VITK_LAUNCH((attn_bwd_mma_kernel<1>), batch * VITK_HEADS, AM_THREADS, AM_BWD_SMEM, st, (const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, dqkv_colsum, batch);
     return VITK_OK;
   }
   const int items = batch * VITK_HEADS, sms = sm_count();
-  attn_bwd_mma2_kernel<<<items < sms ? items : sms, A2_THREADS, A2_BWD_SMEM, st>>>(
-      (const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, batch, items);
-  VITK_LAUNCH_CHECK();
+  VITK_LAUNCH((attn_bwd_mma2_kernel), (items < sms ? items : sms), A2_THREADS, A2_BWD_SMEM, st, (const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, batch, items);
   // the qkv bias gradient: a stand-alone coalesced column-sum pass (fusing it into the mma.sync kernel measured slower)
   if (dqkv_colsum) VITK_TRY(colsum_headmajor(dqkv, VITK_BF16, batch * VITK_NTOK, 3 * VITK_DIM, dqkv_colsum, st));
   return VITK_OK;

@@ -24,6 +24,7 @@ __device__ __forceinline__ void at_load_matrix(const T* __restrict__ src, float*
 template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32)
 attn_fwd_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ lse, int batch) {
+  pdl_sync();
   extern __shared__ float smem[];
   float* Ks = smem;
   float* Vs = Ks + AT_N * AT_P;
@@ -89,6 +90,7 @@ template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32)
 attn_bwd_simt_kernel(const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
                      const float* __restrict__ lse, T* __restrict__ dqkv, int batch) {
+  pdl_sync();
   extern __shared__ float smem[];
   float* Qs = smem;
   float* Ks = Qs + AT_N * AT_P;
@@ -207,8 +209,7 @@ static int attn_fwd_simt_t(const void* qkv, void* out, float* lse, int batch, cu
     VITK_CUDA(cudaFuncSetAttribute(attn_fwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_FWD_SMEM));
     configured = true;
   }
-  attn_fwd_simt_kernel<T><<<batch * VITK_HEADS, AT_WARPS * 32, AT_FWD_SMEM, st>>>((const T*)qkv, (T*)out, lse, batch);
-  VITK_LAUNCH_CHECK();
+  VITK_LAUNCH((attn_fwd_simt_kernel<T>), batch * VITK_HEADS, AT_WARPS * 32, AT_FWD_SMEM, st, (const T*)qkv, (T*)out, lse, batch);
   return VITK_OK;
 }
 template <typename T>
@@ -219,9 +220,7 @@ static int attn_bwd_simt_t(const void* qkv, const void* out, const void* dout, c
     VITK_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_BWD_SMEM));
     configured = true;
   }
-  attn_bwd_simt_kernel<T><<<batch * VITK_HEADS, AT_WARPS * 32, AT_BWD_SMEM, st>>>((const T*)qkv, (const T*)out,
-                                                                                  (const T*)dout, lse, (T*)dqkv, batch);
-  VITK_LAUNCH_CHECK();
+  VITK_LAUNCH((attn_bwd_simt_kernel<T>), batch * VITK_HEADS, AT_WARPS * 32, AT_BWD_SMEM, st, (const T*)qkv, (const T*)out, (const T*)dout, lse, (T*)dqkv, batch);
   return VITK_OK;
 }
 

@@ -44,6 +44,40 @@ int default_engine();  // process-wide GEMM/attention engine (VITK_ENGINE_*)
     VITK_CUDA(cudaPeekAtLastError());       \
   } while (0)
 
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched with the programmatic-stream-
+// serialization attribute and begins with pdl_sync(): griddepcontrol.wait (returns once the preceding kernel of the
+// stream has completed and flushed) followed by griddepcontrol.launch_dependents (the next kernel may start being
+// scheduled as SMs drain).  Launch latency, CTA ramp-up and the prologue in front of pdl_sync() -- barrier init,
+// TMEM allocation, tensor-map prefetch -- overlap the tail of the previous kernel; no kernel touches global memory
+// before its pdl_sync().  vitk_debug_set(6, 1) turns the attribute off (plain stream order) for A/B timing.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KA, typename... A>
+static inline cudaError_t launch_kernel(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+#endif
+// launch + count + error check
+#define VITK_LAUNCH(kern, grid, block, smem, st, ...)                                  \
+  do {                                                                                 \
+    vitk::count_launch();                                                              \
+    VITK_CUDA(vitk::launch_kernel(kern, dim3(grid), dim3(block), smem, st, __VA_ARGS__)); \
+  } while (0)
+
 #define VITK_TRY(expr)          \
   do {                          \
     int _r = (expr);            \

@@ -26,6 +26,7 @@ __device__ __forceinline__ void simt_load_tile(const T* __restrict__ base, const
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(ST_THREADS)
 gemm_simt_kernel(GemmProblem p, int r_per_split) {
+  pdl_sync();
   __shared__ float As[ST_BK][ST_BM + ST_PAD];
   __shared__ float Bs[ST_BK][ST_BN + ST_PAD];
   const int i0 = blockIdx.y * ST_BM, j0 = blockIdx.x * ST_BN;
@@ -79,11 +80,10 @@ int gemm_simt(const GemmProblem& p, int splits, cudaStream_t st) {
   splits = (p.R + r_per_split - 1) / r_per_split;
   dim3 grid((p.J + ST_BN - 1) / ST_BN, (p.I + ST_BM - 1) / ST_BM, splits);
   const bool in16 = p.in_dtype == VITK_BF16, out16 = p.ep.out_dtype == VITK_BF16;
-  if (!in16 && !out16) gemm_simt_kernel<float, float><<<grid, ST_THREADS, 0, st>>>(p, r_per_split);
-  else if (in16 && out16) gemm_simt_kernel<bf16, bf16><<<grid, ST_THREADS, 0, st>>>(p, r_per_split);
-  else if (in16 && !out16) gemm_simt_kernel<bf16, float><<<grid, ST_THREADS, 0, st>>>(p, r_per_split);
-  else gemm_simt_kernel<float, bf16><<<grid, ST_THREADS, 0, st>>>(p, r_per_split);
-  VITK_LAUNCH_CHECK();
+  if (!in16 && !out16) VITK_LAUNCH((gemm_simt_kernel<float, float>), grid, ST_THREADS, 0, st, p, r_per_split);
+  else if (in16 && out16) VITK_LAUNCH((gemm_simt_kernel<bf16, bf16>), grid, ST_THREADS, 0, st, p, r_per_split);
+  else if (in16 && !out16) VITK_LAUNCH((gemm_simt_kernel<bf16, float>), grid, ST_THREADS, 0, st, p, r_per_split);
+  else VITK_LAUNCH((gemm_simt_kernel<float, bf16>), grid, ST_THREADS, 0, st, p, r_per_split);
   return VITK_OK;
 }
 

@@ -46,6 +46,7 @@ struct OpCoord {
 };
 
 struct TcParams {
+  int32_t dbg;              // timing experiments only (vitk_debug_set(7, v)): bit 0 skip the epilogue body, bit 1 no operand loads
   int32_t I, J, R;
   int32_t a_mode, b_mode;
   OpCoord ca, cb;
@@ -105,7 +106,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -372,18 +373,21 @@ __device__ __forceinline__ void epilogue_rows8(const EpiParams& ep, int i, int j
 // arrive the same way: a TMA load into the staging tile issued BEFORE the accumulator is ready, combined in place.
 // No per-thread global loads/stores and no global-memory latency remain on the epilogue warps' critical path.
 enum { EK_LEGACY = 0, EK_STORE_BF16 = 1, EK_STORE_F32 = 2, EK_GELU = 3, EK_RESIDUAL = 4, EK_SCATTER = 5, EK_GELU_BWD = 6 };
-constexpr uint32_t TC_EPI_WARP_BYTES = 8192;   // per epilogue warp: 2 slots x 4 KB (fp32 tile) or 4 x 2 KB (bf16 tiles)
+// staging per epilogue warp: two 4 KB slots for fp32 tiles, two 2 KB slots for bf16 tiles (EK_GELU: one slot pair g | u).
+// Every KB not spent here is operand-ring depth: the mainloop needs ~1.5 us of loads in flight to ride out DRAM latency.
+__host__ __device__ constexpr uint32_t tc_epi_warp_bytes(int ek) { return (ek == EK_STORE_F32 || ek == EK_RESIDUAL) ? 8192u : 4096u; }
 
-template <int BN, int CG> struct TcCfg {
+template <int BN, int CG, int EK> struct TcCfg {
   static constexpr int B_ROWS = BN / CG;                                   // rows of the B tile this CTA stages
   static constexpr uint32_t B_STAGE_BYTES = B_ROWS * TC_BK * 2;
   static constexpr uint32_t STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr uint32_t TAIL_BYTES = TC_EPI_WARPS * TC_EPI_WARP_BYTES + TC_EPI_WARPS * 512 + 512;  // staging | bias | barriers
+  static constexpr uint32_t EPI_WARP_BYTES = tc_epi_warp_bytes(EK);
+  static constexpr uint32_t TAIL_BYTES = TC_EPI_WARPS * EPI_WARP_BYTES + TC_EPI_WARPS * 512 + 512;  // staging | bias | barriers
   static constexpr int STAGES_FIT = (227 * 1024 - 1024 - (int)TAIL_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // double-buffered accumulator, power of two
   static constexpr uint32_t EPI_OFF = STAGES * STAGE_BYTES;                                  // 1024-aligned staging tiles
-  static constexpr uint32_t BIAS_OFF = EPI_OFF + TC_EPI_WARPS * TC_EPI_WARP_BYTES;           // 512 B per epilogue warp
+  static constexpr uint32_t BIAS_OFF = EPI_OFF + TC_EPI_WARPS * EPI_WARP_BYTES;              // 512 B per epilogue warp
   static constexpr uint32_t BAR_OFF = BIAS_OFF + TC_EPI_WARPS * 512;
   static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + TAIL_BYTES;
 };
@@ -455,7 +459,7 @@ template <int BN, int CG, int EK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_d, const TcParams p) {
-  using Cfg = TcCfg<BN, CG>;
+  using Cfg = TcCfg<BN, CG, EK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
@@ -506,6 +510,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // peer barriers initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of the B rows) ==========
@@ -526,6 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int a0 = i0 * p.ca.fr0 + kb0 * p.ca.d0, a1 = i0 * p.ca.fr1 + kb0 * p.ca.d1, a2 = (i0 >> 6) * p.ca.fr2 + kb0 * p.ca.d2;
         int b0 = j0 * p.cb.fr0 + kb0 * p.cb.d0, b1 = j0 * p.cb.fr1 + kb0 * p.cb.d1, b2 = (j0 >> 6) * p.cb.fr2 + kb0 * p.cb.d2;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (p.dbg & 2) continue;
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (leader) {
             if (rank == 0) mbar_expect_tx(full_bar(stage), CG * Cfg::STAGE_BYTES);
@@ -544,7 +550,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if constexpr (CG == 2) {
+      if (CG == 2 && !(p.dbg & 2)) {
         // tail: the leader's last multicast commits must have landed in this CTA's `empty` barriers before it may exit
         for (int s = 0; s < Cfg::STAGES; ++s) {
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -578,7 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          if (!(p.dbg & 2)) mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           if (leader) {
             const uint32_t so = (uint32_t)stage * (Cfg::STAGE_BYTES >> 4);
@@ -588,7 +594,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_mma_desc(d_tmem, al + 2 * a_ks, a_hi, bl + 2 * b_ks, b_hi, p.idesc, 1u, CG == 2);
             tc_mma_desc(d_tmem, al + 3 * a_ks, a_hi, bl + 3 * b_ks, b_hi, p.idesc, 1u, CG == 2);
             // smem slot free (in both CTAs) once these MMAs retire
-            if constexpr (CG == 2) tc_commit_2cta(empty_bar(stage)); else tc_commit(empty_bar(stage));
+            if (!(p.dbg & 2)) { if constexpr (CG == 2) tc_commit_2cta(empty_bar(stage)); else tc_commit(empty_bar(stage)); }
             if (kb + 1 == nkb) {   // accumulator complete (both CTAs' epilogues)
               if constexpr (CG == 2) tc_commit_2cta(tfull_bar(acc)); else tc_commit(tfull_bar(acc));
             }
@@ -625,7 +631,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-        const uint32_t tb = smem_base + Cfg::EPI_OFF + (uint32_t)we * TC_EPI_WARP_BYTES;   // 4 KB transpose buffer
+        const uint32_t tb = smem_base + Cfg::EPI_OFF + (uint32_t)we * Cfg::EPI_WARP_BYTES;   // 4 KB transpose buffer
         const int sub_row = lane >> 3, c4 = lane & 7;
         if (i0 + q * 32 < p.I) {   // warps whose 32 rows are all past the end of the matrix have nothing to write
 #pragma unroll 1
@@ -658,7 +664,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr bool kF32 = (EK == EK_STORE_F32 || EK == EK_RESIDUAL);         // fp32 tiles: 4 KB, 128-byte rows
       constexpr uint32_t kTileBytes = kF32 ? 4096u : 2048u;
       constexpr int NCH = BN / 64;                                             // 32-column chunks per warp and tile
-      const uint32_t stg = smem_base + Cfg::EPI_OFF + (uint32_t)we * TC_EPI_WARP_BYTES;   // slot s at stg + s * 4096
+      constexpr uint32_t kSlotBytes = kF32 ? 4096u : 2048u;
+      const uint32_t stg = smem_base + Cfg::EPI_OFF + (uint32_t)we * Cfg::EPI_WARP_BYTES;   // slot s at stg + s * kSlotBytes
       const uint32_t sbias = smem_base + Cfg::BIAS_OFF + (uint32_t)we * 512;
       uint32_t eph = 0;            // phase bits of this warp's two load barriers
       uint32_t slot = 0;           // staging slot of the next chunk (alternates across tiles too)
@@ -673,7 +680,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int k = 0; k < NCH; ++k) bv[k] = p.ep.bias ? __ldg(p.ep.bias + j0 + (half + 2 * k) * 32 + lane) : 0.f;
         auto issue_load = [&](int k, uint32_t s) {   // lane 0: second operand of chunk k -> staging slot s
           mbar_expect_tx(eload_bar(we, s), kTileBytes);
-          tma_load_2d(stg + s * 4096, &map_d, eload_bar(we, s), j0 + (half + 2 * k) * 32, row0);
+          tma_load_2d(stg + s * kSlotBytes, &map_d, eload_bar(we, s), j0 + (half + 2 * k) * 32, row0);
         };
         if constexpr (kLoads) {
           if (active && lane == 0) {
@@ -684,7 +691,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-        if (!active) {
+        if (!active || (p.dbg & 1)) {
           release_tmem();
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           continue;
@@ -697,7 +704,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 1
         for (int k = 0; k < NCH; ++k) {
           const int col = j0 + (half + 2 * k) * 32;
-          const uint32_t s = slot;
+          const uint32_t s = (EK == EK_GELU) ? 0u : slot;   // EK_GELU: both 2 KB slots hold one chunk (g | g')
           slot ^= 1;
           if constexpr (kLoads) {
             if (k + 1 < NCH && lane == 0) {
@@ -719,12 +726,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             v[c4 * 4 + 3] = __uint_as_float(raw[c4 * 4 + 3]) + b.w;
           }
           if (k + 1 < NCH) tc_ld32_issue(taddr + (half + 2 * (k + 1)) * 32, raw);   // next chunk's TMEM read overlaps the rest
-          const uint32_t t0 = stg + s * 4096;
+          const uint32_t t0 = stg + s * kSlotBytes;
           if constexpr (kLoads) {
             mbar_wait(eload_bar(we, s), (eph >> s) & 1u);
             eph ^= 1u << s;
           } else {
-            if (lane == 0) bulk_wait_read<1>();   // the store issued two chunks ago (same slot) has been read out
+            // the store that last used this slot has been read out (two chunks ago; EK_GELU: the previous chunk)
+            if (lane == 0) { if constexpr (EK == EK_GELU) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
             __syncwarp();
           }
           if constexpr (EK == EK_STORE_BF16 || EK == EK_SCATTER) {
@@ -926,7 +934,7 @@ static int epilogue_kind(const EpiParams& ep) {
 
 template <int BN, int CG, int EK>
 static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
-  using Cfg = TcCfg<BN, CG>;
+  using Cfg = TcCfg<BN, CG, EK>;
   static bool configured = false;
   if (!configured) {
     VITK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -935,6 +943,7 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
   CUtensorMap map_a, map_b, map_c, map_d;
   TcParams p{};
   p.I = pr.I; p.J = pr.J; p.R = pr.R;
+  p.dbg = g_tc_debug[7];
   VITK_TRY(make_operand_map(pr.A, pr.la, pr.I, pr.R, TC_BM, &map_a, &p.a_mode));
   VITK_TRY(make_operand_map(pr.B, pr.lb, pr.J, pr.R, Cfg::B_ROWS, &map_b, &p.b_mode));
   const EpiParams& ep = pr.ep;
@@ -993,13 +1002,22 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CG == 2 ? 1 : 0;
+  cfg.numAttrs = na;
+  count_launch();
   VITK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, EK>, map_a, map_b, map_c, map_d, p));
-  VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
 
@@ -1065,8 +1083,10 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
 
 }  // namespace vitk
 
+namespace vitk { void set_pdl(int on); }
 extern "C" int vitk_debug_set(int key, int value) {
   if (key < 0 || key >= 8) return VITK_ERR_ARG;
   vitk::g_tc_debug[key] = value;
+  if (key == 6) vitk::set_pdl(value ? 0 : 1);   // key 6: 1 = plain stream order (no programmatic dependent launch)
   return VITK_OK;
 }

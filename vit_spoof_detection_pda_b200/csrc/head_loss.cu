@@ -33,6 +33,7 @@ head_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ ln_w, 
                 const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                 const float* __restrict__ b2, const float* __restrict__ mask1, const float* __restrict__ mask2,
                 float* __restrict__ logits, float* __restrict__ save, int num_classes) {
+  pdl_sync();
   __shared__ float ys[HD_IN];
   __shared__ float as[HD_HID];
   __shared__ float red[HD_THREADS / 32];
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(HD_THREADS)
 head_bwd_data_kernel(const float* __restrict__ dlogits, float* __restrict__ save, const float* __restrict__ ln_w,
                      const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ mask1,
                      const float* __restrict__ mask2, float* __restrict__ dfeat, int num_classes) {
+  pdl_sync();
   __shared__ float dz[HD_HID];
   __shared__ float red[HD_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -129,6 +131,7 @@ head_bwd_param_kernel(const float* __restrict__ dlogits, const float* __restrict
                       float* __restrict__ dln_w, float* __restrict__ dln_b, float* __restrict__ dw1,
                       float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2, int batch,
                       int num_classes) {
+  pdl_sync();
   const int blk = blockIdx.x, tid = threadIdx.x;
   if (blk < HD_HID) {
     const int t = blk;
@@ -183,6 +186,7 @@ focal_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targe
              float gamma, int reduction, float grad_scale, float* __restrict__ loss_per_sample,
              float* __restrict__ loss_out, float* __restrict__ dlogits, float* __restrict__ probs1,
              int64_t* __restrict__ preds, int* __restrict__ ncorrect, int batch, int C) {
+  pdl_sync();
   __shared__ float red[8];
   __shared__ int redi[8];
   const float gscale = grad_scale * (reduction == 0 ? 1.0f / (float)batch : 1.0f);
@@ -253,9 +257,7 @@ extern "C" int vitk_head_fwd(const float* feat, const float* ln_w, const float* 
                              const float* w2, const float* b2, const float* mask1, const float* mask2, float* logits,
                              float* save, int batch, int num_classes, void* stream) {
   VITK_CHECK_ARG(feat && ln_w && ln_b && w1 && b1 && w2 && b2 && logits && batch > 0 && num_classes > 0);
-  head_fwd_kernel<<<batch, HD_THREADS, 0, (cudaStream_t)stream>>>(feat, ln_w, ln_b, w1, b1, w2, b2, mask1, mask2, logits,
-                                                                  save, num_classes);
-  VITK_LAUNCH_CHECK();
+  VITK_LAUNCH((head_fwd_kernel), batch, HD_THREADS, 0, (cudaStream_t)stream, feat, ln_w, ln_b, w1, b1, w2, b2, mask1, mask2, logits, save, num_classes);
   return VITK_OK;
 }
 
@@ -264,13 +266,10 @@ extern "C" int vitk_head_bwd(const float* dlogits, float* save, const float* ln_
                              float* dw1, float* db1, float* dw2, float* db2, int batch, int num_classes, void* stream) {
   VITK_CHECK_ARG(dlogits && save && ln_w && w1 && w2 && dfeat && batch > 0 && num_classes > 0);
   cudaStream_t st = (cudaStream_t)stream;
-  head_bwd_data_kernel<<<batch, HD_THREADS, 0, st>>>(dlogits, save, ln_w, w1, w2, mask1, mask2, dfeat, num_classes);
-  VITK_LAUNCH_CHECK();
+  VITK_LAUNCH((head_bwd_data_kernel), batch, HD_THREADS, 0, st, dlogits, save, ln_w, w1, w2, mask1, mask2, dfeat, num_classes);
   if (dw1) {
     VITK_CHECK_ARG(dln_w && dln_b && db1 && dw2 && db2);
-    head_bwd_param_kernel<<<HD_HID + 1 + num_classes, 256, 0, st>>>(dlogits, save, mask2, dln_w, dln_b, dw1, db1, dw2, db2,
-                                                                    batch, num_classes);
-    VITK_LAUNCH_CHECK();
+    VITK_LAUNCH((head_bwd_param_kernel), HD_HID + 1 + num_classes, 256, 0, st, dlogits, save, mask2, dln_w, dln_b, dw1, db1, dw2, db2, batch, num_classes);
   }
   return VITK_OK;
 }
@@ -281,8 +280,6 @@ extern "C" int vitk_focal_fwd_bwd(const float* logits, const int64_t* targets, c
                                   int num_classes, void* stream) {
   VITK_CHECK_ARG(logits && targets && alpha && loss_per_sample && batch > 0);
   VITK_CHECK_ARG(num_classes >= 1 && num_classes <= FOCAL_MAX_C && reduction >= 0 && reduction <= 2);
-  focal_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, targets, alpha, gamma, reduction, grad_scale, loss_per_sample,
-                                                    loss_out, dlogits, probs1, preds, ncorrect, batch, num_classes);
-  VITK_LAUNCH_CHECK();
+  VITK_LAUNCH((focal_kernel), 1, 256, 0, (cudaStream_t)stream, logits, targets, alpha, gamma, reduction, grad_scale, loss_per_sample, loss_out, dlogits, probs1, preds, ncorrect, batch, num_classes);
   return VITK_OK;
 }

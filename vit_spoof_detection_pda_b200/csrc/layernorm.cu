@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ gamma,
               const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int rows, float eps) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -87,6 +88,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_s
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* dres, float* dx, bf16* __restrict__ dx16,  // dres may alias dx (in-place residual-grad update)
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx_colsum, int rows) {
+  pdl_sync();
   extern __shared__ float ln_acc[];  // [warp][3][768]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* acc_g = ln_acc + (size_t)warp * 3 * LN_COLS;
@@ -171,9 +173,9 @@ extern "C" int vitk_layernorm_fwd(const float* x, int64_t x_stride, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   if (y_dtype == VITK_F32)
-    ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, st>>>(x, x_stride, gamma, beta, (float*)y, mean, rstd, rows, eps);
+    VITK_LAUNCH((ln_fwd_kernel<float>), grid, LN_WARPS * 32, 0, st, x, x_stride, gamma, beta, (float*)y, mean, rstd, rows, eps);
   else if (y_dtype == VITK_BF16)
-    ln_fwd_kernel<bf16><<<grid, LN_WARPS * 32, 0, st>>>(x, x_stride, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
+    VITK_LAUNCH((ln_fwd_kernel<bf16>), grid, LN_WARPS * 32, 0, st, x, x_stride, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
   else
     VITK_CHECK_ARG(!"bad dtype");
   VITK_LAUNCH_CHECK();
@@ -198,11 +200,9 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, 
   const int cap = sm_count() * 2;  // 2 CTAs per SM are co-resident (launch bounds): one persistent wave
   if (grid > cap) grid = cap;
   if (dy_dtype == VITK_F32)
-    ln_bwd_kernel<float><<<grid, LN_WARPS * 32, LN_BWD_SMEM, st>>>((const float*)dy, x, x_stride, gamma, mean, rstd, dres,
-                                                                  dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
+    VITK_LAUNCH((ln_bwd_kernel<float>), grid, LN_WARPS * 32, LN_BWD_SMEM, st, (const float*)dy, x, x_stride, gamma, mean, rstd, dres, dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
   else if (dy_dtype == VITK_BF16)
-    ln_bwd_kernel<bf16><<<grid, LN_WARPS * 32, LN_BWD_SMEM, st>>>((const bf16*)dy, x, x_stride, gamma, mean, rstd, dres,
-                                                                 dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
+    VITK_LAUNCH((ln_bwd_kernel<bf16>), grid, LN_WARPS * 32, LN_BWD_SMEM, st, (const bf16*)dy, x, x_stride, gamma, mean, rstd, dres, dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
   else
     VITK_CHECK_ARG(!"bad dtype");
   VITK_LAUNCH_CHECK();

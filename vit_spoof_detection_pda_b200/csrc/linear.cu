@@ -47,6 +47,7 @@ static int run_gemm(const GemmProblem& p, int engine, int simt_splits, cudaStrea
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ dy, MatLayout l, int M, int C, int rows_per_block, float* __restrict__ db) {
+  pdl_sync();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -71,6 +72,7 @@ template <int CHUNKS>
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ dy, int64_t ld, int64_t blk_stride, int M, int rows_per_block,
                    float* __restrict__ db, int db_blk_stride) {
+  pdl_sync();
   constexpr int RL = 256 / CHUNKS;
   __shared__ float red[RL][CHUNKS * 8 + 1];
   const int ch = threadIdx.x % CHUNKS, rl = threadIdx.x / CHUNKS;
@@ -101,8 +103,7 @@ static int colsum(const void* dy, int dtype, MatLayout l, int M, int C, float* d
       int rows_per_block = (M + (4 * sms / nblk)) / (4 * sms / nblk + 1);
       if (rows_per_block < 64) rows_per_block = 64;
       dim3 grid(1, (M + rows_per_block - 1) / rows_per_block, nblk);
-      colsum_bf16_kernel<8><<<grid, 256, 0, st>>>((const bf16*)dy, 64, l.s_blk, M, rows_per_block, db, 64);
-      VITK_LAUNCH_CHECK();
+      VITK_LAUNCH((colsum_bf16_kernel<8>), grid, 256, 0, st, (const bf16*)dy, 64, l.s_blk, M, rows_per_block, db, 64);
       return VITK_OK;
     }
     if (l.split == 0 && l.s_col == 1 && C % 256 == 0) {
@@ -110,16 +111,14 @@ static int colsum(const void* dy, int dtype, MatLayout l, int M, int C, float* d
       int rows_per_block = (M + (4 * sms / slabs)) / (4 * sms / slabs + 1);
       if (rows_per_block < 64) rows_per_block = 64;
       dim3 grid(slabs, (M + rows_per_block - 1) / rows_per_block, 1);
-      colsum_bf16_kernel<32><<<grid, 256, 0, st>>>((const bf16*)dy, l.s_row, 0, M, rows_per_block, db, 0);
-      VITK_LAUNCH_CHECK();
+      VITK_LAUNCH((colsum_bf16_kernel<32>), grid, 256, 0, st, (const bf16*)dy, l.s_row, 0, M, rows_per_block, db, 0);
       return VITK_OK;
     }
   }
   const int rows_per_block = 512;
   dim3 grid((C + 31) / 32, (M + rows_per_block - 1) / rows_per_block);
-  if (dtype == VITK_BF16) colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, l, M, C, rows_per_block, db);
-  else colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, l, M, C, rows_per_block, db);
-  VITK_LAUNCH_CHECK();
+  if (dtype == VITK_BF16) VITK_LAUNCH((colsum_kernel<bf16>), grid, 256, 0, st, (const bf16*)dy, l, M, C, rows_per_block, db);
+  else VITK_LAUNCH((colsum_kernel<float>), grid, 256, 0, st, (const float*)dy, l, M, C, rows_per_block, db);
   return VITK_OK;
 }
 
@@ -132,6 +131,7 @@ int colsum_headmajor(const void* x, int dtype, int M, int C, float* db, cudaStre
 template <typename T>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ img, T* __restrict__ patches, int batch) {
+  pdl_sync();
   const int64_t total = (int64_t)batch * VITK_NTOK * (VITK_DIM / 4);
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int k4 = (int)(idx % (VITK_DIM / 4));
@@ -159,6 +159,7 @@ im2col_kernel(const float* __restrict__ img, T* __restrict__ patches, int batch)
 __global__ void __launch_bounds__(256)
 embed_param_grads_kernel(const float* __restrict__ dx0, int batch, float* __restrict__ dpos,
                          float* __restrict__ dcls, float* __restrict__ dbpe) {
+  pdl_sync();
   const int t = blockIdx.x;
   for (int j = threadIdx.x; j < VITK_DIM; j += blockDim.x) {
     float s = 0.f;
@@ -279,9 +280,8 @@ extern "C" int vitk_patch_embed_fwd(const float* images, const void* wpe, const 
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = (int64_t)batch * VITK_NTOK * (VITK_DIM / 4);
   const int grid = (int)((total + 255) / 256 < (int64_t)sm_count() * 16 ? (total + 255) / 256 : (int64_t)sm_count() * 16);
-  if (dtype == VITK_BF16) im2col_kernel<bf16><<<grid, 256, 0, st>>>(images, (bf16*)patches, batch);
-  else im2col_kernel<float><<<grid, 256, 0, st>>>(images, (float*)patches, batch);
-  VITK_LAUNCH_CHECK();
+  if (dtype == VITK_BF16) VITK_LAUNCH((im2col_kernel<bf16>), grid, 256, 0, st, images, (bf16*)patches, batch);
+  else VITK_LAUNCH((im2col_kernel<float>), grid, 256, 0, st, images, (float*)patches, batch);
   GemmProblem p{};
   p.I = batch * VITK_NTOK; p.J = VITK_DIM; p.R = VITK_DIM;
   p.A = patches; p.B = wpe; p.in_dtype = dtype;
@@ -299,7 +299,6 @@ extern "C" int vitk_patch_embed_wgrad(const float* dx0, const void* dx0_act, con
   // CLS rows of `patches` are zero, so the plain token-row wgrad is exact (no row remap needed)
   VITK_TRY(vitk_linear_wgrad(dx0_act, VITK_LAYOUT_ROWMAJOR, patches, dwpe, nullptr, batch * VITK_NTOK, VITK_DIM,
                              VITK_DIM, dtype, engine, stream));
-  embed_param_grads_kernel<<<VITK_NTOK, 256, 0, st>>>(dx0, batch, dpos, dcls, dbpe);
-  VITK_LAUNCH_CHECK();
+  VITK_LAUNCH((embed_param_grads_kernel), VITK_NTOK, 256, 0, st, dx0, batch, dpos, dcls, dbpe);
   return VITK_OK;
 }

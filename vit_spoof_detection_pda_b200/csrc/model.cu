@@ -110,6 +110,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 scatter_cls_grad_kernel(const float* __restrict__ dxc, float* __restrict__ dx, T* __restrict__ dx16, int64_t M,
                         float* __restrict__ colsum) {
+  pdl_sync();
   const int64_t total = M * (D / 4);
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = idx / (D / 4);
@@ -270,8 +271,7 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
                                 m->batch, st));
     const int64_t total = (int64_t)M * (D / 4);
     const int grid = (int)((total + 255) / 256 < (int64_t)sm_count() * 8 ? (total + 255) / 256 : (int64_t)sm_count() * 8);
-    scatter_cls_grad_kernel<bf16><<<grid, 256, 0, c.st>>>(dxc, dx, (bf16*)dx16, M, c.G(po.blk[m->depth - 1].fc2b));
-    VITK_LAUNCH_CHECK();
+    VITK_LAUNCH((scatter_cls_grad_kernel<bf16>), grid, 256, 0, c.st, dxc, dx, (bf16*)dx16, M, c.G(po.blk[m->depth - 1].fc2b));
     return VITK_OK;
   }
   if (m->frozen_backbone) return VITK_OK;
