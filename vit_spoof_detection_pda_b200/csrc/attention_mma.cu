@@ -692,7 +692,10 @@ constexpr size_t AM_BWD_SMEM = 4 * AM_MAT_BYTES + (2 * AM_NP + 3 * AM_D) * sizeo
 
 int colsum_headmajor(const void* x, int dtype, int M, int C, float* db, cudaStream_t st);
 
+int attn_fwd_tc(const void* qkv, void* out, float* lse, int batch, cudaStream_t st);
+
 int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t st) {
+  if (attn_debug_variant() == 0) return attn_fwd_tc(qkv, out, lse, batch, st);   // default: tcgen05 kernel (attention_tc.cu)
   static bool configured = false;
   if (!configured) {
     VITK_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AM_FWD_SMEM));
@@ -708,8 +711,15 @@ int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t
   return VITK_OK;
 }
 
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch, cudaStream_t st);
+
 int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum,
                  int batch, cudaStream_t st) {
+  if (attn_debug_variant() == 0) {   // default: tcgen05 kernel (attention_tc.cu)
+    VITK_TRY(attn_bwd_tc(qkv, out, dout, lse, dqkv, batch, st));
+    if (dqkv_colsum) VITK_TRY(colsum_headmajor(dqkv, VITK_BF16, batch * VITK_NTOK, 3 * VITK_DIM, dqkv_colsum, st));
+    return VITK_OK;
+  }
   static bool configured = false;
   if (!configured) {
     VITK_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AM_BWD_SMEM));

@@ -1,0 +1,787 @@
+// Fused multi-head self-attention for sequence length 197, d = 64 on the 5th-generation tensor cores
+// (tcgen05.mma, accumulators and the probability matrix in tensor memory, operands staged by TMA).
+// Replaces F.scaled_dot_product_attention reached from timm Attention.forward
+// (/root/reference/train_advanced.py:203 -> self.vit(x)).
+//
+// One persistent CTA per SM walks (batch, head) items; 320 threads:
+//   warp 0      TMA producer: Q (256-row box), K, V (208-row boxes) of the NEXT item land in the other smem stage
+//               while the current item computes (head-major q/k/v: one item is three dense [197][64] tiles)
+//   warp 1      MMA issuer (one elected lane):
+//                 S_t  = Q_t K^T        t = 0,1: query rows 128t..128t+127, N = 208 keys, K = 64   -> TMEM cols 208t..
+//                 O_t  = P_t V          A operand P_t read from TENSOR MEMORY (bf16, written over S_t by the
+//                                       softmax warps), B = V as an MN-major shared-memory operand, K = 208 keys
+//   warps 2..9  softmax / epilogue: lane = query row (tcgen05.ld 32x32b); two passes over the 208 scores (row max, then
+//               exp2 + row sum + bf16 pack -> tcgen05.st in place), later O_t * (1/l) -> global, log-sum-exp saved.
+// Rows / keys 197..255 of the boxes are other items' rows (or TMA zero fill at the end of the tensor): rows only
+// pollute their own (never stored) output rows, key columns >= 197 are masked to p = 0.
+// Algorithmic FLOPs per item: 4 * 197^2 * 64; exps: 197 * 208 (MUFU-bound: 16/clk/SM).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace vitk {
+
+int attn_debug_variant();  // gemm_tc.cu: vitk_debug_set(3, v)
+
+namespace atc {
+
+constexpr int N_TOK = VITK_NTOK;            // 197
+constexpr int NK = 208;                     // key columns of S (multiple of 16)
+constexpr int THREADS = 320;
+constexpr uint32_t Q_BYTES = 256 * 128;     // 32 KB  (two 128-row A tiles)
+constexpr uint32_t KV_BYTES = NK * 128;     // 26 KB
+constexpr uint32_t STAGE_BYTES = Q_BYTES + 2 * KV_BYTES;   // 86,016
+constexpr uint32_t BAR_OFF = 2 * STAGE_BYTES;
+constexpr size_t FWD_SMEM = 1024 + 2 * STAGE_BYTES + 256;
+constexpr float SCALE = 0.125f;
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                       uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]      (A: 128 lanes x K bf16, two per 32-bit column)
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tm_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tm_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tm_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// instruction descriptor: D = f32, A = B = bf16, majors, N >> 3, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+// shared-memory matrix descriptor halves (SWIZZLE_128B, 8-row groups 1024 B apart)
+constexpr uint32_t DESC_HI = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                   bf16* __restrict__ out, float* __restrict__ lse, int batch, int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + BAR_OFF;
+  // barriers: ld_full[2] | ld_empty[2] | s_full[2] | p_full[2] | o_full[2] | t_free[2] | tmem ptr
+  auto ld_full = [&](int s) { return bars + 8u * s; };
+  auto ld_empty = [&](int s) { return bars + 8u * (2 + s); };
+  auto s_full = [&](int t) { return bars + 8u * (4 + t); };
+  auto p_full = [&](int t) { return bars + 8u * (6 + t); };
+  auto o_full = [&](int t) { return bars + 8u * (8 + t); };
+  auto t_free = [&](int t) { return bars + 8u * (10 + t); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + 8 * 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_kv)) : "memory");
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(ld_full(s), 1);
+      mbar_init(ld_empty(s), 1);
+      mbar_init(s_full(s), 1);
+      mbar_init(p_full(s), 4);     // the four softmax warps of a 128-row tile
+      mbar_init(o_full(s), 1);
+      mbar_init(t_free(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();
+
+  const int64_t M = (int64_t)batch * N_TOK;
+  const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const bool leader = elect_one();
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
+      const int s = it & 1;
+      mbar_wait(ld_empty(s), ((it >> 1) & 1) ^ 1);
+      if (leader) {
+        mbar_expect_tx(ld_full(s), STAGE_BYTES);
+        const uint32_t dst = sbase + s * STAGE_BYTES;
+        tma_load_3d(dst, &map_q, ld_full(s), 0, b * N_TOK, h);
+        tma_load_3d(dst + Q_BYTES, &map_kv, ld_full(s), 0, b * N_TOK, VITK_HEADS + h);
+        tma_load_3d(dst + Q_BYTES + KV_BYTES, &map_kv, ld_full(s), 0, b * N_TOK, 2 * VITK_HEADS + h);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    constexpr uint32_t IDESC_S = make_idesc(NK, 0, 0);    // S = Q K^T : both K-major, N = 208
+    constexpr uint32_t IDESC_O = make_idesc(64, 0, 1);    // O = P V   : A in TMEM, B = V MN-major, N = 64
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it & 1;
+      const uint32_t par = it & 1;
+      const uint32_t sq = sbase + s * STAGE_BYTES, sk = sq + Q_BYTES, sv = sk + KV_BYTES;
+      mbar_wait(ld_full(s), (it >> 1) & 1);
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(t_free(t), par ^ 1);     // the previous item's O_t has been read out of tensor memory
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(tmem_base + t * NK, desc_lo(sq + t * 16384 + k * 32), DESC_HI, desc_lo(sk + k * 32), DESC_HI, IDESC_S, k > 0 ? 1u : 0u);
+          tc_commit(s_full(t));
+        }
+        __syncwarp();
+      }
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(p_full(t), par);         // P_t (bf16) is in tensor memory columns [208t, 208t + 104)
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < NK / 16; ++ks)
+            mma_ts(tmem_base + t * NK + 128, tmem_base + t * NK + ks * 8, desc_lo(sv + ks * 2048), DESC_HI, IDESC_O, ks > 0 ? 1u : 0u);
+          tc_commit(o_full(t));
+          if (t == 1) tc_commit(ld_empty(s));   // every MMA reading this stage has retired
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue warps =====================
+    const int we = warp - 2;
+    const int t = we >> 2;               // 128-row tile of this warp
+    const int qr = warp & 3;             // TMEM lane quarter this warp may touch
+    const int row = qr * 32 + lane;      // row inside the tile
+    const int q = t * 128 + row;         // query index
+    const bool warp_valid = (t * 128 + qr * 32) < N_TOK;
+    const uint32_t taddr = tmem_base + ((uint32_t)(qr * 32) << 16) + (uint32_t)(t * NK);
+    const float sl2 = SCALE * LOG2E;
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
+      const uint32_t par = it & 1;
+      mbar_wait(s_full(t), par);
+      tc_fence_after();
+      float m = -INFINITY, l = 0.f;
+      if (warp_valid) {
+        // ---- pass 1: row max over the 197 valid keys
+        uint32_t v[32];
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+          tm_ld32(taddr + c * 32, v);
+          tm_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        uint32_t w[16];
+        tm_ld16(taddr + 192, w);
+        tm_ld_wait();
+#pragma unroll
+        for (int j = 0; j < N_TOK - 192; ++j) m = fmaxf(m, __uint_as_float(w[j]));
+        const float mb = m * sl2;
+        // ---- pass 2: p = 2^(s*scale*log2e - max), row sum, bf16 pairs written over S (32 scores -> 16 columns)
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+          tm_ld32(taddr + c * 32, v);
+          tm_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), sl2, -mb));
+            const float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb));
+            l += p0 + p1;
+            pk[j] = pack_bf16x2(p0, p1);
+          }
+          tm_st16(taddr + c * 16, pk);
+        }
+        tm_ld16(taddr + 192, w);
+        tm_ld_wait();
+        uint32_t pk8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k0 = 192 + 2 * j;
+          const float p0 = k0 < N_TOK ? ex2(fmaf(__uint_as_float(w[2 * j]), sl2, -mb)) : 0.f;
+          const float p1 = k0 + 1 < N_TOK ? ex2(fmaf(__uint_as_float(w[2 * j + 1]), sl2, -mb)) : 0.f;
+          l += p0 + p1;
+          pk8[j] = pack_bf16x2(p0, p1);
+        }
+        tm_st8(taddr + 96, pk8);
+        tm_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(t));
+      // ---- O_t = P_t V is accumulated into columns [208t + 128, 208t + 192)
+      mbar_wait(o_full(t), par);
+      tc_fence_after();
+      if (warp_valid) {
+        uint32_t o[32];
+        const float inv = 1.0f / l;
+        bf16* orow = out + ((int64_t)b * N_TOK + q) * VITK_DIM + h * VITK_HEAD_DIM;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tm_ld32(taddr + 128 + half * 32, o);
+          tm_ld_wait();
+          if (q < N_TOK) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+              u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+              u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+              u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + half * 32 + j * 8) = u;
+            }
+          }
+        }
+        if (lse && q < N_TOK) lse[(int64_t)h * M + (int64_t)b * N_TOK + q] = m * SCALE + logf(l);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_free(t));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// head-major [n_blk][M][64] bf16 -> 3-D map (64, M, n_blk), box (64, box_rows, 1), SWIZZLE_128B
+static int make_hm_map(const void* base, int64_t M, int n_blk, int box_rows, CUtensorMap* map) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return VITK_ERR_DRIVER; }
+  cuuint64_t dims[3] = {64, (cuuint64_t)M, (cuuint64_t)n_blk};
+  cuuint64_t strides[2] = {128, (cuuint64_t)M * 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
+  if ((uintptr_t)base & 15) { set_error("attention: qkv must be 16-byte aligned"); return VITK_ERR_ARG; }
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention) failed: CUresult %d", (int)r); return VITK_ERR_DRIVER; }
+  return VITK_OK;
+}
+
+
+// ================================================================================================
+// backward:  dQ, dK, dV from dO with P recomputed from the saved log-sum-exp -- no recomputation of S beyond that,
+// every product on tcgen05.  Key-major formulation, per item two key tiles t (128 keys) x four query chunks c
+// (64, 64, 64, 16 queries) = 8 steps; per step
+//     MMA1  S^T  = K_t Q_c^T          MMA2  dP^T = V_t dO_c^T            (A, B from smem, D = TMEM buffer s & 1)
+//     softmax warps (lane = key): P^T = 2^(S^T*scale*log2e - L_q), dS^T = P^T o (dP^T - D_q)  -> bf16, written in place
+//           into tensor memory (A operands of MMA3/4) and, dS^T only, into shared memory in the UMMA MN-major layout
+//     MMA3  dV_t += P^T dO_c          MMA4  dK_t += dS^T Q_c             (A from TMEM, B = MN-major smem operand)
+//     MMA5  dQ_m += dS_(m,t) K_t      after chunks 2m, 2m+1              (A = dS^T smem read MN-major, M = queries)
+// Tensor memory (512 columns): 2 x (S^T 64 | dP^T 64) | dV 64 | dK 64 | dQ 2 x 64.
+// Shared memory operands are single-buffered but recycled at box granularity (K/V per key tile, Q/dO per chunk): the
+// producer refills a box with the next item's rows as soon as the last MMA reading it has retired, so loads overlap
+// the second key tile of the current item.
+// ================================================================================================
+constexpr uint32_t B_SK = 0, B_SV = 32768, B_SQ = 65536, B_SDO = 98304, B_SDS = 131072;   // byte offsets
+constexpr uint32_t B_SL = B_SDS + 65536, B_SD = B_SL + 1024, B_BAR = B_SD + 1024;
+constexpr size_t BWD_SMEM = 1024 + B_BAR + 512;
+constexpr uint32_t T_DV = 256, T_DK = 320, T_DQ = 384;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
+                   const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ out, const float* __restrict__ lse,
+                   bf16* __restrict__ dqkv, int batch, int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + B_BAR;
+  // barriers (8 B each)
+  auto kv_full = [&](int t) { return bars + 8u * t; };          // 0,1
+  auto kv_free = [&](int t) { return bars + 8u * (2 + t); };    // 2,3
+  auto qd_full = [&](int c) { return bars + 8u * (4 + c); };    // 4..7
+  auto qd_free = [&](int c) { return bars + 8u * (8 + c); };    // 8..11
+  auto st_full = [&](int b) { return bars + 8u * (12 + b); };   // 12,13
+  auto p_full = [&](int b) { return bars + 8u * (14 + b); };    // 14,15
+  auto ds_free = [&](int m) { return bars + 8u * (16 + m); };   // 16,17
+  const uint32_t dvk_full = bars + 8u * 18, dvk_free = bars + 8u * 19, dq_full = bars + 8u * 20, dq_free = bars + 8u * 21;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + B_BAR + 8 * 22);
+  float* sL = reinterpret_cast<float*>(smem + B_SL);
+  float* sD = reinterpret_cast<float*>(smem + B_SD);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_kv)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_do)) : "memory");
+    for (int i = 0; i < 2; ++i) { mbar_init(kv_full(i), 1); mbar_init(kv_free(i), 1); mbar_init(st_full(i), 1); mbar_init(p_full(i), 8); mbar_init(ds_free(i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(qd_full(i), 1); mbar_init(qd_free(i), 1); }
+    mbar_init(dvk_full, 1); mbar_init(dvk_free, 8); mbar_init(dq_full, 1); mbar_init(dq_free, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();
+
+  const int64_t M = (int64_t)batch * N_TOK;
+  const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const bool leader = elect_one();
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
+      const uint32_t fpar = (it & 1) ^ 1;     // the box was released once per previous item
+      auto load_kv = [&](int t) {
+        mbar_wait(kv_free(t), fpar);
+        if (leader) {
+          mbar_expect_tx(kv_full(t), 32768);
+          tma_load_3d(sbase + B_SK + t * 16384, &map_kv, kv_full(t), 0, b * N_TOK + t * 128, VITK_HEADS + h);
+          tma_load_3d(sbase + B_SV + t * 16384, &map_kv, kv_full(t), 0, b * N_TOK + t * 128, 2 * VITK_HEADS + h);
+        }
+        __syncwarp();
+      };
+      load_kv(0);
+      for (int c = 0; c < 4; ++c) {
+        mbar_wait(qd_free(c), fpar);
+        if (leader) {
+          mbar_expect_tx(qd_full(c), 16384);
+          tma_load_3d(sbase + B_SQ + c * 8192, &map_q, qd_full(c), 0, b * N_TOK + c * 64, h);
+          tma_load_2d(sbase + B_SDO + c * 8192, &map_do, qd_full(c), h * VITK_HEAD_DIM, b * N_TOK + c * 64);
+        }
+        __syncwarp();
+      }
+      load_kv(1);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    constexpr uint32_t ID_S64 = make_idesc(64, 0, 0), ID_S16 = make_idesc(16, 0, 0);   // S^T / dP^T chunks
+    constexpr uint32_t ID_TS = make_idesc(64, 0, 1);                                    // dV, dK: A in TMEM, B MN-major
+    constexpr uint32_t ID_DQ = make_idesc(64, 1, 1);                                    // dQ: A, B MN-major
+    const uint32_t sK = sbase + B_SK, sV = sbase + B_SV, sQ = sbase + B_SQ, sdO = sbase + B_SDO, sDS = sbase + B_SDS;
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t ipar = it & 1;
+      // front(s): MMA1, MMA2 of step s;  back(s): MMA3, MMA4 (and MMA5 after odd chunks) of step s
+      auto front = [&](int s) {
+        const int t = s >> 2, c = s & 3, buf = s & 1;
+        if (c == 0) mbar_wait(kv_full(t), ipar);
+        if (t == 0) mbar_wait(qd_full(c), ipar);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t idesc = c < 3 ? ID_S64 : ID_S16;
+          const uint32_t d_st = tmem_base + buf * 128, d_dp = d_st + 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(d_st, desc_lo(sK + t * 16384 + k * 32), DESC_HI, desc_lo(sQ + c * 8192 + k * 32), DESC_HI, idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_ss(d_dp, desc_lo(sV + t * 16384 + k * 32), DESC_HI, desc_lo(sdO + c * 8192 + k * 32), DESC_HI, idesc, k > 0 ? 1u : 0u);
+          tc_commit(st_full(buf));
+        }
+        __syncwarp();
+      };
+      auto back = [&](int s) {
+        const int t = s >> 2, c = s & 3, buf = s & 1;
+        const int n_b = it * 4 + (s >> 1);                 // completions of this buffer's barriers so far
+        mbar_wait(p_full(buf), n_b & 1);
+        if (c == 0) mbar_wait(dvk_free, ((it * 2 + t) & 1) ^ 1);   // the previous dV / dK tile has been read out
+        tc_fence_after();
+        if (leader) {
+          const uint32_t a_p = tmem_base + buf * 128, a_ds = a_p + 64;
+          const int nks = c < 3 ? 4 : 1;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+            mma_ts(tmem_base + T_DV, a_p + ks * 8, desc_lo(sdO + c * 8192 + ks * 2048), DESC_HI, ID_TS, acc);
+            mma_ts(tmem_base + T_DK, a_ds + ks * 8, desc_lo(sQ + c * 8192 + ks * 2048), DESC_HI, ID_TS, acc);
+          }
+          if (t == 1) tc_commit(qd_free(c));       // Q_c / dO_c no longer needed by this item
+          if (c == 3) tc_commit(dvk_full);         // dV_t, dK_t complete
+        }
+        __syncwarp();
+        if (c & 1) {
+          const int m = c >> 1;
+          if (t == 0) mbar_wait(dq_free, ipar ^ 1);          // the previous item's dQ has been read out
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              mma_ss(tmem_base + T_DQ + m * 64, desc_lo_mn(sDS + m * 32768 + ks * 2048, 16384), DESC_HI,
+                     desc_lo(sK + t * 16384 + ks * 2048), DESC_HI, ID_DQ, (t > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(ds_free(m));
+            if (m == 1) tc_commit(kv_free(t));     // K_t / V_t no longer needed
+            if (t == 1 && m == 1) tc_commit(dq_full);
+          }
+          __syncwarp();
+        }
+      };
+      front(0);
+      for (int s = 1; s < 8; ++s) {
+        front(s);
+        back(s - 1);
+      }
+      back(7);
+    }
+  } else {
+    // ===================== softmax / epilogue warps =====================
+    const int we = warp - 2;
+    const int qr = warp & 3;             // TMEM lane quarter
+    const int ch = we >> 2;              // column half (32 of the 64 chunk columns) / output selector
+    const int row = qr * 32 + lane;      // TMEM lane = key (steps, dV/dK) or query (dQ) inside a 128-row tile
+    const int tid = we * 32 + lane;      // 0..255
+    const float sl2 = SCALE * LOG2E;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(qr * 32) << 16);
+    const uint32_t sdO = sbase + B_SDO, sDS = sbase + B_SDS;
+    const int64_t hstride = (int64_t)VITK_HEADS * M * 64;
+    uint4 ov[8];
+    float lsv = 0.f;
+    auto fetch_o = [&](int item) {
+      if (tid < N_TOK) {
+        const int b = item / VITK_HEADS, h = item % VITK_HEADS;
+        const uint4* op = reinterpret_cast<const uint4*>(out + ((int64_t)b * N_TOK + tid) * VITK_DIM + h * VITK_HEAD_DIM);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) ov[c8] = __ldg(op + c8);
+        lsv = __ldg(lse + (int64_t)h * M + (int64_t)b * N_TOK + tid);
+      }
+    };
+    if (n_my > 0) fetch_o(blockIdx.x);
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
+      const uint32_t ipar = it & 1;
+      const int64_t hm = ((int64_t)h * M + (int64_t)b * N_TOK) * 64;
+#pragma unroll 1
+      for (int s = 0; s < 8; ++s) {
+        const int t = s >> 2, c = s & 3, buf = s & 1, m = c >> 1;
+        const int n_b = it * 4 + (s >> 1);
+        const int key = t * 128 + row;
+        mbar_wait(st_full(buf), n_b & 1);      // MMA1/2 of this step retired: Q_c / dO_c are in shared memory
+        if ((c & 1) == 0) mbar_wait(ds_free(m), ((it * 2 + t) & 1) ^ 1);   // MMA5 of the previous key tile has read dS^T buffer m
+        tc_fence_after();
+        if (t == 0) {
+          // ---- delta_q = dO_q . O_q and L_q = lse_q * log2(e) of this chunk's 64 queries (thread tid = query tid)
+          if ((tid >> 6) == c) {
+            float dl = 0.f, ls = 0.f;
+            if (tid < N_TOK) {
+              const int r = tid & 63;
+              const uint32_t rb = sdO + c * 8192 + r * 128;
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8) {
+                uint4 av;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(av.x), "=r"(av.y), "=r"(av.z), "=r"(av.w) : "r"(rb + ((c8 ^ (r & 7)) << 4)));
+                const float2 a0 = unpack_bf16x2(av.x), a1 = unpack_bf16x2(av.y), a2 = unpack_bf16x2(av.z), a3 = unpack_bf16x2(av.w);
+                const float2 o0 = unpack_bf16x2(ov[c8].x), o1 = unpack_bf16x2(ov[c8].y), o2 = unpack_bf16x2(ov[c8].z), o3 = unpack_bf16x2(ov[c8].w);
+                dl += a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
+              }
+              ls = lsv * LOG2E;
+            }
+            sD[tid] = dl;
+            sL[tid] = ls;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        } else if (s == 4 && it + 1 < n_my) {
+          fetch_o(item + gridDim.x);   // next item's O rows: in flight during this item's second key tile
+        }
+        const uint32_t a_st = lane_addr + buf * 128 + ch * 32, a_dp = a_st + 64;
+        const uint32_t ds_row = sDS + m * 32768 + (c & 1) * 16384 + row * 128;
+        if (c < 3) {
+          uint32_t vs[32], vd[32];
+          tm_ld32(a_st, vs);
+          tm_ld32(a_dp, vd);
+          tm_ld_wait();
+          // the partner warp (other column half, same lanes) must have read its scores before either overwrites them
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + qr) : "memory");
+          uint32_t pp[16], pd[16];
+          const int q0 = c * 64 + ch * 32;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 Lq = *reinterpret_cast<const float4*>(sL + q0 + j4 * 4);
+            const float4 Dq = *reinterpret_cast<const float4*>(sD + q0 + j4 * 4);
+            const float Lv[4] = {Lq.x, Lq.y, Lq.z, Lq.w}, Dv[4] = {Dq.x, Dq.y, Dq.z, Dq.w};
+            float p[4], d[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              p[e] = key < N_TOK ? ex2(fmaf(__uint_as_float(vs[j4 * 4 + e]), sl2, -Lv[e])) : 0.f;
+              d[e] = p[e] * (__uint_as_float(vd[j4 * 4 + e]) - Dv[e]);
+            }
+            pp[j4 * 2] = pack_bf16x2(p[0], p[1]); pp[j4 * 2 + 1] = pack_bf16x2(p[2], p[3]);
+            pd[j4 * 2] = pack_bf16x2(d[0], d[1]); pd[j4 * 2 + 1] = pack_bf16x2(d[2], d[3]);
+          }
+          tm_st16(lane_addr + buf * 128 + ch * 16, pp);
+          tm_st16(lane_addr + buf * 128 + 64 + ch * 16, pd);
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + (((ch * 4 + g4) ^ (row & 7)) << 4)),
+                         "r"(pd[g4 * 4]), "r"(pd[g4 * 4 + 1]), "r"(pd[g4 * 4 + 2]), "r"(pd[g4 * 4 + 3]) : "memory");
+          tm_st_wait();
+        } else if (ch == 0) {
+          // last chunk: queries 192..207 (16 columns), valid up to 196
+          uint32_t vs[16], vd[16];
+          tm_ld16(lane_addr + buf * 128, vs);
+          tm_ld16(lane_addr + buf * 128 + 64, vd);
+          tm_ld_wait();
+          uint32_t pp[8], pd[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float p[2], d[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int q = 192 + 2 * j + e;
+              p[e] = (key < N_TOK && q < N_TOK) ? ex2(fmaf(__uint_as_float(vs[2 * j + e]), sl2, -sL[q])) : 0.f;
+              d[e] = p[e] * (__uint_as_float(vd[2 * j + e]) - sD[q]);
+            }
+            pp[j] = pack_bf16x2(p[0], p[1]);
+            pd[j] = pack_bf16x2(d[0], d[1]);
+          }
+          tm_st8(lane_addr + buf * 128, pp);
+          tm_st8(lane_addr + buf * 128 + 64, pd);
+#pragma unroll
+          for (int g4 = 0; g4 < 2; ++g4)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + ((g4 ^ (row & 7)) << 4)),
+                         "r"(pd[g4 * 4]), "r"(pd[g4 * 4 + 1]), "r"(pd[g4 * 4 + 2]), "r"(pd[g4 * 4 + 3]) : "memory");
+          tm_st_wait();
+        }
+        fence_proxy_async_smem();     // dS^T rows in shared memory are read by the tensor core (async proxy)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(buf));
+
+        if (c == 3) {
+          // ---- dV_t (ch 0) / dK_t (ch 1): lane = key
+          mbar_wait(dvk_full, (it * 2 + t) & 1);
+          tc_fence_after();
+          bf16* dst = dqkv + hm + (ch == 0 ? 2 : 1) * hstride + (int64_t)key * 64;
+          const float sc = ch == 0 ? 1.0f : SCALE;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t o[32];
+            tm_ld32(lane_addr + (ch == 0 ? T_DV : T_DK) + half * 32, o);
+            tm_ld_wait();
+            if (key < N_TOK) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * sc, __uint_as_float(o[8 * j + 1]) * sc);
+                u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * sc, __uint_as_float(o[8 * j + 3]) * sc);
+                u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * sc, __uint_as_float(o[8 * j + 5]) * sc);
+                u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * sc, __uint_as_float(o[8 * j + 7]) * sc);
+                *reinterpret_cast<uint4*>(dst + half * 32 + j * 8) = u;
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dvk_free);
+        }
+      }
+      // ---- dQ: q-tile m = ch, lane = query
+      {
+        mbar_wait(dq_full, ipar);
+        tc_fence_after();
+        const int q = ch * 128 + row;
+        bf16* dst = dqkv + hm + (int64_t)q * 64;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o[32];
+          tm_ld32(lane_addr + T_DQ + ch * 64 + half * 32, o);
+          tm_ld_wait();
+          if (q < N_TOK) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * SCALE, __uint_as_float(o[8 * j + 1]) * SCALE);
+              u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * SCALE, __uint_as_float(o[8 * j + 3]) * SCALE);
+              u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * SCALE, __uint_as_float(o[8 * j + 5]) * SCALE);
+              u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * SCALE, __uint_as_float(o[8 * j + 7]) * SCALE);
+              *reinterpret_cast<uint4*>(dst + half * 32 + j * 8) = u;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_free);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// dout [M][768] bf16 -> 2-D map (768, M), box (64, 64), SWIZZLE_128B
+static int make_dout_map(const void* base, int64_t M, CUtensorMap* map) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return VITK_ERR_DRIVER; }
+  cuuint64_t dims[2] = {(cuuint64_t)VITK_DIM, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)VITK_DIM * 2};
+  cuuint32_t box[2] = {64, 64}, estr[2] = {1, 1};
+  if ((uintptr_t)base & 15) { set_error("attention: dout must be 16-byte aligned"); return VITK_ERR_ARG; }
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention dout) failed: CUresult %d", (int)r); return VITK_ERR_DRIVER; }
+  return VITK_OK;
+}
+
+}  // namespace atc
+
+int attn_fwd_tc(const void* qkv, void* out, float* lse, int batch, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    VITK_CUDA(cudaFuncSetAttribute(atc::attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atc::FWD_SMEM));
+    configured = true;
+  }
+  const int64_t M = (int64_t)batch * VITK_NTOK;
+  CUtensorMap map_q, map_kv;
+  VITK_TRY(atc::make_hm_map(qkv, M, 3 * VITK_HEADS, 256, &map_q));
+  VITK_TRY(atc::make_hm_map(qkv, M, 3 * VITK_HEADS, atc::NK, &map_kv));
+  const int items = batch * VITK_HEADS, sms = sm_count();
+  VITK_LAUNCH((atc::attn_fwd_tc_kernel), (items < sms ? items : sms), atc::THREADS, atc::FWD_SMEM, st, map_q, map_kv, (bf16*)out, lse, batch, items);
+  return VITK_OK;
+}
+
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    VITK_CUDA(cudaFuncSetAttribute(atc::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atc::BWD_SMEM));
+    configured = true;
+  }
+  const int64_t M = (int64_t)batch * VITK_NTOK;
+  CUtensorMap map_kv, map_q, map_do;
+  VITK_TRY(atc::make_hm_map(qkv, M, 3 * VITK_HEADS, 128, &map_kv));
+  VITK_TRY(atc::make_hm_map(qkv, M, 3 * VITK_HEADS, 64, &map_q));
+  VITK_TRY(atc::make_dout_map(dout, M, &map_do));
+  const int items = batch * VITK_HEADS, sms = sm_count();
+  VITK_LAUNCH((atc::attn_bwd_tc_kernel), (items < sms ? items : sms), atc::THREADS, atc::BWD_SMEM, st, map_kv, map_q, map_do,
+              (const bf16*)out, lse, (bf16*)dqkv, batch, items);
+  return VITK_OK;
+}
+
+}  // namespace vitk
