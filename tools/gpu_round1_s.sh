@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+rm -f gpurun_out/s_attn.log
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 120 -x -k "attention" > gpurun_out/s_pytest.log 2>&1
+echo "pytest exit $?" > gpurun_out/s_status.log
+tail -3 gpurun_out/s_pytest.log | cut -c1-300
+for k in "" "7:3"; do
+  VITK_KNOBS="$k" timeout 300 python tools/attn_bench.py >> gpurun_out/s_attn.log 2>&1
+done
+cat gpurun_out/s_status.log gpurun_out/s_attn.log

@@ -22,6 +22,7 @@
 namespace vitk {
 
 int attn_debug_variant();  // gemm_tc.cu: vitk_debug_set(3, v)
+int debug_knob(int key);     // gemm_tc.cu: vitk_debug_set(key, v); key 7 = timing experiments (bit 0 no MMAs, bit 1 no softmax math)
 
 namespace atc {
 
@@ -31,8 +32,9 @@ constexpr int THREADS = 320;
 constexpr uint32_t Q_BYTES = 256 * 128;     // 32 KB  (two 128-row A tiles)
 constexpr uint32_t KV_BYTES = NK * 128;     // 26 KB
 constexpr uint32_t STAGE_BYTES = Q_BYTES + 2 * KV_BYTES;   // 86,016
-constexpr uint32_t BAR_OFF = 2 * STAGE_BYTES;
-constexpr size_t FWD_SMEM = 1024 + 2 * STAGE_BYTES + 256;
+constexpr uint32_t STG_OFF = 2 * STAGE_BYTES;                 // 8 epilogue warps x 2 KB staging tiles
+constexpr uint32_t BAR_OFF = STG_OFF + 8 * 2048;
+constexpr size_t FWD_SMEM = 1024 + BAR_OFF + 256;
 constexpr float SCALE = 0.125f;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -138,6 +140,36 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Output rows leave the SM coalesced: tcgen05.ld gives every lane one ROW (32 fp32 columns); the lane packs it to 64 B of
+// bf16 and writes it into a swizzled 32 x 64 B staging tile, then 4 lanes cooperate on each row, so one store
+// instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes (4x fewer cache lines per instruction:
+// row-per-thread stores measured ~17 us of a 92 us backward launch).
+//   stg: this warp's 2 KB staging tile; row_ptr(r): global address of column 0 of this 32-column slab in row r, or
+//   nullptr when row r must not be written.
+template <typename RowPtr>
+__device__ __forceinline__ void store_slab32(uint32_t stg, int lane, const uint32_t (&o)[32], float scale, RowPtr row_ptr) {
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    const uint32_t a = stg + (uint32_t)(lane * 64 + ((k4 ^ ((lane >> 1) & 3)) << 4));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                 "r"(pack_bf16x2(__uint_as_float(o[8 * k4 + 0]) * scale, __uint_as_float(o[8 * k4 + 1]) * scale)),
+                 "r"(pack_bf16x2(__uint_as_float(o[8 * k4 + 2]) * scale, __uint_as_float(o[8 * k4 + 3]) * scale)),
+                 "r"(pack_bf16x2(__uint_as_float(o[8 * k4 + 4]) * scale, __uint_as_float(o[8 * k4 + 5]) * scale)),
+                 "r"(pack_bf16x2(__uint_as_float(o[8 * k4 + 6]) * scale, __uint_as_float(o[8 * k4 + 7]) * scale)) : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), k4 = lane & 3;
+    uint4 u;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                 : "r"(stg + (uint32_t)(r * 64 + ((k4 ^ ((r >> 1) & 3)) << 4))));
+    bf16* dst = row_ptr(r);
+    if (dst) *reinterpret_cast<uint4*>(dst + k4 * 8) = u;
+  }
+  __syncwarp();
 }
 
 // instruction descriptor: D = f32, A = B = bf16, majors, N >> 3, M = 128
@@ -313,23 +345,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_after();
       if (warp_valid) {
         uint32_t o[32];
+        // 1/l of every row of this warp (the staging transpose hands rows to other lanes)
         const float inv = 1.0f / l;
-        bf16* orow = out + ((int64_t)b * N_TOK + q) * VITK_DIM + h * VITK_HEAD_DIM;
+        const int q0w = t * 128 + qr * 32;        // first query of this warp
+        bf16* obase = out + ((int64_t)b * N_TOK) * VITK_DIM + h * VITK_HEAD_DIM;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           tm_ld32(taddr + 128 + half * 32, o);
           tm_ld_wait();
-          if (q < N_TOK) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
-              u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
-              u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
-              u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
-              *reinterpret_cast<uint4*>(orow + half * 32 + j * 8) = u;
-            }
-          }
+          store_slab32(sbase + STG_OFF + (uint32_t)we * 2048, lane, o, inv,
+                       [&](int r) -> bf16* { return (q0w + r < N_TOK) ? obase + (int64_t)(q0w + r) * VITK_DIM + half * 32 : nullptr; });
         }
         if (lse && q < N_TOK) lse[(int64_t)h * M + (int64_t)b * N_TOK + q] = m * SCALE + logf(l);
       }
@@ -393,7 +418,7 @@ static int make_hm_map(const void* base, int64_t M, int n_blk, int box_rows, CUt
 // the second key tile of the current item.
 // ================================================================================================
 constexpr uint32_t B_SK = 0, B_SV = 32768, B_SQ = 65536, B_SDO = 98304, B_SDS = 131072;   // byte offsets
-constexpr uint32_t B_SL = B_SDS + 65536, B_SD = B_SL + 1024, B_BAR = B_SD + 1024;
+constexpr uint32_t B_SL = B_SDS + 65536, B_SD = B_SL + 1024, B_STG = B_SD + 1024, B_BAR = B_STG + 8 * 2048;
 constexpr size_t BWD_SMEM = 1024 + B_BAR + 512;
 constexpr uint32_t T_DV = 256, T_DK = 320, T_DQ = 384;
 
@@ -407,7 +432,7 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t lbo) { r
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
                    const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ out, const float* __restrict__ lse,
-                   bf16* __restrict__ dqkv, int batch, int n_items) {
+                   bf16* __restrict__ dqkv, int batch, int n_items, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -458,9 +483,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
       auto load_kv = [&](int t) {
         mbar_wait(kv_free(t), fpar);
         if (leader) {
-          mbar_expect_tx(kv_full(t), 32768);
-          tma_load_3d(sbase + B_SK + t * 16384, &map_kv, kv_full(t), 0, b * N_TOK + t * 128, VITK_HEADS + h);
-          tma_load_3d(sbase + B_SV + t * 16384, &map_kv, kv_full(t), 0, b * N_TOK + t * 128, 2 * VITK_HEADS + h);
+          if (dbg & 16) { mbar_arrive(kv_full(t)); }
+          else {
+            mbar_expect_tx(kv_full(t), 32768);
+            tma_load_3d(sbase + B_SK + t * 16384, &map_kv, kv_full(t), 0, b * N_TOK + t * 128, VITK_HEADS + h);
+            tma_load_3d(sbase + B_SV + t * 16384, &map_kv, kv_full(t), 0, b * N_TOK + t * 128, 2 * VITK_HEADS + h);
+          }
         }
         __syncwarp();
       };
@@ -468,9 +496,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
       for (int c = 0; c < 4; ++c) {
         mbar_wait(qd_free(c), fpar);
         if (leader) {
-          mbar_expect_tx(qd_full(c), 16384);
-          tma_load_3d(sbase + B_SQ + c * 8192, &map_q, qd_full(c), 0, b * N_TOK + c * 64, h);
-          tma_load_2d(sbase + B_SDO + c * 8192, &map_do, qd_full(c), h * VITK_HEAD_DIM, b * N_TOK + c * 64);
+          if (dbg & 16) { mbar_arrive(qd_full(c)); }
+          else {
+            mbar_expect_tx(qd_full(c), 16384);
+            tma_load_3d(sbase + B_SQ + c * 8192, &map_q, qd_full(c), 0, b * N_TOK + c * 64, h);
+            tma_load_2d(sbase + B_SDO + c * 8192, &map_do, qd_full(c), h * VITK_HEAD_DIM, b * N_TOK + c * 64);
+          }
         }
         __syncwarp();
       }
@@ -479,6 +510,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const bool leader = elect_one();
+    const bool do_mma = !(dbg & 1);
     constexpr uint32_t ID_S64 = make_idesc(64, 0, 0), ID_S16 = make_idesc(16, 0, 0);   // S^T / dP^T chunks
     constexpr uint32_t ID_TS = make_idesc(64, 0, 1);                                    // dV, dK: A in TMEM, B MN-major
     constexpr uint32_t ID_DQ = make_idesc(64, 1, 1);                                    // dQ: A, B MN-major
@@ -494,12 +526,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
         if (leader) {
           const uint32_t idesc = c < 3 ? ID_S64 : ID_S16;
           const uint32_t d_st = tmem_base + buf * 128, d_dp = d_st + 64;
+          if (do_mma) {
+            // the two accumulation chains are interleaved: consecutive MMAs on one accumulator are dependent
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_ss(d_st, desc_lo(sK + t * 16384 + k * 32), DESC_HI, desc_lo(sQ + c * 8192 + k * 32), DESC_HI, idesc, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_ss(d_dp, desc_lo(sV + t * 16384 + k * 32), DESC_HI, desc_lo(sdO + c * 8192 + k * 32), DESC_HI, idesc, k > 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              mma_ss(d_st, desc_lo(sK + t * 16384 + k * 32), DESC_HI, desc_lo(sQ + c * 8192 + k * 32), DESC_HI, idesc, k > 0 ? 1u : 0u);
+              mma_ss(d_dp, desc_lo(sV + t * 16384 + k * 32), DESC_HI, desc_lo(sdO + c * 8192 + k * 32), DESC_HI, idesc, k > 0 ? 1u : 0u);
+            }
+          }
           tc_commit(st_full(buf));
         }
         __syncwarp();
@@ -513,7 +547,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
         if (leader) {
           const uint32_t a_p = tmem_base + buf * 128, a_ds = a_p + 64;
           const int nks = c < 3 ? 4 : 1;
-          for (int ks = 0; ks < nks; ++ks) {
+          for (int ks = 0; ks < nks && do_mma; ++ks) {
             const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
             mma_ts(tmem_base + T_DV, a_p + ks * 8, desc_lo(sdO + c * 8192 + ks * 2048), DESC_HI, ID_TS, acc);
             mma_ts(tmem_base + T_DK, a_ds + ks * 8, desc_lo(sQ + c * 8192 + ks * 2048), DESC_HI, ID_TS, acc);
@@ -529,7 +563,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
           if (leader) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              mma_ss(tmem_base + T_DQ + m * 64, desc_lo_mn(sDS + m * 32768 + ks * 2048, 16384), DESC_HI,
+              if (do_mma) mma_ss(tmem_base + T_DQ + m * 64, desc_lo_mn(sDS + m * 32768 + ks * 2048, 16384), DESC_HI,
                      desc_lo(sK + t * 16384 + ks * 2048), DESC_HI, ID_DQ, (t > 0 || ks > 0) ? 1u : 0u);
             tc_commit(ds_free(m));
             if (m == 1) tc_commit(kv_free(t));     // K_t / V_t no longer needed
@@ -556,16 +590,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qr * 32) << 16);
     const uint32_t sdO = sbase + B_SDO, sDS = sbase + B_SDS;
     const int64_t hstride = (int64_t)VITK_HEADS * M * 64;
+    // O rows of the item whose delta is computed next, fetched one item ahead.  8 lanes share a row (16 B each): every
+    // load instruction covers 4 full 128-byte rows.  ov[g] = chunk (lane & 7) of query we*32 + 4g + (lane >> 3).
     uint4 ov[8];
     float lsv = 0.f;
     auto fetch_o = [&](int item) {
-      if (tid < N_TOK) {
-        const int b = item / VITK_HEADS, h = item % VITK_HEADS;
-        const uint4* op = reinterpret_cast<const uint4*>(out + ((int64_t)b * N_TOK + tid) * VITK_DIM + h * VITK_HEAD_DIM);
+      if (dbg & 8) return;
+      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
+      const bf16* obase = out + ((int64_t)b * N_TOK) * VITK_DIM + h * VITK_HEAD_DIM + (lane & 7) * 8;
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) ov[c8] = __ldg(op + c8);
-        lsv = __ldg(lse + (int64_t)h * M + (int64_t)b * N_TOK + tid);
+      for (int g = 0; g < 8; ++g) {
+        const int q = we * 32 + g * 4 + (lane >> 3);
+        ov[g] = q < N_TOK ? __ldg(reinterpret_cast<const uint4*>(obase + (int64_t)q * VITK_DIM)) : make_uint4(0u, 0u, 0u, 0u);
       }
+      if (tid < N_TOK) lsv = __ldg(lse + (int64_t)h * M + (int64_t)b * N_TOK + tid);
     };
     if (n_my > 0) fetch_o(blockIdx.x);
     for (int it = 0; it < n_my; ++it) {
@@ -573,6 +611,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
       const int b = item / VITK_HEADS, h = item % VITK_HEADS;
       const uint32_t ipar = it & 1;
       const int64_t hm = ((int64_t)h * M + (int64_t)b * N_TOK) * 64;
+      // delta_q = dO_q . O_q and L_q = lse_q * log2(e) for the 64 queries of chunk c (thread tid = query tid); runs one
+      // chunk ahead of its use, off the critical path of the step that needs it
+      auto delta_chunk = [&](int c) {
+        if ((we >> 1) == c && !(dbg & 8)) {
+          mbar_wait(qd_full(c), ipar);       // dO_c has landed
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int q = we * 32 + g * 4 + (lane >> 3), r = q & 63;
+            uint4 av;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(av.x), "=r"(av.y), "=r"(av.z), "=r"(av.w)
+                         : "r"(sdO + c * 8192 + r * 128 + (((lane & 7) ^ (r & 7)) << 4)));
+            const float2 a0 = unpack_bf16x2(av.x), a1 = unpack_bf16x2(av.y), a2 = unpack_bf16x2(av.z), a3 = unpack_bf16x2(av.w);
+            const float2 o0 = unpack_bf16x2(ov[g].x), o1 = unpack_bf16x2(ov[g].y), o2 = unpack_bf16x2(ov[g].z), o3 = unpack_bf16x2(ov[g].w);
+            float dl = a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
+            dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+            dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+            dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+            if ((lane & 7) == 0) sD[q] = q < N_TOK ? dl : 0.f;
+          }
+          sL[tid] = tid < N_TOK ? lsv * LOG2E : 0.f;
+        }
+      };
+      delta_chunk(0);
 #pragma unroll 1
       for (int s = 0; s < 8; ++s) {
         const int t = s >> 2, c = s & 3, buf = s & 1, m = c >> 1;
@@ -582,45 +643,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
         if ((c & 1) == 0) mbar_wait(ds_free(m), ((it * 2 + t) & 1) ^ 1);   // MMA5 of the previous key tile has read dS^T buffer m
         tc_fence_after();
         if (t == 0) {
-          // ---- delta_q = dO_q . O_q and L_q = lse_q * log2(e) of this chunk's 64 queries (thread tid = query tid)
-          if ((tid >> 6) == c) {
-            float dl = 0.f, ls = 0.f;
-            if (tid < N_TOK) {
-              const int r = tid & 63;
-              const uint32_t rb = sdO + c * 8192 + r * 128;
-#pragma unroll
-              for (int c8 = 0; c8 < 8; ++c8) {
-                uint4 av;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(av.x), "=r"(av.y), "=r"(av.z), "=r"(av.w) : "r"(rb + ((c8 ^ (r & 7)) << 4)));
-                const float2 a0 = unpack_bf16x2(av.x), a1 = unpack_bf16x2(av.y), a2 = unpack_bf16x2(av.z), a3 = unpack_bf16x2(av.w);
-                const float2 o0 = unpack_bf16x2(ov[c8].x), o1 = unpack_bf16x2(ov[c8].y), o2 = unpack_bf16x2(ov[c8].z), o3 = unpack_bf16x2(ov[c8].w);
-                dl += a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
-              }
-              ls = lsv * LOG2E;
-            }
-            sD[tid] = dl;
-            sL[tid] = ls;
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");   // delta / L of this chunk (written during the previous step) visible
         } else if (s == 4 && it + 1 < n_my) {
           fetch_o(item + gridDim.x);   // next item's O rows: in flight during this item's second key tile
         }
         const uint32_t a_st = lane_addr + buf * 128 + ch * 32, a_dp = a_st + 64;
         const uint32_t ds_row = sDS + m * 32768 + (c & 1) * 16384 + row * 128;
-        if (c < 3) {
+        if (dbg & 2) {
+        } else if (c < 3) {
           uint32_t vs[32], vd[32];
           tm_ld32(a_st, vs);
           tm_ld32(a_dp, vd);
+          const int q0 = c * 64 + ch * 32;
+          float4 Lr[8], Dr[8];      // per-query constants of this warp's 32 columns (broadcast reads)
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Lr[j4].x), "=f"(Lr[j4].y), "=f"(Lr[j4].z), "=f"(Lr[j4].w)
+                         : "r"(sbase + B_SL + (q0 + j4 * 4) * 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Dr[j4].x), "=f"(Dr[j4].y), "=f"(Dr[j4].z), "=f"(Dr[j4].w)
+                         : "r"(sbase + B_SD + (q0 + j4 * 4) * 4));
+          }
           tm_ld_wait();
           // the partner warp (other column half, same lanes) must have read its scores before either overwrites them
           asm volatile("bar.sync %0, 64;" ::"r"(2 + qr) : "memory");
           uint32_t pp[16], pd[16];
-          const int q0 = c * 64 + ch * 32;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 Lq = *reinterpret_cast<const float4*>(sL + q0 + j4 * 4);
-            const float4 Dq = *reinterpret_cast<const float4*>(sD + q0 + j4 * 4);
-            const float Lv[4] = {Lq.x, Lq.y, Lq.z, Lq.w}, Dv[4] = {Dq.x, Dq.y, Dq.z, Dq.w};
+            const float Lv[4] = {Lr[j4].x, Lr[j4].y, Lr[j4].z, Lr[j4].w}, Dv[4] = {Dr[j4].x, Dr[j4].y, Dr[j4].z, Dr[j4].w};
             float p[4], d[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -668,29 +717,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(buf));
+        if (t == 0 && c < 3) delta_chunk(c + 1);
 
         if (c == 3) {
           // ---- dV_t (ch 0) / dK_t (ch 1): lane = key
           mbar_wait(dvk_full, (it * 2 + t) & 1);
           tc_fence_after();
-          bf16* dst = dqkv + hm + (ch == 0 ? 2 : 1) * hstride + (int64_t)key * 64;
+          bf16* dbase = dqkv + hm + (ch == 0 ? 2 : 1) * hstride;
           const float sc = ch == 0 ? 1.0f : SCALE;
+          const int k0w = t * 128 + qr * 32;      // first key of this warp
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          for (int half = 0; half < 2 && !(dbg & 4); ++half) {
             uint32_t o[32];
             tm_ld32(lane_addr + (ch == 0 ? T_DV : T_DK) + half * 32, o);
             tm_ld_wait();
-            if (key < N_TOK) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 u;
-                u.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * sc, __uint_as_float(o[8 * j + 1]) * sc);
-                u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * sc, __uint_as_float(o[8 * j + 3]) * sc);
-                u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * sc, __uint_as_float(o[8 * j + 5]) * sc);
-                u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * sc, __uint_as_float(o[8 * j + 7]) * sc);
-                *reinterpret_cast<uint4*>(dst + half * 32 + j * 8) = u;
-              }
-            }
+            store_slab32(sbase + B_STG + (uint32_t)we * 2048, lane, o, sc,
+                         [&](int r) -> bf16* { return (k0w + r < N_TOK) ? dbase + (int64_t)(k0w + r) * 64 + half * 32 : nullptr; });
           }
           tc_fence_before();
           __syncwarp();
@@ -701,24 +743,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
       {
         mbar_wait(dq_full, ipar);
         tc_fence_after();
-        const int q = ch * 128 + row;
-        bf16* dst = dqkv + hm + (int64_t)q * 64;
+        const int q0w = ch * 128 + qr * 32;       // first query of this warp
+        bf16* dbase = dqkv + hm;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < 2 && !(dbg & 4); ++half) {
           uint32_t o[32];
           tm_ld32(lane_addr + T_DQ + ch * 64 + half * 32, o);
           tm_ld_wait();
-          if (q < N_TOK) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * SCALE, __uint_as_float(o[8 * j + 1]) * SCALE);
-              u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * SCALE, __uint_as_float(o[8 * j + 3]) * SCALE);
-              u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * SCALE, __uint_as_float(o[8 * j + 5]) * SCALE);
-              u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * SCALE, __uint_as_float(o[8 * j + 7]) * SCALE);
-              *reinterpret_cast<uint4*>(dst + half * 32 + j * 8) = u;
-            }
-          }
+          store_slab32(sbase + B_STG + (uint32_t)we * 2048, lane, o, SCALE,
+                       [&](int r) -> bf16* { return (q0w + r < N_TOK) ? dbase + (int64_t)(q0w + r) * 64 + half * 32 : nullptr; });
         }
         tc_fence_before();
         __syncwarp();
@@ -780,7 +813,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   VITK_TRY(atc::make_dout_map(dout, M, &map_do));
   const int items = batch * VITK_HEADS, sms = sm_count();
   VITK_LAUNCH((atc::attn_bwd_tc_kernel), (items < sms ? items : sms), atc::THREADS, atc::BWD_SMEM, st, map_kv, map_q, map_do,
-              (const bf16*)out, lse, (bf16*)dqkv, batch, items);
+              (const bf16*)out, lse, (bf16*)dqkv, batch, items, debug_knob(7));
   return VITK_OK;
 }
 

@@ -727,20 +727,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (k + 1 < NCH) tc_ld32_issue(taddr + (half + 2 * (k + 1)) * 32, raw);   // next chunk's TMEM read overlaps the rest
           const uint32_t t0 = stg + s * kSlotBytes;
+          // the staging slot is reusable once the TMA store that last read it has drained it (two chunks ago; EK_GELU: the
+          // previous chunk) -- checked as late as possible, after this chunk's math, so the drain overlaps it
+          auto slot_ready = [&]() {
+            if (lane == 0) { if constexpr (EK == EK_GELU) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
+            __syncwarp();
+          };
           if constexpr (kLoads) {
             mbar_wait(eload_bar(we, s), (eph >> s) & 1u);
             eph ^= 1u << s;
-          } else {
-            // the store that last used this slot has been read out (two chunks ago; EK_GELU: the previous chunk)
-            if (lane == 0) { if constexpr (EK == EK_GELU) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
-            __syncwarp();
           }
           if constexpr (EK == EK_STORE_BF16 || EK == EK_SCATTER) {
+            uint32_t ob[16];
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              sts128(t0 + row_off_64(lane, k4), pack_bf16x2(v[k4 * 8 + 0], v[k4 * 8 + 1]), pack_bf16x2(v[k4 * 8 + 2], v[k4 * 8 + 3]),
-                     pack_bf16x2(v[k4 * 8 + 4], v[k4 * 8 + 5]), pack_bf16x2(v[k4 * 8 + 6], v[k4 * 8 + 7]));
+            for (int e = 0; e < 16; ++e) ob[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+            slot_ready();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) sts128(t0 + row_off_64(lane, k4), ob[k4 * 4], ob[k4 * 4 + 1], ob[k4 * 4 + 2], ob[k4 * 4 + 3]);
           } else if constexpr (EK == EK_STORE_F32) {
+            slot_ready();
 #pragma unroll
             for (int k8 = 0; k8 < 8; ++k8)
               sts128(t0 + row_off_128(lane, k8), __float_as_uint(v[k8 * 4 + 0]), __float_as_uint(v[k8 * 4 + 1]),
@@ -757,6 +762,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               g[e] = pack_bf16x2(g0, g1);
               dg[e] = pack_bf16x2(d0, d1);
             }
+            slot_ready();
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               sts128(t0 + row_off_64(lane, k4), g[k4 * 4], g[k4 * 4 + 1], g[k4 * 4 + 2], g[k4 * 4 + 3]);
@@ -892,6 +898,7 @@ static int make_operand_map(const void* base, const MatLayout& l, int rows, int 
 
 static int g_tc_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 int attn_debug_variant() { return g_tc_debug[3]; }
+int debug_knob(int key) { return (key >= 0 && key < 8) ? g_tc_debug[key] : 0; }
 
 // 32 x 32 element tile maps of the epilogue operands: row-major [rows][ld] (2-D) or head-major [C/64][rows][64] (3-D).
 // 4-byte elements -> 128-byte tile rows (SWIZZLE_128B), 2-byte -> 64-byte rows (SWIZZLE_64B).
@@ -1041,9 +1048,12 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
       pr.ep.out_dtype != VITK_BF16) { set_error("gemm_tc: epilogue expects bf16 output"); return VITK_ERR_UNSUPPORTED; }
   if (pr.J % 128 != 0 || pr.ep.ldc % 8 != 0) { set_error("gemm_tc: J must be a multiple of 128 (got %d)", pr.J); return VITK_ERR_UNSUPPORTED; }
   // Tile shape: CTA pair (CG = 2, 256 x BN) or single CTA (128 x BN), BN in {256, 192, 128}: minimise
-  // (waves of the persistent grid) x (k-blocks x 2*BN tensor clocks + per-tile overhead).  With M = B*197 the tile count
-  // is rarely a multiple of the slot count, so the wave term matters (12608 x 768 on 74 CTA pairs: 150 tiles of 256x256 =
-  // 3 waves for 2.03 waves of work, 200 tiles of 256x192 = 3 waves of 3/4 the cost).  Pairs win ties (half the B traffic).
+  //   (waves of the persistent grid) x (k-blocks x max(tensor clocks, operand-ingest clocks) + per-tile overhead).
+  // A 64-deep k-block costs 2*BN tensor clocks and pulls (128 + BN/CG) x 128 B into the SM; measured with the epilogue
+  // and the loads switched off in turn (vitk_debug_set(7, .)), the mainloop sustains ~36 B/clk/SM of operand traffic
+  // -- it, not the tensor pipe, bounds every shape here -- so wider tiles win unless they cost a whole extra wave: with
+  // M = B*197 the tile count is rarely a multiple of the slot count (12608 x 768 on 74 CTA pairs: 150 tiles of 256x256 =
+  // 3 waves for 2.03 waves of work, 200 tiles of 256x192 = 3 waves of 7/8 the bytes).
   const bool b_mn = pr.lb.s_row == 1 && pr.lb.s_col != 1;   // MN-major B: staged in 64-row atoms
   int cg = 0, bn = 0;
   const int forced_bn = (g_tc_debug[2] == 128 || g_tc_debug[2] == 192 || g_tc_debug[2] == 256) ? g_tc_debug[2] : 0;
@@ -1064,7 +1074,8 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
         if (forced_bn && forced_bn != cand) continue;
         const long tiles = tiles_m * (pr.J / cand);
         const long waves = (tiles + slots - 1) / slots;
-        const double cost = (double)waves * ((double)kb * 2.0 * cand + 1200.0);
+        const double ingest = (128.0 + cand / c) * 128.0 / 36.0, mma = 2.0 * cand;
+        const double cost = (double)waves * ((double)kb * (ingest > mma ? ingest : mma) + 1200.0);
         if (best < 0.0 || cost < best) { best = cost; bn = cand; cg = c; }
       }
     }
