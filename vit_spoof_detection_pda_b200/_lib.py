@@ -87,6 +87,9 @@ def load():
         raise RuntimeError("libvitk.so version mismatch: rebuild")
     if os.environ.get("VITK_NO_PDL") == "1":   # A/B timing: plain stream order instead of programmatic dependent launch
         lib.vitk_debug_set(6, 1)
+    for kv in os.environ.get("VITK_KNOBS", "").split(","):   # A/B timing knobs, e.g. VITK_KNOBS=8:1 (wgrad on the main stream)
+        if kv:
+            lib.vitk_debug_set(int(kv.split(":")[0]), int(kv.split(":")[1]))
     _lib = lib
     return lib
 

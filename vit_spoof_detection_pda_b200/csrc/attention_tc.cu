@@ -293,48 +293,73 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_after();
       float m = -INFINITY, l = 0.f;
       if (warp_valid) {
-        // ---- pass 1: row max over the 197 valid keys
-        uint32_t v[32];
-#pragma unroll 1
-        for (int c = 0; c < 6; ++c) {
-          tm_ld32(taddr + c * 32, v);
-          tm_ld_wait();
+        // ---- ONE pass over the 208 scores (tensor-memory reads are the scarce resource: ~64 B/clk/SM).  p = 2^((s - m)*c)
+        // with a LAZY row maximum m: it is only raised -- and the probabilities already written rescaled -- when a chunk
+        // exceeds it by more than 2^8 (p <= 256 is harmless in bf16 / fp32; 1/l and the log-sum-exp absorb the shift).
+        // The next chunk's tcgen05.ld is in flight while the current one is exponentiated.
+        uint32_t v[2][32];
+        tm_ld32(taddr, v[0]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-        }
-        uint32_t w[16];
-        tm_ld16(taddr + 192, w);
-        tm_ld_wait();
-#pragma unroll
-        for (int j = 0; j < N_TOK - 192; ++j) m = fmaxf(m, __uint_as_float(w[j]));
-        const float mb = m * sl2;
-        // ---- pass 2: p = 2^(s*scale*log2e - max), row sum, bf16 pairs written over S (32 scores -> 16 columns)
-#pragma unroll 1
-        for (int c = 0; c < 6; ++c) {
-          tm_ld32(taddr + c * 32, v);
+        for (int c = 0; c < 7; ++c) {
+          uint32_t (&cur)[32] = v[c & 1];
           tm_ld_wait();
+          if (c < 5) tm_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+          else if (c == 5) {
+            uint32_t (&nx)[32] = v[0];
+            uint32_t w16[16];
+            tm_ld16(taddr + 192, w16);
+            tm_ld_wait();   // the last (16-column) chunk is short: fetch it synchronously
+#pragma unroll
+            for (int j = 0; j < 16; ++j) nx[j] = w16[j];
+#pragma unroll
+            for (int j = 16; j < 32; ++j) nx[j] = 0xff800000u;   // -inf
+          }
+          const int nval = c < 6 ? 32 : N_TOK - 192;      // valid keys of this chunk
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nval) cm = fmaxf(cm, __uint_as_float(cur[j]));
+          if (c == 0) {
+            m = cm;
+          } else {
+            const bool raise = (cm - m) * sl2 > 8.0f;
+            if (__any_sync(0xffffffffu, raise)) {
+              const float mn = raise ? cm : m;
+              const float f = ex2((m - mn) * sl2);     // 1 for the lanes that keep their maximum
+              l *= f;
+              tm_st_wait();                              // earlier probability chunks have landed in tensor memory
+              for (int cc = 0; cc < c; ++cc) {           // rescale the probabilities already in tensor memory
+                uint32_t pk[16];
+                tm_ld16(taddr + cc * 16, pk);
+                tm_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float2 pr = unpack_bf16x2(pk[j]);
+                  pk[j] = pack_bf16x2(pr.x * f, pr.y * f);
+                }
+                tm_st16(taddr + cc * 16, pk);
+              }
+              m = mn;
+            }
+          }
+          const float mb = m * sl2;
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), sl2, -mb));
-            const float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb));
+            const float p0 = (2 * j < nval) ? ex2(fmaf(__uint_as_float(cur[2 * j]), sl2, -mb)) : 0.f;
+            const float p1 = (2 * j + 1 < nval) ? ex2(fmaf(__uint_as_float(cur[2 * j + 1]), sl2, -mb)) : 0.f;
             l += p0 + p1;
             pk[j] = pack_bf16x2(p0, p1);
           }
-          tm_st16(taddr + c * 16, pk);
-        }
-        tm_ld16(taddr + 192, w);
-        tm_ld_wait();
-        uint32_t pk8[8];
+          if (c < 6) {
+            tm_st16(taddr + c * 16, pk);
+          } else {
+            uint32_t pk8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k0 = 192 + 2 * j;
-          const float p0 = k0 < N_TOK ? ex2(fmaf(__uint_as_float(w[2 * j]), sl2, -mb)) : 0.f;
-          const float p1 = k0 + 1 < N_TOK ? ex2(fmaf(__uint_as_float(w[2 * j + 1]), sl2, -mb)) : 0.f;
-          l += p0 + p1;
-          pk8[j] = pack_bf16x2(p0, p1);
+            for (int j = 0; j < 8; ++j) pk8[j] = pk[j];
+            tm_st8(taddr + 96, pk8);
+          }
         }
-        tm_st8(taddr + 96, pk8);
         tm_st_wait();
       }
       tc_fence_before();

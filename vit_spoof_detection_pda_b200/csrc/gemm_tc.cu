@@ -896,9 +896,9 @@ static int make_operand_map(const void* base, const MatLayout& l, int rows, int 
 }
 
 
-static int g_tc_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static int g_tc_debug[16] = {0};
 int attn_debug_variant() { return g_tc_debug[3]; }
-int debug_knob(int key) { return (key >= 0 && key < 8) ? g_tc_debug[key] : 0; }
+int debug_knob(int key) { return (key >= 0 && key < 16) ? g_tc_debug[key] : 0; }
 
 // 32 x 32 element tile maps of the epilogue operands: row-major [rows][ld] (2-D) or head-major [C/64][rows][64] (3-D).
 // 4-byte elements -> 128-byte tile rows (SWIZZLE_128B), 2-byte -> 64-byte rows (SWIZZLE_64B).
@@ -1096,7 +1096,7 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
 
 namespace vitk { void set_pdl(int on); }
 extern "C" int vitk_debug_set(int key, int value) {
-  if (key < 0 || key >= 8) return VITK_ERR_ARG;
+  if (key < 0 || key >= 16) return VITK_ERR_ARG;
   vitk::g_tc_debug[key] = value;
   if (key == 6) vitk::set_pdl(value ? 0 : 1);   // key 6: 1 = plain stream order (no programmatic dependent launch)
   return VITK_OK;

@@ -34,7 +34,7 @@ head_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ ln_w, 
                 const float* __restrict__ b2, const float* __restrict__ mask1, const float* __restrict__ mask2,
                 float* __restrict__ logits, float* __restrict__ save, int num_classes) {
   pdl_sync();
-  __shared__ float ys[HD_IN];
+  __shared__ __align__(16) float ys[HD_IN];
   __shared__ float as[HD_HID];
   __shared__ float red[HD_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -54,18 +54,35 @@ head_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ ln_w, 
   }
   if (sv && tid == 0) sv[HS_RSTD] = rstd;
   __syncthreads();
-  for (int t = warp; t < HD_HID; t += HD_THREADS / 32) {
-    const float* wr = w1 + (int64_t)t * HD_IN;
-    float a = 0.f;
-#pragma unroll 4
-    for (int k = lane; k < HD_IN; k += 32) a = fmaf(ys[k], wr[k], a);
-    a = warp_sum(a);
-    if (lane == 0) {
-      const float z = a + b1[t];
-      if (sv) sv[HS_Z1 + t] = z;
-      float g = gelu_erf(z);
-      if (mask2) g *= mask2[(int64_t)b * HD_HID + t];
-      as[t] = g;
+  // 768 -> 512 mat-vec: every warp owns 32 consecutive hidden units; the LN output lives in registers (6 float4 per
+  // lane) and two weight rows (12 independent 16-byte loads per lane) are in flight at a time -- the kernel is
+  // latency-bound on the 1.5 MB weight read, not on arithmetic.
+  {
+    float4 yv[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) yv[i] = *reinterpret_cast<const float4*>(ys + (i * 32 + lane) * 4);
+    for (int t = warp * 32; t < warp * 32 + 32; t += 2) {
+      const float4* w0 = reinterpret_cast<const float4*>(w1 + (int64_t)t * HD_IN);
+      const float4* w1r = reinterpret_cast<const float4*>(w1 + (int64_t)(t + 1) * HD_IN);
+      float4 wa[6], wb[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { wa[i] = __ldg(w0 + i * 32 + lane); wb[i] = __ldg(w1r + i * 32 + lane); }
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        a0 = fmaf(yv[i].x, wa[i].x, fmaf(yv[i].y, wa[i].y, fmaf(yv[i].z, wa[i].z, fmaf(yv[i].w, wa[i].w, a0))));
+        a1 = fmaf(yv[i].x, wb[i].x, fmaf(yv[i].y, wb[i].y, fmaf(yv[i].z, wb[i].z, fmaf(yv[i].w, wb[i].w, a1))));
+      }
+      a0 = warp_sum(a0);
+      a1 = warp_sum(a1);
+      if (lane < 2) {
+        const int tt = t + lane;
+        const float z = (lane == 0 ? a0 : a1) + b1[tt];
+        if (sv) sv[HS_Z1 + tt] = z;
+        float g = gelu_erf(z);
+        if (mask2) g *= mask2[(int64_t)b * HD_HID + tt];
+        as[tt] = g;
+      }
     }
   }
   __syncthreads();
@@ -106,7 +123,8 @@ head_bwd_data_kernel(const float* __restrict__ dlogits, float* __restrict__ save
     dxh[e] = 0.f; xh[e] = 0.f;
     if (k < HD_IN) {
       float dy = 0.f;
-      for (int t = 0; t < HD_HID; ++t) dy = fmaf(dz[t], w1[(int64_t)t * HD_IN + k], dy);
+#pragma unroll 16
+      for (int t = 0; t < HD_HID; ++t) dy = fmaf(dz[t], __ldg(w1 + (int64_t)t * HD_IN + k), dy);   // 16 loads in flight
       if (mask1) dy *= mask1[(int64_t)b * HD_IN + k];
       sv[HS_DYM + k] = dy;
       xh[e] = sv[HS_XHAT + k];
@@ -137,6 +155,7 @@ head_bwd_param_kernel(const float* __restrict__ dlogits, const float* __restrict
     const int t = blk;
     float acc[3] = {0.f, 0.f, 0.f};
     float sb = 0.f;
+#pragma unroll 8
     for (int b = 0; b < batch; ++b) {
       const float* sv = save + (int64_t)b * HS_TOTAL;
       const float d = sv[HS_DZ1 + t];
@@ -150,6 +169,7 @@ head_bwd_param_kernel(const float* __restrict__ dlogits, const float* __restrict
   } else if (blk == HD_HID) {
     for (int k = tid; k < HD_IN; k += 256) {
       float g = 0.f, bb = 0.f;
+#pragma unroll 8
       for (int b = 0; b < batch; ++b) {
         const float* sv = save + (int64_t)b * HS_TOTAL;
         const float d = sv[HS_DYM + k];
@@ -164,6 +184,7 @@ head_bwd_param_kernel(const float* __restrict__ dlogits, const float* __restrict
     float sb = 0.f;
     for (int t = tid; t < HD_HID; t += 256) {
       float a = 0.f;
+#pragma unroll 8
       for (int b = 0; b < batch; ++b) {
         const float* sv = save + (int64_t)b * HS_TOTAL;
         float g = gelu_erf(sv[HS_Z1 + t]);

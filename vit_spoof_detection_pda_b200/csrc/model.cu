@@ -9,7 +9,31 @@ int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dty
 int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                       float* dqkv_colsum, int batch, int dtype, cudaStream_t st);
 
+int debug_knob(int key);   // gemm_tc.cu: vitk_debug_set(8, 1) keeps the weight-gradient GEMMs on the main stream
+
 constexpr int D = VITK_DIM, NT = VITK_NTOK, MLP = VITK_MLP, HID = VITK_HEAD_HIDDEN;
+
+// Weight-gradient side stream.  The four wgrad GEMMs of a block only feed the optimizer, so they run on a second
+// stream next to the dgrad / LayerNorm / attention chain: CTAs of whichever kernel is pending take the SMs that the
+// other stream's kernel leaves idle in its ramp, its last partial wave and its tail (persistent grids of 148 CTAs are
+// work-conserving this way).  Ordering is by events; the stage joins the side stream before it returns, so callers
+// (autograd, the bucketed all-reduce) still see plain stream semantics.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+static SideStream* side_stream() {
+  static thread_local SideStream per_dev[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& ss = per_dev[dev];
+  if (!ss.s) {
+    if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (auto& e : ss.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &ss;
+}
 
 struct BlockOffsets { int64_t n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b; };
 struct ParamOffsets {
@@ -293,26 +317,45 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   void* dh = ws + pl.dh;
   void* dqkv = ws + pl.dqkv;
 
+  SideStream* ss = (dt == VITK_BF16 && debug_knob(8) != 1) ? side_stream() : nullptr;
+  cudaStream_t ms = c.st;
+  void* wst = ss ? (void*)ss->s : st;     // stream of the weight-gradient GEMMs
+  auto after = [&](int e, cudaStream_t from, cudaStream_t to) -> int {   // `to` continues after everything enqueued on `from`
+    if (!ss) return VITK_OK;
+    VITK_CUDA(cudaEventRecord(ss->ev[e], from));
+    VITK_CUDA(cudaStreamWaitEvent(to, ss->ev[e], 0));
+    return VITK_OK;
+  };
   // MLP:  x_out = x_mid + fc2(gelu(fc1(ln2(x_mid))))
   // (fc2 / proj bias gradients = column sums of the residual-stream gradient: produced by the kernel that wrote
   //  it -- the LayerNorm backward below, or the CLS scatter for the last block)
-  VITK_TRY(vitk_linear_wgrad(dxa, VITK_LAYOUT_ROWMAJOR, g, c.G(b.fc2w), nullptr, M, D, MLP, dt, eng, st));
+  VITK_TRY(after(0, ms, ss ? ss->s : ms));   // dx / dx16 of the previous stage are final
+  VITK_TRY(vitk_linear_wgrad(dxa, VITK_LAYOUT_ROWMAJOR, g, c.G(b.fc2w), nullptr, M, D, MLP, dt, eng, wst));
+  if (ss) VITK_CUDA(cudaEventRecord(ss->ev[1], ss->s));                  // fc2 wgrad has read dx16
   // fc1's bias gradient = column sums of du: fused into the epilogue of the GEMM that produces du
   VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.fc2w), du, u, c.G(b.fc1b), M, D, MLP, dt, eng, st));
-  VITK_TRY(vitk_linear_wgrad(du, VITK_LAYOUT_ROWMAJOR, ln2, c.G(b.fc1w), nullptr, M, MLP, D, dt, eng, st));
+  VITK_TRY(after(2, ms, ss ? ss->s : ms));   // du ready
+  VITK_TRY(vitk_linear_wgrad(du, VITK_LAYOUT_ROWMAJOR, ln2, c.G(b.fc1w), nullptr, M, MLP, D, dt, eng, wst));
   VITK_TRY(vitk_linear_dgrad(du, VITK_LAYOUT_ROWMAJOR, c.W(b.fc1w), dh, nullptr, nullptr, M, MLP, D, dt, eng, st));
+  if (ss) VITK_CUDA(cudaStreamWaitEvent(ms, ss->ev[1], 0));              // the LayerNorm backward overwrites dx16
   VITK_TRY(vitk_layernorm_bwd(dh, dt, xmid, D, c.P(b.n2w), (float*)c.at(pl.mean2, pl.stat_stride, l),
                               (float*)c.at(pl.rstd2, pl.stat_stride, l), dx, dx, dx16, c.G(b.n2w), c.G(b.n2b), c.G(b.projb), M, st));
   // attention:  x_mid = x + proj(attn(qkv(ln1(x))))
-  VITK_TRY(vitk_linear_wgrad(dxa, VITK_LAYOUT_ROWMAJOR, ao, c.G(b.projw), nullptr, M, D, D, dt, eng, st));
+  VITK_TRY(after(3, ms, ss ? ss->s : ms));   // dx16 (gradient of x_mid) ready
+  VITK_TRY(vitk_linear_wgrad(dxa, VITK_LAYOUT_ROWMAJOR, ao, c.G(b.projw), nullptr, M, D, D, dt, eng, wst));
+  if (ss) VITK_CUDA(cudaEventRecord(ss->ev[4], ss->s));                  // proj wgrad has read dx16
   VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.projw), dh, nullptr, nullptr, M, D, D, dt, eng, st));
   // (the qkv bias gradient stays a separate coalesced column-sum pass inside wgrad: fusing it into the mma.sync
   //  attention kernel measured +48 us per layer against 16 us for the stand-alone reduction)
   VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, nullptr, m->batch, dt, c.st));
-  VITK_TRY(vitk_linear_wgrad(dqkv, VITK_LAYOUT_HEADMAJOR, ln1, c.G(b.qkvw), c.G(b.qkvb), M, 3 * D, D, dt, eng, st));
+  VITK_TRY(after(5, ms, ss ? ss->s : ms));   // dqkv ready
+  VITK_TRY(vitk_linear_wgrad(dqkv, VITK_LAYOUT_HEADMAJOR, ln1, c.G(b.qkvw), c.G(b.qkvb), M, 3 * D, D, dt, eng, wst));
   VITK_TRY(vitk_linear_dgrad(dqkv, VITK_LAYOUT_HEADMAJOR, c.W(b.qkvw), dh, nullptr, nullptr, M, 3 * D, D, dt, eng, st));
+  if (ss) VITK_CUDA(cudaStreamWaitEvent(ms, ss->ev[4], 0));              // the LayerNorm backward overwrites dx16
   VITK_TRY(vitk_layernorm_bwd(dh, dt, x, D, c.P(b.n1w), (float*)c.at(pl.mean1, pl.stat_stride, l),
                               (float*)c.at(pl.rstd1, pl.stat_stride, l), dx, dx, dx16, c.G(b.n1w), c.G(b.n1b),
                               l > 0 ? c.G(po.blk[l - 1].fc2b) : nullptr, M, st));
+  // join: du / dqkv / dx16 are rewritten by the next stage, and the caller may reduce this stage's gradients
+  if (ss) VITK_TRY(after(0, ss->s, ms));
   return VITK_OK;
 }
