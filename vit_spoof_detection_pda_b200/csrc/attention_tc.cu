@@ -443,7 +443,8 @@ static int make_hm_map(const void* base, int64_t M, int n_blk, int box_rows, CUt
 // the second key tile of the current item.
 // ================================================================================================
 constexpr uint32_t B_SK = 0, B_SV = 32768, B_SQ = 65536, B_SDO = 98304, B_SDS = 131072;   // byte offsets
-constexpr uint32_t B_SL = B_SDS + 65536, B_SD = B_SL + 1024, B_STG = B_SD + 1024, B_BAR = B_STG + 8 * 2048;
+constexpr uint32_t B_SL = B_SDS + 65536, B_SD = B_SL + 2048, B_STG = B_SD + 2048, B_BAR = B_STG + 4 * 2048;
+constexpr int BWD_THREADS = 64 + 8 * 32 + 4 * 32;   // producer, MMA issuer, 8 softmax warps, 4 epilogue / delta warps
 constexpr size_t BWD_SMEM = 1024 + B_BAR + 512;
 constexpr uint32_t T_DV = 256, T_DK = 320, T_DQ = 384;
 
@@ -454,7 +455,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
                    const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ out, const float* __restrict__ lse,
                    bf16* __restrict__ dqkv, int batch, int n_items, int dbg) {
@@ -471,7 +472,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
   auto p_full = [&](int b) { return bars + 8u * (14 + b); };    // 14,15
   auto ds_free = [&](int m) { return bars + 8u * (16 + m); };   // 16,17
   const uint32_t dvk_full = bars + 8u * 18, dvk_free = bars + 8u * 19, dq_full = bars + 8u * 20, dq_free = bars + 8u * 21;
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + B_BAR + 8 * 22);
+  auto delta_ready = [&](int c) { return bars + 8u * (22 + c); };   // 22..25
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + B_BAR + 8 * 26);
+  // L_q = lse_q * log2(e) and delta_q = dO_q . O_q, double-buffered by item parity: [2][256] floats each
   float* sL = reinterpret_cast<float*>(smem + B_SL);
   float* sD = reinterpret_cast<float*>(smem + B_SD);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -481,8 +484,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_do)) : "memory");
     for (int i = 0; i < 2; ++i) { mbar_init(kv_full(i), 1); mbar_init(kv_free(i), 1); mbar_init(st_full(i), 1); mbar_init(p_full(i), 8); mbar_init(ds_free(i), 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(qd_full(i), 1); mbar_init(qd_free(i), 1); }
-    mbar_init(dvk_full, 1); mbar_init(dvk_free, 8); mbar_init(dq_full, 1); mbar_init(dq_free, 8);
+    for (int i = 0; i < 4; ++i) { mbar_init(qd_full(i), 1); mbar_init(qd_free(i), 1); mbar_init(delta_ready(i), 4); }
+    mbar_init(dvk_full, 1); mbar_init(dvk_free, 4); mbar_init(dq_full, 1); mbar_init(dq_free, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -604,74 +607,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
       }
       back(7);
     }
-  } else {
-    // ===================== softmax / epilogue warps =====================
+  } else if (warp < 10) {
+    // ===================== softmax warps: never leave the step loop =====================
     const int we = warp - 2;
     const int qr = warp & 3;             // TMEM lane quarter
-    const int ch = we >> 2;              // column half (32 of the 64 chunk columns) / output selector
-    const int row = qr * 32 + lane;      // TMEM lane = key (steps, dV/dK) or query (dQ) inside a 128-row tile
-    const int tid = we * 32 + lane;      // 0..255
+    const int ch = we >> 2;              // column half (32 of the 64 chunk columns)
+    const int row = qr * 32 + lane;      // TMEM lane = key inside the 128-key tile
     const float sl2 = SCALE * LOG2E;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qr * 32) << 16);
-    const uint32_t sdO = sbase + B_SDO, sDS = sbase + B_SDS;
-    const int64_t hstride = (int64_t)VITK_HEADS * M * 64;
-    // O rows of the item whose delta is computed next, fetched one item ahead.  8 lanes share a row (16 B each): every
-    // load instruction covers 4 full 128-byte rows.  ov[g] = chunk (lane & 7) of query we*32 + 4g + (lane >> 3).
-    uint4 ov[8];
-    float lsv = 0.f;
-    auto fetch_o = [&](int item) {
-      if (dbg & 8) return;
-      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
-      const bf16* obase = out + ((int64_t)b * N_TOK) * VITK_DIM + h * VITK_HEAD_DIM + (lane & 7) * 8;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int q = we * 32 + g * 4 + (lane >> 3);
-        ov[g] = q < N_TOK ? __ldg(reinterpret_cast<const uint4*>(obase + (int64_t)q * VITK_DIM)) : make_uint4(0u, 0u, 0u, 0u);
-      }
-      if (tid < N_TOK) lsv = __ldg(lse + (int64_t)h * M + (int64_t)b * N_TOK + tid);
-    };
-    if (n_my > 0) fetch_o(blockIdx.x);
+    const uint32_t sDS = sbase + B_SDS;
     for (int it = 0; it < n_my; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
-      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
       const uint32_t ipar = it & 1;
-      const int64_t hm = ((int64_t)h * M + (int64_t)b * N_TOK) * 64;
-      // delta_q = dO_q . O_q and L_q = lse_q * log2(e) for the 64 queries of chunk c (thread tid = query tid); runs one
-      // chunk ahead of its use, off the critical path of the step that needs it
-      auto delta_chunk = [&](int c) {
-        if ((we >> 1) == c && !(dbg & 8)) {
-          mbar_wait(qd_full(c), ipar);       // dO_c has landed
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int q = we * 32 + g * 4 + (lane >> 3), r = q & 63;
-            uint4 av;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(av.x), "=r"(av.y), "=r"(av.z), "=r"(av.w)
-                         : "r"(sdO + c * 8192 + r * 128 + (((lane & 7) ^ (r & 7)) << 4)));
-            const float2 a0 = unpack_bf16x2(av.x), a1 = unpack_bf16x2(av.y), a2 = unpack_bf16x2(av.z), a3 = unpack_bf16x2(av.w);
-            const float2 o0 = unpack_bf16x2(ov[g].x), o1 = unpack_bf16x2(ov[g].y), o2 = unpack_bf16x2(ov[g].z), o3 = unpack_bf16x2(ov[g].w);
-            float dl = a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
-            dl += __shfl_xor_sync(0xffffffffu, dl, 1);
-            dl += __shfl_xor_sync(0xffffffffu, dl, 2);
-            dl += __shfl_xor_sync(0xffffffffu, dl, 4);
-            if ((lane & 7) == 0) sD[q] = q < N_TOK ? dl : 0.f;
-          }
-          sL[tid] = tid < N_TOK ? lsv * LOG2E : 0.f;
-        }
-      };
-      delta_chunk(0);
+      const uint32_t sLb = sbase + B_SL + ipar * 1024, sDb = sbase + B_SD + ipar * 1024;   // this item's L / delta
 #pragma unroll 1
       for (int s = 0; s < 8; ++s) {
         const int t = s >> 2, c = s & 3, buf = s & 1, m = c >> 1;
         const int n_b = it * 4 + (s >> 1);
         const int key = t * 128 + row;
-        mbar_wait(st_full(buf), n_b & 1);      // MMA1/2 of this step retired: Q_c / dO_c are in shared memory
+        mbar_wait(st_full(buf), n_b & 1);      // MMA1/2 of this step retired
         if ((c & 1) == 0) mbar_wait(ds_free(m), ((it * 2 + t) & 1) ^ 1);   // MMA5 of the previous key tile has read dS^T buffer m
+        if (t == 0) mbar_wait(delta_ready(c), ipar);                       // L / delta of this chunk's queries (epilogue warps)
         tc_fence_after();
-        if (t == 0) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");   // delta / L of this chunk (written during the previous step) visible
-        } else if (s == 4 && it + 1 < n_my) {
-          fetch_o(item + gridDim.x);   // next item's O rows: in flight during this item's second key tile
-        }
         const uint32_t a_st = lane_addr + buf * 128 + ch * 32, a_dp = a_st + 64;
         const uint32_t ds_row = sDS + m * 32768 + (c & 1) * 16384 + row * 128;
         if (dbg & 2) {
@@ -684,9 +640,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Lr[j4].x), "=f"(Lr[j4].y), "=f"(Lr[j4].z), "=f"(Lr[j4].w)
-                         : "r"(sbase + B_SL + (q0 + j4 * 4) * 4));
+                         : "r"(sLb + (q0 + j4 * 4) * 4));
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Dr[j4].x), "=f"(Dr[j4].y), "=f"(Dr[j4].z), "=f"(Dr[j4].w)
-                         : "r"(sbase + B_SD + (q0 + j4 * 4) * 4));
+                         : "r"(sDb + (q0 + j4 * 4) * 4));
           }
           tm_ld_wait();
           // the partner warp (other column half, same lanes) must have read its scores before either overwrites them
@@ -716,6 +672,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
           uint32_t vs[16], vd[16];
           tm_ld16(lane_addr + buf * 128, vs);
           tm_ld16(lane_addr + buf * 128 + 64, vd);
+          float Lq[16], Dq[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Lq[j4 * 4]), "=f"(Lq[j4 * 4 + 1]), "=f"(Lq[j4 * 4 + 2]), "=f"(Lq[j4 * 4 + 3])
+                         : "r"(sLb + (192 + j4 * 4) * 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Dq[j4 * 4]), "=f"(Dq[j4 * 4 + 1]), "=f"(Dq[j4 * 4 + 2]), "=f"(Dq[j4 * 4 + 3])
+                         : "r"(sDb + (192 + j4 * 4) * 4));
+          }
           tm_ld_wait();
           uint32_t pp[8], pd[8];
 #pragma unroll
@@ -723,9 +687,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
             float p[2], d[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int q = 192 + 2 * j + e;
-              p[e] = (key < N_TOK && q < N_TOK) ? ex2(fmaf(__uint_as_float(vs[2 * j + e]), sl2, -sL[q])) : 0.f;
-              d[e] = p[e] * (__uint_as_float(vd[2 * j + e]) - sD[q]);
+              const int qi = 2 * j + e;
+              p[e] = (key < N_TOK && 192 + qi < N_TOK) ? ex2(fmaf(__uint_as_float(vs[qi]), sl2, -Lq[qi])) : 0.f;
+              d[e] = p[e] * (__uint_as_float(vd[qi]) - Dq[qi]);
             }
             pp[j] = pack_bf16x2(p[0], p[1]);
             pd[j] = pack_bf16x2(d[0], d[1]);
@@ -742,46 +706,93 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(buf));
-        if (t == 0 && c < 3) delta_chunk(c + 1);
-
-        if (c == 3) {
-          // ---- dV_t (ch 0) / dK_t (ch 1): lane = key
-          mbar_wait(dvk_full, (it * 2 + t) & 1);
-          tc_fence_after();
-          bf16* dbase = dqkv + hm + (ch == 0 ? 2 : 1) * hstride;
-          const float sc = ch == 0 ? 1.0f : SCALE;
-          const int k0w = t * 128 + qr * 32;      // first key of this warp
-#pragma unroll
-          for (int half = 0; half < 2 && !(dbg & 4); ++half) {
-            uint32_t o[32];
-            tm_ld32(lane_addr + (ch == 0 ? T_DV : T_DK) + half * 32, o);
-            tm_ld_wait();
-            store_slab32(sbase + B_STG + (uint32_t)we * 2048, lane, o, sc,
-                         [&](int r) -> bf16* { return (k0w + r < N_TOK) ? dbase + (int64_t)(k0w + r) * 64 + half * 32 : nullptr; });
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dvk_free);
-        }
       }
-      // ---- dQ: q-tile m = ch, lane = query
-      {
-        mbar_wait(dq_full, ipar);
-        tc_fence_after();
-        const int q0w = ch * 128 + qr * 32;       // first query of this warp
-        bf16* dbase = dqkv + hm;
+    }
+  } else {
+    // ===================== epilogue / delta warps (10..13): everything that is not on the step critical path ==========
+    //   delta_q = dO_q . O_q and L_q for the NEXT item's queries as its dO chunks land; dV / dK after each key tile and dQ
+    //   after the item: tensor memory -> staging tile -> coalesced global rows.
+    const int ew = warp - 10;            // 0..3
+    const int qr = warp & 3;             // TMEM lane quarter this warp may touch
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(qr * 32) << 16);
+    const uint32_t sdO = sbase + B_SDO, stg = sbase + B_STG + (uint32_t)ew * 2048;
+    const int64_t hstride = (int64_t)VITK_HEADS * M * 64;
+    // chunk c of item `it_` (its dO_c must have landed): every warp takes 16 of the 64 queries, 8 lanes per query
+    auto delta_chunk = [&](int it_, int c) {
+      if (dbg & 8) { __syncwarp(); if (lane == 0) mbar_arrive(delta_ready(c)); return; }
+      const int item = blockIdx.x + it_ * gridDim.x;
+      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
+      const bf16* obase = out + ((int64_t)b * N_TOK) * VITK_DIM + h * VITK_HEAD_DIM + (lane & 7) * 8;
+      float* dD = sD + (it_ & 1) * 256;
+      float* dL = sL + (it_ & 1) * 256;
+      uint4 ov[4];
 #pragma unroll
-        for (int half = 0; half < 2 && !(dbg & 4); ++half) {
-          uint32_t o[32];
-          tm_ld32(lane_addr + T_DQ + ch * 64 + half * 32, o);
-          tm_ld_wait();
-          store_slab32(sbase + B_STG + (uint32_t)we * 2048, lane, o, SCALE,
-                       [&](int r) -> bf16* { return (q0w + r < N_TOK) ? dbase + (int64_t)(q0w + r) * 64 + half * 32 : nullptr; });
-        }
+      for (int g = 0; g < 4; ++g) {
+        const int q = c * 64 + ew * 16 + g * 4 + (lane >> 3);
+        ov[g] = q < N_TOK ? __ldg(reinterpret_cast<const uint4*>(obase + (int64_t)q * VITK_DIM)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      const int ql = c * 64 + ew * 16 + (lane & 15);     // lanes 0..15: the log-sum-exp of this warp's 16 queries
+      const float lv = (lane < 16 && ql < N_TOK) ? __ldg(lse + (int64_t)h * M + (int64_t)b * N_TOK + ql) : 0.f;
+      mbar_wait(qd_full(c), it_ & 1);     // dO_c of that item has landed
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int q = c * 64 + ew * 16 + g * 4 + (lane >> 3), r = q & 63;
+        uint4 av;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(av.x), "=r"(av.y), "=r"(av.z), "=r"(av.w)
+                     : "r"(sdO + c * 8192 + r * 128 + (((lane & 7) ^ (r & 7)) << 4)));
+        const float2 a0 = unpack_bf16x2(av.x), a1 = unpack_bf16x2(av.y), a2 = unpack_bf16x2(av.z), a3 = unpack_bf16x2(av.w);
+        const float2 o0 = unpack_bf16x2(ov[g].x), o1 = unpack_bf16x2(ov[g].y), o2 = unpack_bf16x2(ov[g].z), o3 = unpack_bf16x2(ov[g].w);
+        float dl = a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
+        dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+        dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+        dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+        if ((lane & 7) == 0) dD[q] = q < N_TOK ? dl : 0.f;
+      }
+      if (lane < 16) dL[ql] = lv * LOG2E;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(delta_ready(c));     // release: the stores above are visible to the waiting softmax warps
+    };
+    // one 128-row x 64-column fp32 accumulator tile (TMEM column `col`) -> bf16 rows of `dst` (row stride 64), rows < n_valid
+    auto drain_tile = [&](uint32_t col, bf16* dst, int row0, float scale) {
+#pragma unroll
+      for (int half = 0; half < 2 && !(dbg & 4); ++half) {
+        uint32_t o[32];
+        tm_ld32(lane_addr + col + half * 32, o);
+        tm_ld_wait();
+        store_slab32(stg, lane, o, scale,
+                     [&](int r) -> bf16* { return (row0 + qr * 32 + r < N_TOK) ? dst + (int64_t)(row0 + qr * 32 + r) * 64 + half * 32 : nullptr; });
+      }
+    };
+    if (n_my > 0)
+      for (int c = 0; c < 4; ++c) delta_chunk(0, c);
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
+      const uint32_t ipar = it & 1;
+      const int64_t hm = ((int64_t)h * M + (int64_t)b * N_TOK) * 64;
+      const bool has_next = it + 1 < n_my;
+      for (int t = 0; t < 2; ++t) {
+        // ---- dV_t, dK_t (lane = key)
+        mbar_wait(dvk_full, (it * 2 + t) & 1);
+        tc_fence_after();
+        drain_tile(T_DV, dqkv + hm + 2 * hstride, t * 128, 1.0f);
+        drain_tile(T_DK, dqkv + hm + hstride, t * 128, SCALE);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(dq_free);
+        if (lane == 0) mbar_arrive(dvk_free);
+        // the next item's dO chunks 0..2 land while this item's second key tile runs
+        if (t == 0 && has_next)
+          for (int c = 0; c < 3; ++c) delta_chunk(it + 1, c);
       }
+      // ---- dQ (lane = query), two 128-query tiles
+      mbar_wait(dq_full, ipar);
+      tc_fence_after();
+      drain_tile(T_DQ, dqkv + hm, 0, SCALE);
+      drain_tile(T_DQ + 64, dqkv + hm, 128, SCALE);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+      if (has_next) delta_chunk(it + 1, 3);
     }
   }
 
@@ -837,7 +848,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   VITK_TRY(atc::make_hm_map(qkv, M, 3 * VITK_HEADS, 64, &map_q));
   VITK_TRY(atc::make_dout_map(dout, M, &map_do));
   const int items = batch * VITK_HEADS, sms = sm_count();
-  VITK_LAUNCH((atc::attn_bwd_tc_kernel), (items < sms ? items : sms), atc::THREADS, atc::BWD_SMEM, st, map_kv, map_q, map_do,
+  VITK_LAUNCH((atc::attn_bwd_tc_kernel), (items < sms ? items : sms), atc::BWD_THREADS, atc::BWD_SMEM, st, map_kv, map_q, map_do,
               (const bf16*)out, lse, (bf16*)dqkv, batch, items, debug_knob(7));
   return VITK_OK;
 }
