@@ -180,7 +180,7 @@ def run_ours(args):
     torch.manual_seed(42)
     model = pkg.ViTFaceAntiSpoofing(dropout=0.1, depth=12, precision="bf16").to(dev)
     model.train()
-    net = pkg.DataParallel(model) if world > 1 else model
+    net = pkg.DataParallel(model, bucket_mb=float(os.environ.get("VITK_BUCKET_MB", "50"))) if world > 1 else model
     crit = pkg.FocalLoss(alpha=0.25, gamma=2.0)
     opt = pkg.FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4, adamw=False)
     total_sched_steps = 2 * (args.warmup + args.steps) + 64
@@ -299,7 +299,12 @@ def run_ours(args):
         achieved = fl / tt / 1e12 if tt > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "vitk::gemm_tc_kernel (tcgen05.mma kind::f16, all GEMM launches of a step)",
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] +
+                "frac": achieved / peaks["bf16_tflops_sustained"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of the most expensive launch family (fc1 forward,
+                # 12608x3072x768 + GELU: 24.26 MB read + 105.75 MB written back by kernel end; algorithmic 179 MB, the
+                # rest of the 155 MB of output is still in the 126 MB L2) from profiles/r1_ncu_gemm_tc_v5.md
+                "traffic": 130.0e6, "traffic_unit": "B per launch (ncu --set full, fc1 forward launch)",
+                "peak_source": peaks["source"] +
                 " (sustained cuBLAS bf16: kernel timed inside a long step)", "gemm_launches_per_step": n // 2,
                 "gemm_share_of_step": (tt / 2) / (ms_total / args.steps / 1e3)}
         fam_sorted = sorted(fam.items(), key=lambda kv: -kv[1][2])
