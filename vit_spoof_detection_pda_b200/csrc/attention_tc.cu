@@ -16,6 +16,7 @@
 // pollute their own (never stored) output rows, key columns >= 197 are masked to p = 0.
 // Algorithmic FLOPs per item: 4 * 197^2 * 64; exps: 197 * 208 (MUFU-bound: 16/clk/SM).
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -420,10 +421,17 @@ static int make_hm_map(const void* base, int64_t M, int n_blk, int box_rows, CUt
   cuuint64_t strides[2] = {128, (cuuint64_t)M * 128};
   cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
   if ((uintptr_t)base & 15) { set_error("attention: qkv must be 16-byte aligned"); return VITK_ERR_ARG; }
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = 3; key.dtype = VITK_BF16; key.swizzle = 128; key.l2promo = 128;
+  for (int i = 0; i < 3; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  key.strides[0] = strides[0]; key.strides[1] = strides[1];
+  if (tmap_cache_get(key, map)) return VITK_OK;
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention) failed: CUresult %d", (int)r); return VITK_ERR_DRIVER; }
+  tmap_cache_put(key, map);
   return VITK_OK;
 }
 
@@ -812,10 +820,17 @@ static int make_dout_map(const void* base, int64_t M, CUtensorMap* map) {
   cuuint64_t strides[1] = {(cuuint64_t)VITK_DIM * 2};
   cuuint32_t box[2] = {64, 64}, estr[2] = {1, 1};
   if ((uintptr_t)base & 15) { set_error("attention: dout must be 16-byte aligned"); return VITK_ERR_ARG; }
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = 2; key.dtype = VITK_BF16; key.swizzle = 128; key.l2promo = 129;
+  key.dims[0] = dims[0]; key.dims[1] = dims[1]; key.box[0] = box[0]; key.box[1] = box[1];
+  key.strides[0] = strides[0];
+  if (tmap_cache_get(key, map)) return VITK_OK;
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention dout) failed: CUresult %d", (int)r); return VITK_ERR_DRIVER; }
+  tmap_cache_put(key, map);
   return VITK_OK;
 }
 

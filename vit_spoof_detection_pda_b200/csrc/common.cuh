@@ -44,6 +44,20 @@ int default_engine();  // process-wide GEMM/attention engine (VITK_ENGINE_*)
     VITK_CUDA(cudaPeekAtLastError());       \
   } while (0)
 
+// Host-side cache of encoded TMA tensor maps.  Workspaces, parameters and gradient buffers are persistent, so the same
+// (base, dims, strides, box, type, swizzle) keys recur every step; cuTensorMapEncodeTiled costs microseconds and a
+// training step needs ~700 maps -- a lookup keeps the launch path off the host's critical path.  A descriptor depends on
+// nothing but its key, so entries never go stale.  `key` is hashed as raw bytes: zero-initialise it before filling it in.
+struct TmapKey {
+  const void* base;
+  uint64_t dims[3];
+  uint64_t strides[2];
+  uint32_t box[3];
+  uint32_t rank, dtype, swizzle, l2promo;
+};
+bool tmap_cache_get(const TmapKey& key, void* map128);   // map128: CUtensorMap (128 bytes)
+void tmap_cache_put(const TmapKey& key, const void* map128);
+
 // Programmatic dependent launch (PDL).  Every kernel of the library is launched with the programmatic-stream-
 // serialization attribute and begins with pdl_sync(): griddepcontrol.wait (returns once the preceding kernel of the
 // stream has completed and flushed) followed by griddepcontrol.launch_dependents (the next kernel may start being

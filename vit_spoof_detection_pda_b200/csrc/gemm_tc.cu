@@ -24,6 +24,7 @@
 // Replaces the cuBLASLt GEMMs behind timm's nn.Linear layers (SURVEY.md 2.1 K4,K6,K7,K8 and their
 // autograd backward), reached from /root/reference/train_advanced.py:327-330.
 #include <cuda.h>
+#include <string.h>
 
 #include "gemm.cuh"
 
@@ -883,9 +884,16 @@ static int make_operand_map(const void* base, const MatLayout& l, int rows, int 
     set_error("gemm_tc: operand base/strides must be 16-byte aligned");
     return VITK_ERR_ARG;
   }
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = 3; key.dtype = VITK_BF16; key.swizzle = 128; key.l2promo = 256;
+  for (int i = 0; i < 3; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  key.strides[0] = strides[0]; key.strides[1] = strides[1];
+  if (tmap_cache_get(key, map)) return VITK_OK;
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) tmap_cache_put(key, map);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u)", (int)r,
               (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
@@ -918,11 +926,18 @@ static int make_tile_map(const void* base, int dtype, int64_t cols, int64_t rows
     strides[0] = (cuuint64_t)ld * elt; strides[1] = strides[0] * (cuuint64_t)rows;
   }
   if (((uintptr_t)base & 15) || (strides[0] & 15)) { set_error("gemm_tc: epilogue operand must be 16-byte aligned"); return VITK_ERR_ARG; }
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = (uint32_t)rank; key.dtype = (uint32_t)dtype; key.swizzle = dtype == VITK_BF16 ? 64 : 128; key.l2promo = 128;
+  for (int i = 0; i < 3; ++i) { key.dims[i] = i < rank ? dims[i] : 0; key.box[i] = box[i]; }
+  key.strides[0] = strides[0]; key.strides[1] = rank == 3 ? strides[1] : 0;
+  if (tmap_cache_get(key, map)) return VITK_OK;
   const CUresult r = enc(map, dtype == VITK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
                          const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          dtype == VITK_BF16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (epilogue tile) failed: CUresult %d", (int)r); return VITK_ERR_DRIVER; }
+  tmap_cache_put(key, map);
   return VITK_OK;
 }
 
