@@ -118,6 +118,12 @@ int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, float* dw, f
 int vitk_patch_embed_fwd(const float* images, const void* wpe, const float* bpe, const float* cls,
                          const float* pos, void* patches, float* x0, int batch, int dtype, int engine,
                          void* stream);
+/* same forward from uint8 HWC pixels [B][224][224][3]: ToTensor (x / 255) + Normalize ((x - mean[c]) / std[c]) of the
+ * reference's transforms (train_advanced.py:174-175, 180-181; test.py get_test_transforms) fused into the patch loader:
+ * 150 KB instead of 602 KB read per image, no fp32 NCHW tensor materialised */
+int vitk_patch_embed_fwd_u8(const uint8_t* images_hwc, const float* mean3, const float* std3, const void* wpe,
+                            const float* bpe, const float* cls, const float* pos, void* patches, float* x0, int batch,
+                            int dtype, int engine, void* stream);
 int vitk_patch_embed_wgrad(const float* dx0, const void* dx0_act, const void* patches, float* dwpe,
                            float* dbpe, float* dcls, float* dpos, int batch, int dtype, int engine,
                            void* stream);
@@ -166,6 +172,20 @@ int vitk_focal_fwd_bwd(const float* logits, const int64_t* targets, const float*
                        int num_classes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Evaluation post-processing on the device: replaces the per-batch device->host copy of scores and the
+ * numpy/sklearn loop of find_optimal_threshold (train_advanced.py:239-275: np.linspace(0.3, 0.7, 41), preds =
+ * probs >= thresh, accuracy / precision / recall / F1 per threshold) and the confusion counts of calculate_metrics
+ * (test.py:241-243).
+ *   vitk_threshold_hist  : hist[(label == 1)][k] += 1 with k = |{s : thresholds[s] <= probs[i]}| (float64 comparison, as
+ *                          numpy does for a float32 array against a float64 scalar); thresholds ascending, steps <= 255;
+ *                          hist = uint64 [2][steps + 1], ACCUMULATED across calls (caller zeroes it once per epoch)
+ *   vitk_threshold_counts: counts[s] = (tp, fp, tn, fn) at thresholds[s] (live = 1 is the positive class), int64 [steps][4]
+ * ------------------------------------------------------------------------------------------- */
+int vitk_threshold_hist(const float* probs, const int64_t* labels, const double* thresholds, int n, int steps,
+                        unsigned long long* hist, void* stream);
+int vitk_threshold_counts(const unsigned long long* hist, int steps, long long* counts, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused multi-tensor Adam / AdamW over one flat fp32 parameter buffer
  * (torch.optim.AdamW at train_advanced.py:592-597, Adam-L2 per README.md:140-147,
  *  clip_grad_norm_ at :334, GradScaler.unscale_ at :333).
@@ -206,6 +226,11 @@ typedef struct vitk_model {
   const float* dlogits;                         /* [B][C] fp32, input of backward                     */
   int32_t frozen_backbone;                      /* 1: backward stops after the head (config 4)        */
   int32_t reserved;
+  /* input edge: when images_u8 != NULL the patch loader reads uint8 HWC pixels [B][224][224][3]
+   * and applies ToTensor + Normalize (train_advanced.py:174-175 / 180-181: x/255, (x - mean[c]) / std[c], fp32, in that
+   * order) itself; `images` is then ignored */
+  const uint8_t* images_u8;
+  float norm_mean[3], norm_std[3];
 } vitk_model;
 
 /* n_tensors = 4 + 12*depth + 8; offsets/sizes in elements, state_dict order. returns total elements */

@@ -7,7 +7,9 @@ Public API mirrors the reference's own objects for this path (/root/reference/tr
 from . import _lib
 from .dp import DataParallel, DevicePrefetcher
 from .loss import FocalLoss, eval_postprocess
+from .metrics import ThresholdSweep, confusion_counts, find_optimal_threshold
 from .module import ViTFaceAntiSpoofing
 from .optim import FusedAdam, clip_grad_norm_
 
-__all__ = ["ViTFaceAntiSpoofing", "FocalLoss", "FusedAdam", "clip_grad_norm_", "DataParallel", "DevicePrefetcher", "eval_postprocess", "_lib"]
+__all__ = ["ViTFaceAntiSpoofing", "FocalLoss", "FusedAdam", "clip_grad_norm_", "DataParallel", "DevicePrefetcher", "eval_postprocess", "ThresholdSweep",
+           "find_optimal_threshold", "confusion_counts", "_lib"]

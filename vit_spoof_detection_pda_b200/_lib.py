@@ -27,7 +27,8 @@ class VitkModel(C.Structure):
     _fields_ = [("batch", C.c_int32), ("depth", C.c_int32), ("num_classes", C.c_int32), ("precision", C.c_int32),
                 ("training", C.c_int32), ("engine", C.c_int32),
                 ("params", vp), ("params16", vp), ("grads", vp), ("workspace", vp), ("images", vp), ("logits", vp),
-                ("mask1", vp), ("mask2", vp), ("dlogits", vp), ("frozen_backbone", C.c_int32), ("reserved", C.c_int32)]
+                ("mask1", vp), ("mask2", vp), ("dlogits", vp), ("frozen_backbone", C.c_int32), ("reserved", C.c_int32),
+                ("images_u8", vp), ("norm_mean", C.c_float * 3), ("norm_std", C.c_float * 3)]
 
 
 # name -> (restype, argtypes); every symbol include/vitk.h declares
@@ -42,6 +43,7 @@ PROTOTYPES = {
     "vitk_linear_dgrad": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "vitk_linear_wgrad": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "vitk_patch_embed_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "vitk_patch_embed_fwd_u8": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "vitk_patch_embed_wgrad": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "vitk_attn_fwd": (i32, [vp, vp, vp, i32, i32, vp]),
     "vitk_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp]),
@@ -49,6 +51,8 @@ PROTOTYPES = {
     "vitk_head_fwd": (i32, [vp] * 11 + [i32, i32, vp]),
     "vitk_head_bwd": (i32, [vp] * 14 + [i32, i32, vp]),
     "vitk_focal_fwd_bwd": (i32, [vp, vp, vp, f32, i32, f32, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    "vitk_threshold_hist": (i32, [vp, vp, vp, i32, i32, vp, vp]),
+    "vitk_threshold_counts": (i32, [vp, i32, vp, vp]),
     "vitk_grad_sumsq_scratch_floats": (sz, []),
     "vitk_grad_sumsq": (i32, [vp, sz, vp, vp, vp]),
     "vitk_adam_step": (i32, [vp, vp, vp, vp, vp, sz, f64, f64, f64, f64, f64, i32, i32, f32, vp, f32, vp]),

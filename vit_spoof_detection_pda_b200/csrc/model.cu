@@ -217,7 +217,7 @@ extern "C" int vitk_model_num_bwd_stages(int depth) { return depth + 2; }
 extern "C" int vitk_model_fwd(const vitk_model* m, void* stream) {
   Ctx c;
   VITK_TRY(make_ctx(m, stream, &c));
-  VITK_CHECK_ARG(m->images && m->logits);
+  VITK_CHECK_ARG((m->images || m->images_u8) && m->logits);
   const ParamOffsets& po = c.po;
   const Plan& pl = c.pl;
   const int M = c.M, dt = c.dt, eng = m->engine;
@@ -225,8 +225,12 @@ extern "C" int vitk_model_fwd(const vitk_model* m, void* stream) {
   char* ws = c.ws;
   auto xin = [&](int l) { return (float*)(ws + pl.x_in + pl.x_stride * (size_t)(c.save ? l : (l & 1))); };
 
-  VITK_TRY(vitk_patch_embed_fwd(m->images, c.W(po.pew), c.P(po.peb), c.P(po.cls), c.P(po.pos), ws + pl.patches, xin(0),
-                                m->batch, dt, eng, st));
+  if (m->images_u8)   // uint8 HWC pixels: ToTensor + Normalize fused into the patch loader
+    VITK_TRY(vitk_patch_embed_fwd_u8(m->images_u8, m->norm_mean, m->norm_std, c.W(po.pew), c.P(po.peb), c.P(po.cls), c.P(po.pos),
+                                     ws + pl.patches, xin(0), m->batch, dt, eng, st));
+  else
+    VITK_TRY(vitk_patch_embed_fwd(m->images, c.W(po.pew), c.P(po.peb), c.P(po.cls), c.P(po.pos), ws + pl.patches, xin(0),
+                                  m->batch, dt, eng, st));
   for (int l = 0; l < m->depth; ++l) {
     const BlockOffsets& b = po.blk[l];
     float* x = xin(l);

@@ -296,7 +296,15 @@ class ViTFaceAntiSpoofing(nn.Module):
         m.grads = L.ptr(grads)
         base = ws.data_ptr()
         m.workspace = (base + 255) // 256 * 256
-        m.images = L.ptr(images)
+        if images is not None and images.dtype == torch.uint8:
+            # uint8 HWC pixels: ToTensor + Normalize happen inside the patch loader
+            m.images = None
+            m.images_u8 = L.ptr(images)
+            m.norm_mean = (C.c_float * 3)(*self.pixel_mean)
+            m.norm_std = (C.c_float * 3)(*self.pixel_std)
+        else:
+            m.images = L.ptr(images)
+            m.images_u8 = None
         m.logits = L.ptr(logits)
         m.dlogits = L.ptr(dlogits)
         m.mask1 = L.ptr(masks[0]) if masks else None
@@ -304,11 +312,20 @@ class ViTFaceAntiSpoofing(nn.Module):
         m.frozen_backbone = 1 if frozen else 0
         return m
 
+    # ImageNet statistics of the reference's transforms.Normalize (train_advanced.py:175, 181; test.py:162)
+    pixel_mean = (0.485, 0.456, 0.406)
+    pixel_std = (0.229, 0.224, 0.225)
+
     def _prep_images(self, x):
-        if x.dim() != 4 or tuple(x.shape[1:]) != (3, L.IMG, L.IMG):
-            raise ValueError(f"expected images [B,3,{L.IMG},{L.IMG}], got {tuple(x.shape)}")
         if not x.is_cuda:
             raise RuntimeError("vitk forward needs CUDA tensors (no CPU fallback)")
+        if x.dtype == torch.uint8:
+            # raw resized pixels, HWC as PIL / the decoder delivers them: [B,224,224,3]
+            if x.dim() != 4 or tuple(x.shape[1:]) != (L.IMG, L.IMG, 3):
+                raise ValueError(f"expected uint8 images [B,{L.IMG},{L.IMG},3] (HWC), got {tuple(x.shape)}")
+            return x.detach().contiguous()
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, L.IMG, L.IMG):
+            raise ValueError(f"expected images [B,3,{L.IMG},{L.IMG}], got {tuple(x.shape)}")
         return x.detach().to(torch.float32).contiguous()
 
     def _run_forward(self, images, training: bool):
