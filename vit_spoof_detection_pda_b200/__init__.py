@@ -9,7 +9,7 @@ from .dp import DataParallel, DevicePrefetcher
 from .loss import FocalLoss, eval_postprocess
 from .metrics import ThresholdSweep, confusion_counts, find_optimal_threshold
 from .module import ViTFaceAntiSpoofing
-from .optim import FusedAdam, clip_grad_norm_
+from .optim import FusedAdam, FusedGradScaler, clip_grad_norm_
 
-__all__ = ["ViTFaceAntiSpoofing", "FocalLoss", "FusedAdam", "clip_grad_norm_", "DataParallel", "DevicePrefetcher", "eval_postprocess", "ThresholdSweep",
+__all__ = ["ViTFaceAntiSpoofing", "FocalLoss", "FusedAdam", "FusedGradScaler", "clip_grad_norm_", "DataParallel", "DevicePrefetcher", "eval_postprocess", "ThresholdSweep",
            "find_optimal_threshold", "confusion_counts", "_lib"]

@@ -66,7 +66,9 @@ def clip_grad_norm_(parameters, max_norm: float):
         owner._sumsq = torch.zeros(1, dtype=torch.float32, device=g.device)
     L.call("vitk_grad_sumsq", L.ptr(g), g.numel(), L.ptr(owner._sumsq_scratch), L.ptr(owner._sumsq), L.stream_ptr())
     owner._pending_clip = (owner._sumsq, float(max_norm))
-    return owner._sumsq.sqrt().reshape(())
+    mult = getattr(owner, "_grad_mult", 1.0)     # 1/scale after FusedGradScaler.unscale_ (folded into the Adam pass)
+    norm = owner._sumsq.sqrt().reshape(())
+    return norm * mult if mult != 1.0 else norm
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -113,6 +115,8 @@ class FusedAdam(torch.optim.Optimizer):
         # frozen parameters must not move: zero their gradient AND skip decay by masking ranges
         frozen = [(off, n) for p, off, n in zip(owner._param_list(), owner._offsets, owner._sizes) if not p.requires_grad]
         self._step += 1
+        self._grad_mult_now = float(self.grad_mult) * float(getattr(owner, "_grad_mult", 1.0))
+        owner._grad_mult = 1.0                      # consumed: the next backward produces freshly scaled gradients
         p16 = owner._flat16 if owner.precision == "bf16" else None
         b1, b2 = grp["betas"]
         if not frozen:
@@ -132,7 +136,7 @@ class FusedAdam(torch.optim.Optimizer):
         L.call("vitk_adam_step", flat.data_ptr() + 4 * lo, g.data_ptr() + 4 * lo, self._m.data_ptr() + 4 * lo,
                self._v.data_ptr() + 4 * lo, (p16.data_ptr() + 2 * lo) if p16 is not None else None, n,
                float(grp["lr"]), float(b1), float(b2), float(grp["eps"]), float(grp["weight_decay"]),
-               1 if grp["adamw"] else 0, self._step, float(self.grad_mult), L.ptr(sumsq), float(max_norm), L.stream_ptr())
+               1 if grp["adamw"] else 0, self._step, float(self._grad_mult_now), L.ptr(sumsq), float(max_norm), L.stream_ptr())
 
     def zero_grad(self, set_to_none: bool = True):
         super().zero_grad(set_to_none=set_to_none)
@@ -165,6 +169,88 @@ class FusedAdam(torch.optim.Optimizer):
             self._m[off:off + n].copy_(st["exp_avg"].reshape(-1))
             self._v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
             self._step = int(float(st["step"]))
+
+
+class FusedGradScaler:
+    """``torch.cuda.amp.GradScaler`` for the fused path (the reference builds one at train_advanced.py:609 and drives it at
+    :330-336: ``scaler.scale(loss).backward(); scaler.unscale_(optimizer); clip_grad_norm_(...); scaler.step(optimizer);
+    scaler.update()``).  Same API and state machine -- skip the step when a gradient is non-finite, halve the scale, double
+    it after ``growth_interval`` clean steps -- but the unscale never touches memory: 1/scale is folded into the single
+    sum-of-squares + Adam pass (``grad_mult``), and the finiteness test is the finiteness of that one sum of squares.
+    Like torch's, ``step`` reads one scalar back (one host sync per step; the reference loop has two more at :345-346).
+    bf16 needs no loss scaling; this exists so the reference's loop runs unmodified."""
+
+    def __init__(self, init_scale: float = 2.0 ** 16, growth_factor: float = 2.0, backoff_factor: float = 0.5,
+                 growth_interval: int = 2000, enabled: bool = True):
+        self._enabled = bool(enabled)
+        self._scale = float(init_scale)
+        self._growth_factor, self._backoff_factor = float(growth_factor), float(backoff_factor)
+        self._growth_interval = int(growth_interval)
+        self._growth_tracker = 0
+        self._found_inf = False
+        self._unscaled = False
+
+    def is_enabled(self):
+        return self._enabled
+
+    def get_scale(self):
+        return self._scale if self._enabled else 1.0
+
+    def scale(self, outputs):
+        return outputs * self._scale if self._enabled else outputs
+
+    def unscale_(self, optimizer):
+        if not self._enabled:
+            return
+        if self._unscaled:
+            raise RuntimeError("unscale_() has already been called on this optimizer since the last update().")
+        optimizer._owner._grad_mult = 1.0 / self._scale
+        self._unscaled = True
+
+    def step(self, optimizer, *args, **kwargs):
+        if not self._enabled:
+            return optimizer.step(*args, **kwargs)
+        if not isinstance(optimizer, FusedAdam):
+            raise TypeError("FusedGradScaler drives FusedAdam; use torch.amp.GradScaler with stock torch optimizers")
+        owner = optimizer._owner
+        if not self._unscaled:
+            self.unscale_(optimizer)
+        if owner._pending_clip is None:          # no clip_grad_norm_ this step: still need the sum of squares
+            clip_grad_norm_(optimizer.param_groups[0]["params"][:1], 0.0)
+        sumsq = owner._pending_clip[0]
+        self._found_inf = not bool(torch.isfinite(sumsq).item())
+        if self._found_inf:
+            owner._pending_clip = None
+            owner._grad_mult = 1.0
+            return None
+        return optimizer.step(*args, **kwargs)
+
+    def update(self, new_scale=None):
+        if not self._enabled:
+            return
+        if new_scale is not None:
+            self._scale = float(new_scale)
+        elif self._found_inf:
+            self._scale *= self._backoff_factor
+            self._growth_tracker = 0
+        else:
+            self._growth_tracker += 1
+            if self._growth_tracker == self._growth_interval:
+                self._scale *= self._growth_factor
+                self._growth_tracker = 0
+        self._found_inf = False
+        self._unscaled = False
+
+    def state_dict(self):
+        return {"scale": self._scale, "growth_factor": self._growth_factor, "backoff_factor": self._backoff_factor,
+                "growth_interval": self._growth_interval, "_growth_tracker": self._growth_tracker} if self._enabled else {}
+
+    def load_state_dict(self, sd):
+        if not sd:
+            return
+        self._scale = float(sd["scale"])
+        self._growth_factor, self._backoff_factor = float(sd["growth_factor"]), float(sd["backoff_factor"])
+        self._growth_interval, self._growth_tracker = int(sd["growth_interval"]), int(sd["_growth_tracker"])
 
 
 def _complement(ranges, total):
