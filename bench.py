@@ -172,7 +172,9 @@ def run_ours(args):
     if world > 1:
         # SMs NCCL may take for the gradient all-reduce; DataParallel shrinks the persistent GEMM grids by the same
         # number while a collective is in flight (see dp.py)
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        # measured on this pool (gpurun_out/w_scale.log, z_scale.log): 2 GPUs 8 CTAs 93.6 %; 8 GPUs 8 / 16 / 32 CTAs
+        # 85.8 / 92.7 / 94.1 % of 8 x the single-GPU rate -- the ring needs more CTAs as it grows
+        os.environ.setdefault("NCCL_MAX_CTAS", "8" if world <= 2 else ("16" if world <= 4 else "32"))
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     lib = L.load()   # fails loudly when libvitk.so is missing
