@@ -41,7 +41,7 @@ for kv in os.environ.get('VITK_KNOBS', '').split(','):
     if kv:
         lib.vitk_debug_set(int(kv.split(':')[0]), int(kv.split(':')[1]))
 print('knobs:', os.environ.get('VITK_KNOBS', ''))
-for variant in ((0,) if os.environ.get('VITK_KNOBS') else (0, 1, 2)):   # 0: tcgen05 kernels, 1: persistent 13-warp mma.sync kernels, 2: first-generation kernels
+for variant in ((0,) if os.environ.get('VITK_KNOBS') else (0, 1)):   # 0: tcgen05 kernels, 1: persistent 13-warp mma.sync kernels
     lib.vitk_debug_set(3, variant)
     fwd = timeit(lambda: lib.vitk_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, L.BF16, st))
     print(f"variant {variant} attn fwd  B={B}: {fwd:7.1f} us  ({B*12*4*197*197*64/fwd/1e6:.1f} TFLOP/s algorithmic)")

@@ -1,18 +1,13 @@
-// Fused multi-head self-attention forward / backward for sequence length 197, d = 64, bf16 operands on the
-// tensor cores (mma.sync m16n8k16, fp32 accumulate), fp32 softmax with quad warp-shuffle reductions.
+// mma.sync (m16n8k16) attention kernels for sequence length 197, d = 64 -- the register-tiled generation that the
+// tcgen05 kernels of attention_tc.cu replaced (53 / 127 us vs 32 / 75 us per layer at batch 64).  Kept selectable
+// (vitk_debug_set(3, 1)) as the A/B baseline: the legacy HMMA pipe peaks at ~550 TFLOP/s on B200 and every MMA needs a
+// 256-byte B fragment from shared memory, which is exactly the 128 B/clk shared-memory port at full rate.
 // Replaces F.scaled_dot_product_attention reached from timm Attention.forward
 // (/root/reference/train_advanced.py:203 -> self.vit(x)).
 //
-// One CTA per (batch, head).  Q/K/V (and dO in backward) of that head are 197x64 contiguous tiles
-// (head-major storage), staged once in shared memory with cp.async in a 128-byte-row XOR swizzle
-// (16-byte chunk c of row r lives at chunk c ^ (r & 7)) so every ldmatrix is bank-conflict free.
-// Rows 197..207 are zero padding (13 tiles of 16).
-//   forward : each warp owns 16 query rows: S = Q K^T (16 x 208, registers), masked softmax, O = P V.
-//   backward: phase A, per 16 query rows:  dQ = scale * [P o (dO V^T - D)] K
-//             phase B, per 16 key rows:    dV = P^T dO ;  dK = scale * [P o (dO V^T - D)]^T Q
-//             with P recomputed from the saved log-sum-exp; no atomics, no fp32 scratch in HBM.
-// Algorithmic FLOPs per (b,h): forward 4*197*197*64; backward 14*197*197*64 (S and dP are recomputed
-// in both phases).
+// Q/K/V (and dO in backward) of one (batch, head) item are 197x64 contiguous tiles (head-major storage), staged in
+// shared memory with cp.async in a 128-byte-row XOR swizzle (16-byte chunk c of row r lives at chunk c ^ (r & 7)) so
+// every ldmatrix is bank-conflict free.  Rows 197..207 are zero padding (13 tiles of 16).
 #include "common.cuh"
 
 namespace vitk {
@@ -21,8 +16,6 @@ constexpr int AM_N = VITK_NTOK;          // 197
 constexpr int AM_NP = 208;               // padded rows
 constexpr int AM_TILES = AM_NP / 16;     // 13
 constexpr int AM_D = VITK_HEAD_DIM;      // 64
-constexpr int AM_WARPS = 7;
-constexpr int AM_THREADS = AM_WARPS * 32;
 constexpr int AM_MAT_BYTES = AM_NP * 128;  // 26,624
 constexpr float AM_SCALE = 0.125f;
 constexpr float AM_LOG2E = 1.4426950408889634f;
@@ -50,18 +43,6 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// stage a [197][64] bf16 matrix (row stride `ld` elements) into swizzled smem, zero the 11 pad rows
-__device__ __forceinline__ void am_stage(uint32_t sbase, const bf16* __restrict__ g, int64_t ld) {
-  for (int idx = threadIdx.x; idx < AM_N * 8; idx += AM_THREADS) {
-    const int r = idx >> 3, c = idx & 7;
-    cp_async16(sbase + am_off(r, c), g + (int64_t)r * ld + c * 8);
-  }
-  for (int idx = threadIdx.x; idx < (AM_NP - AM_N) * 8; idx += AM_THREADS) {
-    const int r = AM_N + (idx >> 3), c = idx & 7;
-    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sbase + am_off(r, c)), "r"(0) : "memory");
-  }
 }
 
 // A-operand fragments of a 16-row tile over the 64-wide d axis (4 k-steps)
@@ -95,271 +76,8 @@ __device__ __forceinline__ void am_mma_tn(float (&out)[8][4], const uint32_t (&a
   }
 }
 
-__global__ void __launch_bounds__(AM_THREADS)
-attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int batch) {
-  pdl_sync();
-  extern __shared__ __align__(1024) uint8_t am_smem[];
-  const uint32_t sQ = am_smem_u32(am_smem), sK = sQ + AM_MAT_BYTES, sV = sK + AM_MAT_BYTES;
-  const int b = blockIdx.x / VITK_HEADS, h = blockIdx.x % VITK_HEADS;
-  const int64_t M = (int64_t)batch * AM_N;
-  const int64_t hm = ((int64_t)h * M + (int64_t)b * AM_N) * AM_D;
-  const int64_t hstride = (int64_t)VITK_HEADS * M * AM_D;
-  am_stage(sQ, qkv + hm, AM_D);
-  am_stage(sK, qkv + hm + hstride, AM_D);
-  am_stage(sV, qkv + hm + 2 * hstride, AM_D);
-  cp_async_wait_all();
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const float sl2 = AM_SCALE * AM_LOG2E;
-  for (int qt = warp; qt < AM_TILES; qt += AM_WARPS) {
-    uint32_t qf[4][4];
-    am_load_a_tile(sQ, qt * 16, lane, qf);
-    float s[26][4];
-#pragma unroll
-    for (int j = 0; j < 26; ++j) {
-      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      am_mma_nt(s[j], qf, sK, j * 8, lane);
-    }
-    // mask padded keys (>= 197) and take the row max (rows g and g+8)
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 26; ++j) {
-      const int key = j * 8 + 2 * t;
-      if (key >= AM_N) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-      if (key + 1 >= AM_N) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
-      m0 = fmaxf(m0, fmaxf(s[j][0], s[j][1]));
-      m1 = fmaxf(m1, fmaxf(s[j][2], s[j][3]));
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float l0 = 0.f, l1 = 0.f;
-    const float mb0 = m0 * sl2, mb1 = m1 * sl2;
-#pragma unroll
-    for (int j = 0; j < 26; ++j) {
-      s[j][0] = exp2f(fmaf(s[j][0], sl2, -mb0)); s[j][1] = exp2f(fmaf(s[j][1], sl2, -mb0));
-      s[j][2] = exp2f(fmaf(s[j][2], sl2, -mb1)); s[j][3] = exp2f(fmaf(s[j][3], sl2, -mb1));
-      l0 += s[j][0] + s[j][1];
-      l1 += s[j][2] + s[j][3];
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    // O = P V
-    float o[8][4];
-#pragma unroll
-    for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 13; ++kk) {
-      uint32_t a[4];
-      a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-      a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-      a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-      am_mma_tn(o, a, sV, kk * 16, lane);
-    }
-    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-    const int i0 = qt * 16 + g, i1 = i0 + 8;
-#pragma unroll
-    for (int dn = 0; dn < 8; ++dn) {
-      const int d = dn * 8 + 2 * t;
-      if (i0 < AM_N)
-        *reinterpret_cast<uint32_t*>(out + ((int64_t)b * AM_N + i0) * VITK_DIM + h * AM_D + d) = pack_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0);
-      if (i1 < AM_N)
-        *reinterpret_cast<uint32_t*>(out + ((int64_t)b * AM_N + i1) * VITK_DIM + h * AM_D + d) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
-    }
-    if (lse && t == 0) {
-      if (i0 < AM_N) lse[(int64_t)h * M + (int64_t)b * AM_N + i0] = m0 * AM_SCALE + logf(l0);
-      if (i1 < AM_N) lse[(int64_t)h * M + (int64_t)b * AM_N + i1] = m1 * AM_SCALE + logf(l1);
-    }
-  }
-}
-
-// Column sums of one 16 x 64 output tile held in mma accumulator layout (rows g / g+8, cols 8*dn + 2t, +1), of the
-// bf16-rounded scaled values actually stored, rows masked by validity: quad-stride shuffles over g, then lanes 0..3
-// add into the CTA's shared accumulator.  This is the qkv bias gradient, fused instead of re-reading dqkv.
-__device__ __forceinline__ void am_colsum_tile(float* cs, const float (&v)[8][4], float scale, bool valid0, bool valid1, int lane) {
-  const int t = lane & 3;
-#pragma unroll
-  for (int dn = 0; dn < 8; ++dn) {
-    const float2 lo = unpack_bf16x2(pack_bf16x2(v[dn][0] * scale, v[dn][1] * scale));
-    const float2 hi = unpack_bf16x2(pack_bf16x2(v[dn][2] * scale, v[dn][3] * scale));
-    float a = (valid0 ? lo.x : 0.f) + (valid1 ? hi.x : 0.f);
-    float b = (valid0 ? lo.y : 0.f) + (valid1 ? hi.y : 0.f);
-#pragma unroll
-    for (int o = 4; o < 32; o <<= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-    if (lane < 4) {
-      atomicAdd(cs + dn * 8 + 2 * t, a);
-      atomicAdd(cs + dn * 8 + 2 * t + 1, b);
-    }
-  }
-}
-
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(AM_THREADS, MIN_CTAS)
-attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
-                    const float* __restrict__ lse, bf16* __restrict__ dqkv, float* __restrict__ dqkv_colsum, int batch) {
-  pdl_sync();
-  extern __shared__ __align__(1024) uint8_t am_smem[];
-  const uint32_t sQ = am_smem_u32(am_smem), sK = sQ + AM_MAT_BYTES, sV = sK + AM_MAT_BYTES, sdO = sV + AM_MAT_BYTES;
-  float* Ls = reinterpret_cast<float*>(am_smem + 4 * AM_MAT_BYTES);  // lse * log2(e), padded rows 0
-  float* Ds = Ls + AM_NP;                                            // delta_i = dO_i . O_i
-  float* Cs = Ds + AM_NP;                                            // [3][64] column sums of dq, dk, dv (qkv bias grad)
-  if (threadIdx.x < 3 * AM_D) Cs[threadIdx.x] = 0.f;
-  const int b = blockIdx.x / VITK_HEADS, h = blockIdx.x % VITK_HEADS;
-  const int64_t M = (int64_t)batch * AM_N;
-  const int64_t hm = ((int64_t)h * M + (int64_t)b * AM_N) * AM_D;
-  const int64_t hstride = (int64_t)VITK_HEADS * M * AM_D;
-  const int64_t tok = ((int64_t)b * AM_N) * VITK_DIM + h * AM_D;
-  am_stage(sQ, qkv + hm, AM_D);
-  am_stage(sK, qkv + hm + hstride, AM_D);
-  am_stage(sV, qkv + hm + 2 * hstride, AM_D);
-  am_stage(sdO, dout + tok, VITK_DIM);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  // delta_i = dO_i . O_i : one thread per row, 16 independent 16-byte loads in flight per thread (a
-  // warp-per-row loop would serialise ~30 dependent global round trips per warp)
-  if (threadIdx.x < AM_NP) {
-    const int i = threadIdx.x;
-    float dl = 0.f, ls = 0.f;
-    if (i < AM_N) {
-      const uint4* ap = reinterpret_cast<const uint4*>(dout + tok + (int64_t)i * VITK_DIM);
-      const uint4* op = reinterpret_cast<const uint4*>(out + tok + (int64_t)i * VITK_DIM);
-      uint4 av[8], ov[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { av[c] = ap[c]; ov[c] = op[c]; }
-      ls = lse[(int64_t)h * M + (int64_t)b * AM_N + i] * AM_LOG2E;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float2 a0 = unpack_bf16x2(av[c].x), a1 = unpack_bf16x2(av[c].y), a2 = unpack_bf16x2(av[c].z), a3 = unpack_bf16x2(av[c].w);
-        const float2 o0 = unpack_bf16x2(ov[c].x), o1 = unpack_bf16x2(ov[c].y), o2 = unpack_bf16x2(ov[c].z), o3 = unpack_bf16x2(ov[c].w);
-        dl += a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
-      }
-    }
-    Ds[i] = dl;
-    Ls[i] = ls;
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  const float sl2 = AM_SCALE * AM_LOG2E;
-
-  // ---------------- phase A: dQ for 16 query rows per warp iteration ----------------
-  for (int qt = warp; qt < AM_TILES; qt += AM_WARPS) {
-    uint32_t qf[4][4], dof[4][4];
-    am_load_a_tile(sQ, qt * 16, lane, qf);
-    am_load_a_tile(sdO, qt * 16, lane, dof);
-    const float L0 = Ls[qt * 16 + g], L1 = Ls[qt * 16 + g + 8];
-    const float D0 = Ds[qt * 16 + g], D1 = Ds[qt * 16 + g + 8];
-    float dq[8][4];
-#pragma unroll
-    for (int dn = 0; dn < 8; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
-#pragma unroll 1
-    for (int kb = 0; kb < AM_TILES; ++kb) {
-      float s[2][4], dp[2][4];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
-        am_mma_nt(s[nt], qf, sK, kb * 16 + nt * 8, lane);
-        am_mma_nt(dp[nt], dof, sV, kb * 16 + nt * 8, lane);
-      }
-      uint32_t a[4];
-      float ds[2][4];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        ds[nt][0] = exp2f(fmaf(s[nt][0], sl2, -L0)) * (dp[nt][0] - D0);
-        ds[nt][1] = exp2f(fmaf(s[nt][1], sl2, -L0)) * (dp[nt][1] - D0);
-        ds[nt][2] = exp2f(fmaf(s[nt][2], sl2, -L1)) * (dp[nt][2] - D1);
-        ds[nt][3] = exp2f(fmaf(s[nt][3], sl2, -L1)) * (dp[nt][3] - D1);
-      }
-      a[0] = pack_bf16x2(ds[0][0], ds[0][1]); a[1] = pack_bf16x2(ds[0][2], ds[0][3]);
-      a[2] = pack_bf16x2(ds[1][0], ds[1][1]); a[3] = pack_bf16x2(ds[1][2], ds[1][3]);
-      am_mma_tn(dq, a, sK, kb * 16, lane);   // padded key rows of K are zero -> no masking needed
-    }
-    const int i0 = qt * 16 + g, i1 = i0 + 8;
-#pragma unroll
-    for (int dn = 0; dn < 8; ++dn) {
-      const int d = dn * 8 + 2 * t;
-      if (i0 < AM_N) *reinterpret_cast<uint32_t*>(dqkv + hm + (int64_t)i0 * AM_D + d) = pack_bf16x2(dq[dn][0] * AM_SCALE, dq[dn][1] * AM_SCALE);
-      if (i1 < AM_N) *reinterpret_cast<uint32_t*>(dqkv + hm + (int64_t)i1 * AM_D + d) = pack_bf16x2(dq[dn][2] * AM_SCALE, dq[dn][3] * AM_SCALE);
-    }
-    if (dqkv_colsum) am_colsum_tile(Cs, dq, AM_SCALE, i0 < AM_N, i1 < AM_N, lane);
-  }
-
-  // ---------------- phase B: dK, dV for 16 key rows per warp iteration ----------------
-  for (int kt = warp; kt < AM_TILES; kt += AM_WARPS) {
-    uint32_t kf[4][4], vf[4][4];
-    am_load_a_tile(sK, kt * 16, lane, kf);
-    am_load_a_tile(sV, kt * 16, lane, vf);
-    float dk[8][4], dv[8][4];
-#pragma unroll
-    for (int dn = 0; dn < 8; ++dn) {
-      dk[dn][0] = dk[dn][1] = dk[dn][2] = dk[dn][3] = 0.f;
-      dv[dn][0] = dv[dn][1] = dv[dn][2] = dv[dn][3] = 0.f;
-    }
-#pragma unroll 1
-    for (int qb = 0; qb < AM_TILES; ++qb) {
-      float st[2][4], dpt[2][4];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        st[nt][0] = st[nt][1] = st[nt][2] = st[nt][3] = 0.f;
-        dpt[nt][0] = dpt[nt][1] = dpt[nt][2] = dpt[nt][3] = 0.f;
-        am_mma_nt(st[nt], kf, sQ, qb * 16 + nt * 8, lane);    // S^T tile: rows = keys, cols = queries
-        am_mma_nt(dpt[nt], vf, sdO, qb * 16 + nt * 8, lane);  // dP^T tile
-      }
-      uint32_t ap[4], ads[4];
-      float p[2][4], ds[2][4];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int q0 = qb * 16 + nt * 8 + 2 * t;
-        const float La = Ls[q0], Lb = Ls[q0 + 1], Da = Ds[q0], Db = Ds[q0 + 1];
-        p[nt][0] = exp2f(fmaf(st[nt][0], sl2, -La)); p[nt][1] = exp2f(fmaf(st[nt][1], sl2, -Lb));
-        p[nt][2] = exp2f(fmaf(st[nt][2], sl2, -La)); p[nt][3] = exp2f(fmaf(st[nt][3], sl2, -Lb));
-        ds[nt][0] = p[nt][0] * (dpt[nt][0] - Da); ds[nt][1] = p[nt][1] * (dpt[nt][1] - Db);
-        ds[nt][2] = p[nt][2] * (dpt[nt][2] - Da); ds[nt][3] = p[nt][3] * (dpt[nt][3] - Db);
-      }
-      ap[0] = pack_bf16x2(p[0][0], p[0][1]); ap[1] = pack_bf16x2(p[0][2], p[0][3]);
-      ap[2] = pack_bf16x2(p[1][0], p[1][1]); ap[3] = pack_bf16x2(p[1][2], p[1][3]);
-      ads[0] = pack_bf16x2(ds[0][0], ds[0][1]); ads[1] = pack_bf16x2(ds[0][2], ds[0][3]);
-      ads[2] = pack_bf16x2(ds[1][0], ds[1][1]); ads[3] = pack_bf16x2(ds[1][2], ds[1][3]);
-      am_mma_tn(dv, ap, sdO, qb * 16, lane);   // padded query rows of dO / Q are zero -> no masking needed
-      am_mma_tn(dk, ads, sQ, qb * 16, lane);
-    }
-    const int j0 = kt * 16 + g, j1 = j0 + 8;
-    bf16* dkg = dqkv + hm + hstride;
-    bf16* dvg = dqkv + hm + 2 * hstride;
-#pragma unroll
-    for (int dn = 0; dn < 8; ++dn) {
-      const int d = dn * 8 + 2 * t;
-      if (j0 < AM_N) {
-        *reinterpret_cast<uint32_t*>(dkg + (int64_t)j0 * AM_D + d) = pack_bf16x2(dk[dn][0] * AM_SCALE, dk[dn][1] * AM_SCALE);
-        *reinterpret_cast<uint32_t*>(dvg + (int64_t)j0 * AM_D + d) = pack_bf16x2(dv[dn][0], dv[dn][1]);
-      }
-      if (j1 < AM_N) {
-        *reinterpret_cast<uint32_t*>(dkg + (int64_t)j1 * AM_D + d) = pack_bf16x2(dk[dn][2] * AM_SCALE, dk[dn][3] * AM_SCALE);
-        *reinterpret_cast<uint32_t*>(dvg + (int64_t)j1 * AM_D + d) = pack_bf16x2(dv[dn][2], dv[dn][3]);
-      }
-    }
-    if (dqkv_colsum) {
-      am_colsum_tile(Cs + AM_D, dk, AM_SCALE, j0 < AM_N, j1 < AM_N, lane);
-      am_colsum_tile(Cs + 2 * AM_D, dv, 1.0f, j0 < AM_N, j1 < AM_N, lane);
-    }
-  }
-  if (dqkv_colsum) {
-    __syncthreads();
-    if (threadIdx.x < 3 * AM_D) {
-      const int sec = threadIdx.x / AM_D, d = threadIdx.x % AM_D;
-      atomicAdd(dqkv_colsum + (sec * VITK_HEADS + h) * AM_D + d, Cs[threadIdx.x]);
-    }
-  }
-}
-
-
 // ================================================================================================
-// v2 kernels: persistent CTAs (one per SM), 13 warps = one 16-row tile per warp, operands of the NEXT
+// persistent CTAs (one per SM), 13 warps = one 16-row tile per warp, operands of the NEXT
 // (batch, head) item prefetched with cp.async while the current one computes.
 //
 //   forward : Q/K/V double-buffered (2 x 78 KB).  Each warp: S = Q K^T in two key blocks (96 + 112 keys)
@@ -687,52 +405,38 @@ attn_bwd_mma2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
   }
 }
 
-constexpr size_t AM_FWD_SMEM = 3 * AM_MAT_BYTES;
-constexpr size_t AM_BWD_SMEM = 4 * AM_MAT_BYTES + (2 * AM_NP + 3 * AM_D) * sizeof(float);
-
 int colsum_headmajor(const void* x, int dtype, int M, int C, float* db, cudaStream_t st);
-
 int attn_fwd_tc(const void* qkv, void* out, float* lse, int batch, cudaStream_t st);
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch, cudaStream_t st);
 
+// vitk_debug_set(3, 0): tcgen05 kernels (attention_tc.cu, default); (3, 1): the mma.sync kernels of this file
 int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t st) {
-  if (attn_debug_variant() == 0) return attn_fwd_tc(qkv, out, lse, batch, st);   // default: tcgen05 kernel (attention_tc.cu)
+  if (attn_debug_variant() == 0) return attn_fwd_tc(qkv, out, lse, batch, st);
   static bool configured = false;
   if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AM_FWD_SMEM));
     VITK_CUDA(cudaFuncSetAttribute(attn_fwd_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_FWD_SMEM));
     configured = true;
   }
-  if (attn_debug_variant() == 2) {   // debug knob 3 == 2: the first-generation kernel (one CTA per item)
-    VITK_LAUNCH((attn_fwd_mma_kernel), batch * VITK_HEADS, AM_THREADS, AM_FWD_SMEM, st, (const bf16*)qkv, (bf16*)out, lse, batch);
-  } else {
-    const int items = batch * VITK_HEADS, sms = sm_count();
-    VITK_LAUNCH((attn_fwd_mma2_kernel), (items < sms ? items : sms), A2_THREADS, A2_FWD_SMEM, st, (const bf16*)qkv, (bf16*)out, lse, batch, items);
-  }
+  const int items = batch * VITK_HEADS, sms = sm_count();
+  VITK_LAUNCH((attn_fwd_mma2_kernel), (items < sms ? items : sms), A2_THREADS, A2_FWD_SMEM, st, (const bf16*)qkv, (bf16*)out, lse, batch, items);
   return VITK_OK;
 }
 
-int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch, cudaStream_t st);
-
 int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum,
                  int batch, cudaStream_t st) {
-  if (attn_debug_variant() == 0) {   // default: tcgen05 kernel (attention_tc.cu)
+  if (attn_debug_variant() == 0) {
     VITK_TRY(attn_bwd_tc(qkv, out, dout, lse, dqkv, batch, st));
-    if (dqkv_colsum) VITK_TRY(colsum_headmajor(dqkv, VITK_BF16, batch * VITK_NTOK, 3 * VITK_DIM, dqkv_colsum, st));
-    return VITK_OK;
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      VITK_CUDA(cudaFuncSetAttribute(attn_bwd_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_BWD_SMEM));
+      configured = true;
+    }
+    const int items = batch * VITK_HEADS, sms = sm_count();
+    VITK_LAUNCH((attn_bwd_mma2_kernel), (items < sms ? items : sms), A2_THREADS, A2_BWD_SMEM, st, (const bf16*)qkv, (const bf16*)out,
+                (const bf16*)dout, lse, (bf16*)dqkv, batch, items);
   }
-  static bool configured = false;
-  if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AM_BWD_SMEM));
-    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_BWD_SMEM));
-    configured = true;
-  }
-  if (attn_debug_variant() == 2) {
-    VITK_LAUNCH((attn_bwd_mma_kernel<1>), batch * VITK_HEADS, AM_THREADS, AM_BWD_SMEM, st, (const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, dqkv_colsum, batch);
-    return VITK_OK;
-  }
-  const int items = batch * VITK_HEADS, sms = sm_count();
-  VITK_LAUNCH((attn_bwd_mma2_kernel), (items < sms ? items : sms), A2_THREADS, A2_BWD_SMEM, st, (const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, batch, items);
-  // the qkv bias gradient: a stand-alone coalesced column-sum pass (fusing it into the mma.sync kernel measured slower)
+  // the qkv bias gradient: a stand-alone coalesced column-sum pass
   if (dqkv_colsum) VITK_TRY(colsum_headmajor(dqkv, VITK_BF16, batch * VITK_NTOK, 3 * VITK_DIM, dqkv_colsum, st));
   return VITK_OK;
 }

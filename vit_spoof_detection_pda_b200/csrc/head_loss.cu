@@ -12,8 +12,8 @@ namespace vitk {
 constexpr int HD_IN = VITK_DIM;           // 768
 constexpr int HD_HID = VITK_HEAD_HIDDEN;  // 512
 constexpr int HD_THREADS = 512;
-// per-sample save area (floats): xhat | y | z1 | dz1 | dym | rstd(+pad)
-constexpr int HS_XHAT = 0, HS_Y = 768, HS_Z1 = 1536, HS_DZ1 = 2048, HS_DYM = 2560, HS_RSTD = 3328, HS_TOTAL = 3392;
+// per-sample save area (floats): xhat | y | z1 | dz1 | dym | rstd, ticket (+pad) | dy accumulator of the split backward
+constexpr int HS_XHAT = 0, HS_Y = 768, HS_Z1 = 1536, HS_DZ1 = 2048, HS_DYM = 2560, HS_RSTD = 3328, HS_ACC = 3392, HS_TOTAL = 4160;
 constexpr float HD_EPS = 1e-5f;
 
 __device__ __forceinline__ float block_sum_512(float v, float* red) {
@@ -52,7 +52,9 @@ head_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ ln_w, 
     ys[k] = y;
     if (sv) { sv[HS_XHAT + k] = xh; sv[HS_Y + k] = y; }
   }
-  if (sv && tid == 0) sv[HS_RSTD] = rstd;
+  if (sv && tid == 0) { sv[HS_RSTD] = rstd; sv[HS_RSTD + 1] = 0.f; }   // +1: arrival ticket of the split backward
+  if (sv)
+    for (int k = tid; k < HD_IN; k += HD_THREADS) sv[HS_ACC + k] = 0.f;   // accumulated by the backward's 4 CTAs per sample
   __syncthreads();
   // 768 -> 512 mat-vec: every warp owns 32 consecutive hidden units; the LN output lives in registers (6 float4 per
   // lane) and two weight rows (12 independent 16-byte loads per lane) are in flight at a time -- the kernel is
@@ -95,26 +97,51 @@ head_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ ln_w, 
   }
 }
 
-// per-sample backward to the feature; leaves dz1 and dym in the save area for the parameter-grad kernel
+// per-sample backward to the feature; leaves dz1 and dym in the save area for the parameter-grad kernel.
+// The 512 x 768 weight read per sample is the whole cost (latency-bound): HB_SPLIT CTAs per sample each take a quarter
+// of the hidden units, add their partial dy into the save area, and the last one to arrive (ticket) finishes the
+// LayerNorm backward.  (head_fwd zeroes the accumulator and the ticket.)
+constexpr int HB_SPLIT = 4;
+constexpr int HB_T = HD_HID / HB_SPLIT;   // 128 hidden units per CTA
+
 __global__ void __launch_bounds__(HD_THREADS)
-head_bwd_data_kernel(const float* __restrict__ dlogits, float* __restrict__ save, const float* __restrict__ ln_w,
+head_bwd_data_kernel(const float* __restrict__ dlogits, float* save, const float* __restrict__ ln_w,
                      const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ mask1,
                      const float* __restrict__ mask2, float* __restrict__ dfeat, int num_classes) {
   pdl_sync();
-  __shared__ float dz[HD_HID];
+  __shared__ float dz[HB_T];
   __shared__ float red[HD_THREADS / 32];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ int is_last;
+  const int b = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
   float* sv = save + (int64_t)b * HS_TOTAL;
-  {
-    const int t = tid;  // 512 threads == 512 hidden units
+  if (tid < HB_T) {
+    const int t = q * HB_T + tid;
     float da = 0.f;
     for (int c = 0; c < num_classes; ++c) da = fmaf(dlogits[(int64_t)b * num_classes + c], w2[(int64_t)c * HD_HID + t], da);
     if (mask2) da *= mask2[(int64_t)b * HD_HID + t];
     const float v = da * gelu_erf_grad(sv[HS_Z1 + t]);
-    dz[t] = v;
+    dz[tid] = v;
     sv[HS_DZ1 + t] = v;
   }
   __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = tid + e * HD_THREADS;
+    if (k < HD_IN) {
+      float dy = 0.f;
+      const float* wc = w1 + (int64_t)(q * HB_T) * HD_IN + k;
+#pragma unroll 16
+      for (int t = 0; t < HB_T; ++t) dy = fmaf(dz[t], __ldg(wc + (int64_t)t * HD_IN), dy);   // 16 loads in flight
+      atomicAdd(sv + HS_ACC + k, dy);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(reinterpret_cast<int*>(sv + HS_RSTD + 1), 1) == HB_SPLIT - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid == 0) sv[HS_RSTD + 1] = 0.f;        // ticket back to zero
   float dxh[2], xh[2];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -122,9 +149,8 @@ head_bwd_data_kernel(const float* __restrict__ dlogits, float* __restrict__ save
     const int k = tid + e * HD_THREADS;
     dxh[e] = 0.f; xh[e] = 0.f;
     if (k < HD_IN) {
-      float dy = 0.f;
-#pragma unroll 16
-      for (int t = 0; t < HD_HID; ++t) dy = fmaf(dz[t], __ldg(w1 + (int64_t)t * HD_IN + k), dy);   // 16 loads in flight
+      float dy = __ldcg(sv + HS_ACC + k);      // complete sum (L2: the other CTAs' atomics)
+      sv[HS_ACC + k] = 0.f;                    // self-cleaning: a second backward of the same forward starts from zero
       if (mask1) dy *= mask1[(int64_t)b * HD_IN + k];
       sv[HS_DYM + k] = dy;
       xh[e] = sv[HS_XHAT + k];
@@ -143,7 +169,11 @@ head_bwd_data_kernel(const float* __restrict__ dlogits, float* __restrict__ save
   }
 }
 
-// parameter gradients: blockIdx.x in [0,512) -> row t of dw1 (+ db1[t]); 512 -> dln; 513.. -> dw2/db2 class rows
+// parameter gradients: blockIdx.x in [0,64) -> 8 rows t of dw1 (+ db1) per CTA, so the saved activations of the batch
+// are read 64 times instead of 512; 64 -> dln; 65.. -> dw2/db2 class rows
+constexpr int HP_ROWS = 8;
+constexpr int HP_BLOCKS = HD_HID / HP_ROWS;   // 64
+
 __global__ void __launch_bounds__(256)
 head_bwd_param_kernel(const float* __restrict__ dlogits, const float* __restrict__ save, const float* __restrict__ mask2,
                       float* __restrict__ dln_w, float* __restrict__ dln_b, float* __restrict__ dw1,
@@ -151,22 +181,33 @@ head_bwd_param_kernel(const float* __restrict__ dlogits, const float* __restrict
                       int num_classes) {
   pdl_sync();
   const int blk = blockIdx.x, tid = threadIdx.x;
-  if (blk < HD_HID) {
-    const int t = blk;
-    float acc[3] = {0.f, 0.f, 0.f};
-    float sb = 0.f;
-#pragma unroll 8
+  if (blk < HP_BLOCKS) {
+    const int t0 = blk * HP_ROWS;
+    float acc[HP_ROWS][3], sb[HP_ROWS];
+#pragma unroll
+    for (int r = 0; r < HP_ROWS; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = 0.f; sb[r] = 0.f; }
+#pragma unroll 4
     for (int b = 0; b < batch; ++b) {
       const float* sv = save + (int64_t)b * HS_TOTAL;
-      const float d = sv[HS_DZ1 + t];
-      sb += d;
+      const float4 d0 = *reinterpret_cast<const float4*>(sv + HS_DZ1 + t0);
+      const float4 d1 = *reinterpret_cast<const float4*>(sv + HS_DZ1 + t0 + 4);
+      const float d[HP_ROWS] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      const float y0 = sv[HS_Y + tid], y1 = sv[HS_Y + tid + 256], y2 = sv[HS_Y + tid + 512];
 #pragma unroll
-      for (int e = 0; e < 3; ++e) acc[e] = fmaf(d, sv[HS_Y + tid + e * 256], acc[e]);
+      for (int r = 0; r < HP_ROWS; ++r) {
+        sb[r] += d[r];
+        acc[r][0] = fmaf(d[r], y0, acc[r][0]);
+        acc[r][1] = fmaf(d[r], y1, acc[r][1]);
+        acc[r][2] = fmaf(d[r], y2, acc[r][2]);
+      }
     }
 #pragma unroll
-    for (int e = 0; e < 3; ++e) dw1[(int64_t)t * HD_IN + tid + e * 256] += acc[e];
-    if (tid == 0) db1[t] += sb;
-  } else if (blk == HD_HID) {
+    for (int r = 0; r < HP_ROWS; ++r) {
+#pragma unroll
+      for (int e = 0; e < 3; ++e) dw1[(int64_t)(t0 + r) * HD_IN + tid + e * 256] += acc[r][e];
+      if (tid == 0) db1[t0 + r] += sb[r];
+    }
+  } else if (blk == HP_BLOCKS) {
     for (int k = tid; k < HD_IN; k += 256) {
       float g = 0.f, bb = 0.f;
 #pragma unroll 8
@@ -180,7 +221,7 @@ head_bwd_param_kernel(const float* __restrict__ dlogits, const float* __restrict
       dln_b[k] += bb;
     }
   } else {
-    const int c = blk - HD_HID - 1;
+    const int c = blk - HP_BLOCKS - 1;
     float sb = 0.f;
     for (int t = tid; t < HD_HID; t += 256) {
       float a = 0.f;
@@ -287,10 +328,10 @@ extern "C" int vitk_head_bwd(const float* dlogits, float* save, const float* ln_
                              float* dw1, float* db1, float* dw2, float* db2, int batch, int num_classes, void* stream) {
   VITK_CHECK_ARG(dlogits && save && ln_w && w1 && w2 && dfeat && batch > 0 && num_classes > 0);
   cudaStream_t st = (cudaStream_t)stream;
-  VITK_LAUNCH((head_bwd_data_kernel), batch, HD_THREADS, 0, st, dlogits, save, ln_w, w1, w2, mask1, mask2, dfeat, num_classes);
+  VITK_LAUNCH((head_bwd_data_kernel), dim3(batch, HB_SPLIT), HD_THREADS, 0, st, dlogits, save, ln_w, w1, w2, mask1, mask2, dfeat, num_classes);
   if (dw1) {
     VITK_CHECK_ARG(dln_w && dln_b && db1 && dw2 && db2);
-    VITK_LAUNCH((head_bwd_param_kernel), HD_HID + 1 + num_classes, 256, 0, st, dlogits, save, mask2, dln_w, dln_b, dw1, db1, dw2, db2, batch, num_classes);
+    VITK_LAUNCH((head_bwd_param_kernel), HP_BLOCKS + 1 + num_classes, 256, 0, st, dlogits, save, mask2, dln_w, dln_b, dw1, db1, dw2, db2, batch, num_classes);
   }
   return VITK_OK;
 }
