@@ -344,6 +344,31 @@ def run_ours(args):
                 e1.record(); torch.cuda.synchronize()
                 extra["bs256_infer_img_s"] = 256 * 5 / (e0.elapsed_time(e1) / 1e3)
             model.train()
+            # ---- BASELINE configs[3]: frozen backbone (forward-only encoder + head backward + Adam on the head), batch 256
+            fm = pkg.ViTFaceAntiSpoofing(dropout=0.1, depth=12, precision="bf16").to(dev)
+            fm.load_state_dict(model.state_dict())
+            for prm in fm.vit.parameters():
+                prm.requires_grad_(False)
+            fm.train()
+            fopt = pkg.FusedAdam(fm.parameters(), lr=1e-5, weight_decay=1e-4, adamw=False)
+            y256 = torch.randint(0, 2, (256,), device=dev)
+
+            def fstep():
+                floss = crit(fm(x256), y256)
+                floss.backward()
+                pkg.clip_grad_norm_(fm.parameters(), 1.0)
+                fopt.step()
+                fopt.zero_grad(set_to_none=True)
+
+            for _ in range(2):
+                fstep()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fstep()
+            e1.record(); torch.cuda.synchronize()
+            extra["frozen_backbone_bs256_img_s"] = 256 * 5 / (e0.elapsed_time(e1) / 1e3)
+            del fm, fopt
         except Exception as e:  # noqa: BLE001 -- extras never invalidate the headline line
             extra["eval_extra_error"] = repr(e)
 
