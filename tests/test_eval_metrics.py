@@ -101,3 +101,24 @@ def test_uint8_hwc_input_edge_equals_normalised_float_input(precision):
     assert torch.equal(a, b)
     tol = 1e-4 if precision == "fp32" else 2e-2
     assert float((a.cpu() - o).abs().max()) <= tol * max(1.0, float(o.abs().max()))
+
+
+@pytest.mark.gpu
+def test_host_scalars_deliver_every_value_one_step_late():
+    """pkg.HostScalars (the asynchronous stand-in for loss.item() / acc.item(), train_advanced.py:345-346) hands over
+    exactly the pushed values, in order, one push late, and flush() returns the last ones."""
+    import vit_spoof_detection_pda_b200 as pkg
+    dev = torch.device("cuda:0")
+    reader = pkg.HostScalars(dev, slots=3)
+    got = []
+    vals = [(float(i) * 0.25 + 1e-3, float(7 * i)) for i in range(8)]
+    for a, b in vals:
+        ta, tb = torch.tensor(a, device=dev, dtype=torch.float32), torch.tensor(int(b), device=dev, dtype=torch.int32)
+        prev = reader.push(ta, tb)
+        if prev is not None:
+            got.append(prev)
+    got.append(reader.flush())
+    assert reader.flush() is None
+    assert len(got) == len(vals)
+    for (a, b), (ga, gb) in zip(vals, got):
+        assert ga == float(torch.tensor(a, dtype=torch.float32)) and gb == b
