@@ -46,7 +46,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples SM clock / throttle reasons of one GPU every 100 ms while running (pynvml)."""
+    """Samples SM clock / throttle reasons of one GPU every 10 ms while running (pynvml)."""
 
     def __init__(self, index: int):
         self.index = index
@@ -75,7 +75,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv is not None:
