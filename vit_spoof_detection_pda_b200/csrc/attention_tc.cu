@@ -149,8 +149,11 @@ __device__ __forceinline__ float ex2(float x) {
 // row-per-thread stores measured ~17 us of a 92 us backward launch).
 //   stg: this warp's 2 KB staging tile; row_ptr(r): global address of column 0 of this 32-column slab in row r, or
 //   nullptr when row r must not be written.
+//   colsum (optional): += column sums of the bf16 values of the rows that are written (the qkv bias gradient): lane = column,
+//   32 conflict-free 2-byte reads of the staged tile, one atomic per lane.
 template <typename RowPtr>
-__device__ __forceinline__ void store_slab32(uint32_t stg, int lane, const uint32_t (&o)[32], float scale, RowPtr row_ptr) {
+__device__ __forceinline__ void store_slab32(uint32_t stg, int lane, const uint32_t (&o)[32], float scale, RowPtr row_ptr,
+                                             float* colsum = nullptr) {
 #pragma unroll
   for (int k4 = 0; k4 < 4; ++k4) {
     const uint32_t a = stg + (uint32_t)(lane * 64 + ((k4 ^ ((lane >> 1) & 3)) << 4));
@@ -161,6 +164,16 @@ __device__ __forceinline__ void store_slab32(uint32_t stg, int lane, const uint3
                  "r"(pack_bf16x2(__uint_as_float(o[8 * k4 + 6]) * scale, __uint_as_float(o[8 * k4 + 7]) * scale)) : "memory");
   }
   __syncwarp();
+  if (colsum) {
+    float cs = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      uint16_t h;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(stg + (uint32_t)(r * 64 + (((lane >> 3) ^ ((r >> 1) & 3)) << 4) + (lane & 7) * 2)));
+      if (row_ptr(r) != nullptr) cs += __uint_as_float((uint32_t)h << 16);
+    }
+    atomicAdd(colsum + lane, cs);
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = i * 8 + (lane >> 2), k4 = lane & 3;
@@ -466,7 +479,7 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t lbo) { r
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
                    const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ out, const float* __restrict__ lse,
-                   bf16* __restrict__ dqkv, int batch, int n_items, int dbg) {
+                   bf16* __restrict__ dqkv, float* __restrict__ dqkv_colsum, int batch, int n_items, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -761,14 +774,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
       if (lane == 0) mbar_arrive(delta_ready(c));     // release: the stores above are visible to the waiting softmax warps
     };
     // one 128-row x 64-column fp32 accumulator tile (TMEM column `col`) -> bf16 rows of `dst` (row stride 64), rows < n_valid
-    auto drain_tile = [&](uint32_t col, bf16* dst, int row0, float scale) {
+    // cs: this (section, head)'s 64 entries of the qkv bias gradient, or nullptr
+    auto drain_tile = [&](uint32_t col, bf16* dst, int row0, float scale, float* cs) {
+      if (row0 + qr * 32 >= N_TOK) return;      // none of this warp's rows exists
 #pragma unroll
       for (int half = 0; half < 2 && !(dbg & 4); ++half) {
         uint32_t o[32];
         tm_ld32(lane_addr + col + half * 32, o);
         tm_ld_wait();
         store_slab32(stg, lane, o, scale,
-                     [&](int r) -> bf16* { return (row0 + qr * 32 + r < N_TOK) ? dst + (int64_t)(row0 + qr * 32 + r) * 64 + half * 32 : nullptr; });
+                     [&](int r) -> bf16* { return (row0 + qr * 32 + r < N_TOK) ? dst + (int64_t)(row0 + qr * 32 + r) * 64 + half * 32 : nullptr; },
+                     cs ? cs + half * 32 : nullptr);
       }
     };
     if (n_my > 0)
@@ -783,8 +799,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
         // ---- dV_t, dK_t (lane = key)
         mbar_wait(dvk_full, (it * 2 + t) & 1);
         tc_fence_after();
-        drain_tile(T_DV, dqkv + hm + 2 * hstride, t * 128, 1.0f);
-        drain_tile(T_DK, dqkv + hm + hstride, t * 128, SCALE);
+        float* csb = dqkv_colsum ? dqkv_colsum + h * 64 : nullptr;      // [3][12][64]: q | k | v sections
+        drain_tile(T_DV, dqkv + hm + 2 * hstride, t * 128, 1.0f, csb ? csb + 2 * VITK_DIM : nullptr);
+        drain_tile(T_DK, dqkv + hm + hstride, t * 128, SCALE, csb ? csb + VITK_DIM : nullptr);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dvk_free);
@@ -795,8 +812,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
       // ---- dQ (lane = query), two 128-query tiles
       mbar_wait(dq_full, ipar);
       tc_fence_after();
-      drain_tile(T_DQ, dqkv + hm, 0, SCALE);
-      drain_tile(T_DQ + 64, dqkv + hm, 128, SCALE);
+      drain_tile(T_DQ, dqkv + hm, 0, SCALE, dqkv_colsum ? dqkv_colsum + h * 64 : nullptr);
+      drain_tile(T_DQ + 64, dqkv + hm, 128, SCALE, dqkv_colsum ? dqkv_colsum + h * 64 : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
@@ -851,7 +868,8 @@ int attn_fwd_tc(const void* qkv, void* out, float* lse, int batch, cudaStream_t 
   return VITK_OK;
 }
 
-int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch, cudaStream_t st) {
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum, int batch,
+                cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     VITK_CUDA(cudaFuncSetAttribute(atc::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atc::BWD_SMEM));
@@ -864,7 +882,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   VITK_TRY(atc::make_dout_map(dout, M, &map_do));
   const int items = batch * VITK_HEADS, sms = sm_count();
   VITK_LAUNCH((atc::attn_bwd_tc_kernel), (items < sms ? items : sms), atc::BWD_THREADS, atc::BWD_SMEM, st, map_kv, map_q, map_do,
-              (const bf16*)out, lse, (bf16*)dqkv, batch, items, debug_knob(7));
+              (const bf16*)out, lse, (bf16*)dqkv, dqkv_colsum, batch, items, debug_knob(7));
   return VITK_OK;
 }
 

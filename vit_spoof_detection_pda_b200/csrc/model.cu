@@ -349,11 +349,10 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   VITK_TRY(vitk_linear_wgrad(dxa, VITK_LAYOUT_ROWMAJOR, ao, c.G(b.projw), nullptr, M, D, D, dt, eng, wst));
   if (ss) VITK_CUDA(cudaEventRecord(ss->ev[4], ss->s));                  // proj wgrad has read dx16
   VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.projw), dh, nullptr, nullptr, M, D, D, dt, eng, st));
-  // (the qkv bias gradient stays a separate coalesced column-sum pass inside wgrad: fusing it into the mma.sync
-  //  attention kernel measured +48 us per layer against 16 us for the stand-alone reduction)
-  VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, nullptr, m->batch, dt, c.st));
+  // the qkv bias gradient (column sums of dqkv) comes out of the attention backward's epilogue warps
+  VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, c.G(b.qkvb), m->batch, dt, c.st));
   VITK_TRY(after(5, ms, ss ? ss->s : ms));   // dqkv ready
-  VITK_TRY(vitk_linear_wgrad(dqkv, VITK_LAYOUT_HEADMAJOR, ln1, c.G(b.qkvw), c.G(b.qkvb), M, 3 * D, D, dt, eng, wst));
+  VITK_TRY(vitk_linear_wgrad(dqkv, VITK_LAYOUT_HEADMAJOR, ln1, c.G(b.qkvw), nullptr, M, 3 * D, D, dt, eng, wst));
   VITK_TRY(vitk_linear_dgrad(dqkv, VITK_LAYOUT_HEADMAJOR, c.W(b.qkvw), dh, nullptr, nullptr, M, 3 * D, D, dt, eng, st));
   if (ss) VITK_CUDA(cudaStreamWaitEvent(ms, ss->ev[4], 0));              // the LayerNorm backward overwrites dx16
   VITK_TRY(vitk_layernorm_bwd(dh, dt, x, D, c.P(b.n1w), (float*)c.at(pl.mean1, pl.stat_stride, l),
