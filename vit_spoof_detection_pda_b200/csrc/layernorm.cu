@@ -8,6 +8,8 @@
 
 namespace vitk {
 
+int debug_knob(int key);
+
 constexpr int LN_COLS = VITK_DIM;        // 768
 constexpr int LN_VEC = LN_COLS / 128;    // 6 float4 per lane
 constexpr int LN_WARPS = 8;
@@ -31,21 +33,19 @@ template <> struct Vec4IO<bf16> {
   }
 };
 
+// One warp normalises one row held in registers (6 float4 per lane).  Persistent: the grid is a fixed number of CTAs per
+// SM (8 = full occupancy) and every warp walks rows with a stride of the total warp count, TWO rows per iteration: 12,608
+// rows on 148 x 64 resident warps are 1.33 rows per warp, so every warp finishes in one iteration with 6 or 12 independent
+// 16-byte loads per lane in flight, instead of a half-empty second wave of CTAs.
 template <typename T>
-__global__ void __launch_bounds__(LN_WARPS * 32)
-ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ gamma,
-              const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, int rows, float eps) {
-  pdl_sync();
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float* xr = x + (int64_t)row * x_stride;
+__device__ __forceinline__ void ln_row(const float4 (&v_in)[LN_VEC], int lane, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, T* __restrict__ yr, float* __restrict__ mean_out,
+                                       float* __restrict__ rstd_out, int row, float eps) {
   float4 v[LN_VEC];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < LN_VEC; ++i) {
-    v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    v[i] = v_in[i];
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mean = warp_sum(s) * (1.0f / LN_COLS);
@@ -57,12 +57,11 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __rest
   }
   const float var = warp_sum(q) * (1.0f / LN_COLS);
   const float rstd = 1.0f / sqrtf(var + eps);
-  T* yr = y + (int64_t)row * LN_COLS;
 #pragma unroll
   for (int i = 0; i < LN_VEC; ++i) {
     const int c = (i * 32 + lane) * 4;
-    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
-    const float4 b = *reinterpret_cast<const float4*>(beta + c);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
     float4 o;
     o.x = v[i].x * rstd * g.x + b.x;
     o.y = v[i].y * rstd * g.y + b.y;
@@ -73,6 +72,30 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __rest
   if (lane == 0 && mean_out) {
     mean_out[row] = mean;
     rstd_out[row] = rstd;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ gamma,
+              const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, int rows, float eps) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const int nw = gridDim.x * LN_WARPS;
+  for (int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < rows; row += 2 * nw) {
+    const int row2 = row + nw;
+    const float* xr = x + (int64_t)row * x_stride;
+    const float* xr2 = x + (int64_t)row2 * x_stride;
+    float4 a[LN_VEC], b[LN_VEC];
+#pragma unroll
+    for (int i = 0; i < LN_VEC; ++i) a[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    if (row2 < rows) {
+#pragma unroll
+      for (int i = 0; i < LN_VEC; ++i) b[i] = *reinterpret_cast<const float4*>(xr2 + (i * 32 + lane) * 4);
+    }
+    ln_row<T>(a, lane, gamma, beta, y + (int64_t)row * LN_COLS, mean_out, rstd_out, row, eps);
+    if (row2 < rows) ln_row<T>(b, lane, gamma, beta, y + (int64_t)row2 * LN_COLS, mean_out, rstd_out, row2, eps);
   }
 }
 
@@ -171,7 +194,9 @@ extern "C" int vitk_layernorm_fwd(const float* x, int64_t x_stride, const float*
   VITK_CHECK_ARG(x_stride % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0);
   if (rows == 0) return VITK_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int cap = sm_count() * (debug_knob(9) > 0 ? debug_knob(9) : 8);   // CTAs per SM (knob 9 for A/B: 8 measured best in-step)
+  if (grid > cap) grid = cap;
   if (y_dtype == VITK_F32)
     VITK_LAUNCH((ln_fwd_kernel<float>), grid, LN_WARPS * 32, 0, st, x, x_stride, gamma, beta, (float*)y, mean, rstd, rows, eps);
   else if (y_dtype == VITK_BF16)
