@@ -2,12 +2,15 @@
 //
 //   C[i][j] = sum_r A(i,r) * B(j,r)  + fused epilogue (gemm.cuh)
 //
-// One persistent CTA per SM, 320 threads:
-//   warp 0        TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier expect_tx)
-//   warp 1        MMA issuer     (one elected lane: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16,
-//                                 accumulators double-buffered in TMEM; tcgen05.commit -> mbarriers)
-//   warps 2..9    epilogue       (tcgen05.ld 32x32b -> registers -> swizzled smem transpose -> coalesced
-//                                 bias/GELU/residual/scatter global IO; two warps per TMEM lane quarter)
+// One persistent CTA per SM, 320 threads; the whole warp of each role walks the work list (warp-uniform control flow keeps
+// addresses in uniform registers), one elected lane issues:
+//   warp 0        TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring of 5..8 stages, mbarrier expect_tx;
+//                                 coordinates advance by additions only)
+//   warp 1        MMA issuer     (tcgen05.mma.kind::f16, 128|256 x BN x 16, accumulators double-buffered in TMEM, smem
+//                                 descriptors = constant high word + running low word; tcgen05.commit -> mbarriers)
+//   warps 2..9    epilogue       (tcgen05.ld 32x32b gives each lane an accumulator ROW -> epilogue math -> swizzled
+//                                 32 x 32 staging tile -> TMA store; second operands TMA-loaded into the staging tile;
+//                                 compile-time epilogue kinds EK_*; stream-K accumulate keeps a transposing red.global path)
 // Both operands may be K-major (reduction index contiguous: forward X W^T) or MN-major (row index
 // contiguous: dgrad's W, wgrad's dY^T and X) -- the major-ness is a bit in the instruction descriptor
 // plus the canonical 128B-swizzle shared-memory layout the TMA boxes are written in -- and may be stored
@@ -15,11 +18,14 @@
 // CTA pairs (template CG = 2, the default for every shape with >= 2 x 128 rows): the two CTAs of a 2-cluster own
 // one 256 x BN tile -- each stages its own 128 rows of A and HALF of the B tile, the leader's elected lane issues
 // tcgen05.mma.cta_group::2 (M = 256) against both shared memories and multicasts its commits to both CTAs' barriers.
-// Per CTA and k-block that is 128 + BN/2 operand rows from L2 instead of 128 + BN: the kernel is bound by L2->SM
-// bandwidth (~6.3 KB/clk chip-wide), not by the tensor pipe, so this is what moves it.
+// Per CTA and k-block that is 128 + BN/2 operand rows instead of 128 + BN: what bounds the kernel is the rate at which
+// one SM can take operand bytes in (~45 B/clk through TMA, tools/micro/tma_ingest.cu), not the tensor
+// pipe, so halving the B traffic is what moves it.
 // Work: output tiles strided over the persistent CTAs (CTA pairs); accumulate epilogues (wgrad) instead use stream-K --
 // the (tile, k-block) space is cut into one equal contiguous range per CTA and partial tiles are summed
 // with fp32 vector atomics, so 18..72-tile weight-gradient GEMMs still load all 148 SMs evenly.
+// Every launch carries the programmatic-dependent-launch attribute: barrier init, TMEM allocation and tensor-map
+// prefetch run before pdl_sync(), i.e. under the tail of the previous kernel.
 //
 // Replaces the cuBLASLt GEMMs behind timm's nn.Linear layers (SURVEY.md 2.1 K4,K6,K7,K8 and their
 // autograd backward), reached from /root/reference/train_advanced.py:327-330.
@@ -117,14 +123,6 @@ __device__ __forceinline__ void tc_commit_2cta(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -163,14 +161,6 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -222,17 +212,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
-}
-
-// 64-bit shared-memory matrix descriptor (SWIZZLE_128B, version 1 = Blackwell)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // version
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
-  return d;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -398,21 +377,6 @@ __device__ __forceinline__ void tc_tma(uint32_t dst, const CUtensorMap* map, uin
   if constexpr (CG == 2) tma_load_3d_2cta(dst, map, bar, c0, c1, c2);
   else tma_load_3d(dst, map, bar, c0, c1, c2);
 }
-template <int CG>
-__device__ __forceinline__ void tc_issue_operand_loads(const CUtensorMap* map, int mode, uint32_t dst, uint32_t bar,
-                                                       int row0, int rows_in_tile, int r0) {
-  // K-major: one box [rows_in_tile][64 r]; MN-major: rows_in_tile/64 boxes [64 r][64 rows], 8 KB apart
-  if (mode == OP_KM_FLAT) {
-    tc_tma<CG>(dst, map, bar, r0, row0, 0);
-  } else if (mode == OP_KM_SPLIT) {
-    tc_tma<CG>(dst, map, bar, 0, row0, r0 >> 6);
-  } else if (mode == OP_MN_FLAT) {
-    for (int a = 0; a < rows_in_tile / 64; ++a) tc_tma<CG>(dst + a * 8192, map, bar, row0 + a * 64, r0, 0);
-  } else {
-    for (int a = 0; a < rows_in_tile / 64; ++a) tc_tma<CG>(dst + a * 8192, map, bar, 0, r0, (row0 >> 6) + a);
-  }
-}
-
 // Work iterator shared by the three warp roles (they must walk identical sequences).
 struct TcWork {
   int tile, kb0, kb1;
