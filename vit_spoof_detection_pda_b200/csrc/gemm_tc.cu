@@ -978,6 +978,9 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
   if (pr.ep.mode == E_ACCUM && g_tc_debug[1] != 1) {
     const int64_t total = (int64_t)tiles * p.kb_total;
     grid = total < slots ? (int)total : slots;
+    // knob 11 (A/B): at most this many partial sums per output tile -- fewer, longer-lived CTAs and less atomic traffic
+    // for the small weight-gradient GEMMs that run next to the dgrad chain
+    if (g_tc_debug[11] > 0 && grid > tiles * g_tc_debug[11]) grid = tiles * g_tc_debug[11];
     p.streamk = 1;
     p.units_per_cta = (total + grid - 1) / grid;
     grid = (int)((total + p.units_per_cta - 1) / p.units_per_cta);

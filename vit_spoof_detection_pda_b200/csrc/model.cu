@@ -28,7 +28,10 @@ static SideStream* side_stream() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
   SideStream& ss = per_dev[dev];
   if (!ss.s) {
-    if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    // knob 10 (A/B): 1 = lowest priority for the weight-gradient stream (the dgrad chain is the critical path)
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&ss.s, cudaStreamNonBlocking, debug_knob(10) == 1 ? lo : 0) != cudaSuccess) return nullptr;
     for (auto& e : ss.ev)
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
