@@ -21,6 +21,7 @@ constexpr float AM_SCALE = 0.125f;
 constexpr float AM_LOG2E = 1.4426950408889634f;
 
 int attn_debug_variant();  // gemm_tc.cu: vitk_debug_set(3, v)
+int debug_knob(int key);     // gemm_tc.cu: vitk_debug_set(key, v)
 
 __device__ __forceinline__ uint32_t am_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t am_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
@@ -427,7 +428,9 @@ int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float
                  int batch, cudaStream_t st) {
   if (attn_debug_variant() == 0) {
     // the tcgen05 kernel's epilogue warps add the qkv bias gradient (column sums of dqkv) from their staging tiles
-    return attn_bwd_tc(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, st);
+    // (vitk_debug_set(12, 1): A/B -- stand-alone column-sum pass instead)
+    if (debug_knob(12) != 1) return attn_bwd_tc(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, st);
+    VITK_TRY(attn_bwd_tc(qkv, out, dout, lse, dqkv, nullptr, batch, st));
   } else {
     static bool configured = false;
     if (!configured) {

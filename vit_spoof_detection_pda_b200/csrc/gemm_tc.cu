@@ -58,8 +58,9 @@ struct TcParams {
   int32_t a_mode, b_mode;
   OpCoord ca, cb;
   int32_t n_tiles_m, n_tiles_n, kb_total;
-  int32_t streamk;          // 0: tile-strided, full K per tile; 1: contiguous (tile, k-block) unit range per CTA
-  int64_t units_per_cta;    // stream-K: ceil(tiles * kb_total / gridDim.x)
+  int32_t streamk;          // 0: tile-strided, full K per tile; 1: contiguous (tile, k-block) unit range per CTA;
+                            // 2: sliced split-K, CTA c owns k-slice c / tiles of tile c % tiles
+  int64_t units_per_cta;    // stream-K: ceil(tiles * kb_total / gridDim.x); sliced split-K: number of k-slices
   uint32_t idesc;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // bytes
   uint32_t a_kstep, b_kstep;            // bytes advanced per UMMA_K=16 step
@@ -191,6 +192,11 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 // TMA store / load of epilogue tiles (2-D row-major, 3-D head-major) and bulk-group bookkeeping
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+// fp32 reduce-add of a staged tile into global memory (the tensor map's element type selects the add)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
@@ -352,10 +358,11 @@ __device__ __forceinline__ void epilogue_rows8(const EpiParams& ep, int i, int j
 // (rows past the end of the matrix are clipped by the tensor map).  Second operands (fp32 residual, saved gelu')
 // arrive the same way: a TMA load into the staging tile issued BEFORE the accumulator is ready, combined in place.
 // No per-thread global loads/stores and no global-memory latency remain on the epilogue warps' critical path.
-enum { EK_LEGACY = 0, EK_STORE_BF16 = 1, EK_STORE_F32 = 2, EK_GELU = 3, EK_RESIDUAL = 4, EK_SCATTER = 5, EK_GELU_BWD = 6 };
+enum { EK_LEGACY = 0, EK_STORE_BF16 = 1, EK_STORE_F32 = 2, EK_GELU = 3, EK_RESIDUAL = 4, EK_SCATTER = 5, EK_GELU_BWD = 6,
+       EK_ACCUM = 7 };   // EK_ACCUM: fp32 tile -> TMA reduce-add into the gradient buffer (weight-gradient partial tiles)
 // staging per epilogue warp: two 4 KB slots for fp32 tiles, two 2 KB slots for bf16 tiles (EK_GELU: one slot pair g | u).
 // Every KB not spent here is operand-ring depth: the mainloop needs ~1.5 us of loads in flight to ride out DRAM latency.
-__host__ __device__ constexpr uint32_t tc_epi_warp_bytes(int ek) { return (ek == EK_STORE_F32 || ek == EK_RESIDUAL) ? 8192u : 4096u; }
+__host__ __device__ constexpr uint32_t tc_epi_warp_bytes(int ek) { return (ek == EK_STORE_F32 || ek == EK_RESIDUAL || ek == EK_ACCUM) ? 8192u : 4096u; }
 
 template <int BN, int CG, int EK> struct TcCfg {
   static constexpr int B_ROWS = BN / CG;                                   // rows of the B tile this CTA stages
@@ -380,6 +387,7 @@ __device__ __forceinline__ void tc_tma(uint32_t dst, const CUtensorMap* map, uin
 // Work iterator shared by the three warp roles (they must walk identical sequences).
 struct TcWork {
   int tile, kb0, kb1;
+  int tm, tn;   // tile row / tile column
 };
 struct TcWorkIter {
   int64_t cur, end;  // stream-K: unit cursor / end ; tile-strided: next tile / number of tiles
@@ -389,7 +397,10 @@ struct TcWorkIter {
     const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n;
     const int cluster = blockIdx.x / cg;
     stride = gridDim.x / cg;
-    if (p.streamk) {
+    if (p.streamk == 2) {          // sliced split-K: exactly one (tile, k-slice) item per CTA (pair)
+      cur = cluster;
+      end = cur + 1;
+    } else if (p.streamk) {
       const int64_t total = tiles * p.kb_total;
       cur = (int64_t)cluster * p.units_per_cta;
       end = cur + p.units_per_cta < total ? cur + p.units_per_cta : total;
@@ -399,8 +410,21 @@ struct TcWorkIter {
     }
   }
   __device__ __forceinline__ bool next(const TcParams& p, TcWork& w) {
+    if (!next_raw(p, w)) return false;
+    w.tm = w.tile / p.n_tiles_n;     // consecutive CTAs walk along a tile row (column-first order measured identical)
+    w.tn = w.tile % p.n_tiles_n;
+    return true;
+  }
+  __device__ __forceinline__ bool next_raw(const TcParams& p, TcWork& w) {
     if (cur >= end) return false;
-    if (p.streamk) {
+    if (p.streamk == 2) {
+      const int tiles = p.n_tiles_m * p.n_tiles_n, S = (int)p.units_per_cta;
+      const int slice = (int)cur / tiles;
+      w.tile = (int)cur % tiles;
+      w.kb0 = (int)((int64_t)slice * p.kb_total / S);
+      w.kb1 = (int)((int64_t)(slice + 1) * p.kb_total / S);
+      cur = end;
+    } else if (p.streamk) {
       w.tile = (int)(cur / p.kb_total);
       w.kb0 = (int)(cur % p.kb_total);
       const int64_t left = end - cur;
@@ -489,9 +513,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       TcWork w;
       const bool leader = elect_one();
       while (wi.next(p, w)) {
-        const int tile = w.tile;
-        const int i0 = (tile / p.n_tiles_n) * (TC_BM * CG) + (int)rank * TC_BM;
-        const int j0 = (tile % p.n_tiles_n) * BN + (int)rank * Cfg::B_ROWS;
+        const int i0 = w.tm * (TC_BM * CG) + (int)rank * TC_BM;
+        const int j0 = w.tn * BN + (int)rank * Cfg::B_ROWS;
         const int kb0 = w.kb0, kb1 = w.kb1;
         int a0 = i0 * p.ca.fr0 + kb0 * p.ca.d0, a1 = i0 * p.ca.fr1 + kb0 * p.ca.d1, a2 = (i0 >> 6) * p.ca.fr2 + kb0 * p.ca.d2;
         int b0 = j0 * p.cb.fr0 + kb0 * p.cb.d0, b1 = j0 * p.cb.fr1 + kb0 * p.cb.d1, b2 = (j0 >> 6) * p.cb.fr2 + kb0 * p.cb.d2;
@@ -591,8 +614,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if constexpr (EK == EK_LEGACY) {
       while (wi.next(p, w)) {
-        const int tile = w.tile;
-        const int i0 = (tile / p.n_tiles_n) * (TC_BM * CG) + (int)rank * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
+        const int i0 = w.tm * (TC_BM * CG) + (int)rank * TC_BM, j0 = w.tn * BN;
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -626,7 +648,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
       // ---------------- TMA epilogue ----------------
       constexpr bool kLoads = (EK == EK_RESIDUAL || EK == EK_GELU_BWD);       // second operand TMA-loaded into the staging tile
-      constexpr bool kF32 = (EK == EK_STORE_F32 || EK == EK_RESIDUAL);         // fp32 tiles: 4 KB, 128-byte rows
+      constexpr bool kF32 = (EK == EK_STORE_F32 || EK == EK_RESIDUAL || EK == EK_ACCUM);   // fp32 tiles: 4 KB, 128-byte rows
       constexpr uint32_t kTileBytes = kF32 ? 4096u : 2048u;
       constexpr int NCH = BN / 64;                                             // 32-column chunks per warp and tile
       constexpr uint32_t kSlotBytes = kF32 ? 4096u : 2048u;
@@ -635,8 +657,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t eph = 0;            // phase bits of this warp's two load barriers
       uint32_t slot = 0;           // staging slot of the next chunk (alternates across tiles too)
       while (wi.next(p, w)) {
-        const int tile = w.tile;
-        const int i0 = (tile / p.n_tiles_n) * (TC_BM * CG) + (int)rank * TC_BM, j0 = (tile % p.n_tiles_n) * BN;
+        const int i0 = w.tm * (TC_BM * CG) + (int)rank * TC_BM, j0 = w.tn * BN;
         const int row0 = i0 + q * 32;
         const bool active = row0 < p.I;   // warps whose 32 rows are all past the end of the matrix have nothing to do
         // ---- before the accumulator is ready: bias values of this warp's columns, and the first second-operand tile
@@ -709,7 +730,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             slot_ready();
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) sts128(t0 + row_off_64(lane, k4), ob[k4 * 4], ob[k4 * 4 + 1], ob[k4 * 4 + 2], ob[k4 * 4 + 3]);
-          } else if constexpr (EK == EK_STORE_F32) {
+          } else if constexpr (EK == EK_STORE_F32 || EK == EK_ACCUM) {
             slot_ready();
 #pragma unroll
             for (int k8 = 0; k8 < 8; ++k8)
@@ -769,6 +790,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (lane == 0) {
             if constexpr (EK == EK_SCATTER) {
               tma_store_3d(&map_c, t0, col & 63, row0, col >> 6);
+            } else if constexpr (EK == EK_ACCUM) {
+              tma_reduce_add_2d(&map_c, t0, col, row0);
             } else {
               tma_store_2d(&map_c, t0, col, row0);
               if constexpr (EK == EK_GELU) {
@@ -913,6 +936,9 @@ static int epilogue_kind(const EpiParams& ep) {
     case E_BIAS_GELU: return (ok16 && ep.out_dtype == VITK_BF16 && (((uintptr_t)ep.aux & 15) == 0)) ? EK_GELU : EK_LEGACY;
     case E_BIAS_RESIDUAL: return (ok16 && (((uintptr_t)ep.residual & 15) == 0)) ? EK_RESIDUAL : EK_LEGACY;
     case E_QKV_SCATTER: return (ok16 && ep.out_dtype == VITK_BF16) ? EK_SCATTER : EK_LEGACY;
+    // TMA reduce-add of the partial tiles is opt-in (knob 14 = 1): measured 2-3 % slower than the transposing
+    // red.global.add.v4 path on all four weight-gradient shapes (gpurun_out/ac_cublas.log)
+    case E_ACCUM: return (g_tc_debug[14] == 1 && ok16 && ep.out_dtype == VITK_F32 && !ep.colsum && !ep.bias) ? EK_ACCUM : EK_LEGACY;
     case E_GELU_BWD: return (ok16 && ep.out_dtype == VITK_BF16 && ep.aux && (((uintptr_t)ep.aux & 15) == 0)) ? EK_GELU_BWD : EK_LEGACY;
     default: return EK_LEGACY;
   }
@@ -939,7 +965,7 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
     VITK_TRY(make_tile_map(ep.out, VITK_BF16, pr.J, pr.I, 0, ep.hm_rows, &map_c));
     map_d = map_c;
   } else {
-    const int odt = (EK == EK_STORE_F32 || EK == EK_RESIDUAL) ? VITK_F32 : VITK_BF16;
+    const int odt = (EK == EK_STORE_F32 || EK == EK_RESIDUAL || EK == EK_ACCUM) ? VITK_F32 : VITK_BF16;
     VITK_TRY(make_tile_map(ep.out, odt, pr.J, pr.I, ep.ldc, 0, &map_c));
     if constexpr (EK == EK_RESIDUAL) VITK_TRY(make_tile_map(ep.residual, VITK_F32, pr.J, pr.I, ep.ldc, 0, &map_d));
     else if constexpr (EK == EK_GELU_BWD) VITK_TRY(make_tile_map(ep.aux, VITK_BF16, pr.J, pr.I, ep.ldc, 0, &map_d));
@@ -984,6 +1010,17 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
     p.streamk = 1;
     p.units_per_cta = (total + grid - 1) / grid;
     grid = (int)((total + p.units_per_cta - 1) / p.units_per_cta);
+    // Sliced split-K (knob 13 = 1 disables; 13 = p > 1: fill threshold in percent): when tiles x S fills >= 90 % of the slots, every CTA takes ONE k-slice of ONE
+    // tile.  All CTAs of a slice then sweep the same k range in lock-step -- the A panel of a tile row and the B panel of a
+    // tile column are fetched from DRAM once and hit in L2 for the other tiles -- and each CTA drains one accumulator
+    // instead of the two or three partial tiles a contiguous stream-K range straddles.
+    const int S = tiles > 0 ? slots / tiles : 0;
+    const int fill_pct = g_tc_debug[13] > 1 ? g_tc_debug[13] : 90;
+    if (g_tc_debug[13] != 1 && S >= 1 && tiles * S * 100 >= slots * fill_pct && p.kb_total >= 2 * S) {
+      p.streamk = 2;
+      p.units_per_cta = S;
+      grid = tiles * S;
+    }
   }
   p.ep = pr.ep;
   cudaLaunchConfig_t cfg{};
@@ -1019,6 +1056,7 @@ static int launch_tc_kind(const GemmProblem& pr, int ek, cudaStream_t st) {
     case EK_RESIDUAL: return launch_tc<BN, CG, EK_RESIDUAL>(pr, st);
     case EK_SCATTER: return launch_tc<BN, CG, EK_SCATTER>(pr, st);
     case EK_GELU_BWD: return launch_tc<BN, CG, EK_GELU_BWD>(pr, st);
+    case EK_ACCUM: return launch_tc<BN, CG, EK_ACCUM>(pr, st);
     default: return launch_tc<BN, CG, EK_LEGACY>(pr, st);
   }
 }
