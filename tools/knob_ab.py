@@ -36,7 +36,11 @@ def step(i):
 
 def apply(setting):
     for kv in setting.split(","):
-        lib.vitk_debug_set(int(kv.split(":")[0]), int(kv.split(":")[1]))
+        k, v = kv.split(":")
+        if k == "noprezero":       # host-side switch: gradient-buffer clear at the head of backward instead of under the forward
+            os.environ["VITK_NO_PREZERO"] = v
+        else:
+            lib.vitk_debug_set(int(k), int(v))
 
 
 for i in range(5):
