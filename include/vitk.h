@@ -99,8 +99,10 @@ int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, int64_t x_s
  * ------------------------------------------------------------------------------------------- */
 int vitk_linear_fwd(const void* x, int x_layout, const void* w, const float* bias, void* y, void* aux,
                     int M, int N, int K, int epilogue, int dtype, int engine, void* stream);
-/* dx_colsum (optional, only with gelu_grad): fp32 [K] += column sums of dX -- the bias gradient of the Linear in
- * front of the GELU (fc1), fused into this GEMM's epilogue instead of a separate pass over dX. */
+/* dx_colsum (optional): fp32 [K] += column sums of dX, fused into this GEMM's epilogue instead of a separate pass over
+ * dX.  With gelu_grad it is the bias gradient of the Linear in front of the GELU (fc1).  Without, the model driver uses
+ * it on the proj dgrad: with attention dropout 0 the column sums of the attention-output gradient ARE the v section of
+ * the qkv bias gradient (softmax rows sum to one), see csrc/attention.cu. */
 int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, const void* gelu_grad,
                       float* dx_colsum, int M, int N, int K, int dtype, int engine, void* stream);
 int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, float* dw, float* db,

@@ -62,7 +62,7 @@ def linear_dgrad(dy, w, engine, dy_layout=L.LAYOUT_ROWMAJOR, gelu_grad=None, wan
     N, K = w.shape
     M = dy.shape[0] if dy_layout == L.LAYOUT_ROWMAJOR else dy.shape[1]
     dx = torch.empty(M, K, dtype=dy.dtype, device=dy.device)
-    cs = torch.zeros(K, dtype=torch.float32, device=dy.device) if (want_colsum and gelu_grad is not None) else None
+    cs = torch.zeros(K, dtype=torch.float32, device=dy.device) if want_colsum else None
     L.call("vitk_linear_dgrad", L.ptr(dy), dy_layout, L.ptr(w), L.ptr(dx), L.ptr(gelu_grad), L.ptr(cs), M, N, K,
            DT[dy.dtype], engine, L.stream_ptr())
     return (dx, cs) if cs is not None else dx

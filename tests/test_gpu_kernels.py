@@ -118,6 +118,9 @@ def test_linear_dgrad(case, M, N, Kd):
     for eng in engines:
         dx = K.linear_dgrad(dy, w, eng)
         assert K.rel_err(dx.float(), ref) < _tol(dtype), ("plain", eng)
+        dx, cs = K.linear_dgrad(dy, w, eng, want_colsum=True)
+        assert K.rel_err(dx.float(), ref) < _tol(dtype), ("plain + column sums", eng)
+        assert K.rel_err(cs, dx.float().sum(0)) < 1e-3, ("plain: fused column sums", eng)
         dx, cs = K.linear_dgrad(dy, w, eng, gelu_grad=u, want_colsum=True)
         assert K.rel_err(dx.float(), ref * u.float()) < _tol(dtype), ("gelu_bwd", eng)
         assert K.rel_err(cs, dx.float().sum(0)) < 1e-3, ("gelu_bwd fused bias-grad column sums", eng)

@@ -7,7 +7,9 @@ int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const floa
                   int dtype, cudaStream_t st);
 int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t st);
 int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum,
-                 int batch, cudaStream_t st);
+                 int batch, cudaStream_t st, int cs_sections);
+int attn_debug_variant();
+int debug_knob(int key);
 int colsum_headmajor(const void* x, int dtype, int M, int C, float* db, cudaStream_t st);
 
 int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dtype, cudaStream_t st) {
@@ -16,10 +18,22 @@ int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dty
 }
 // dqkv_colsum (optional): fp32 [2304] += column sums of dqkv = the qkv bias gradient; fused into the tensor-core
 // kernel, a separate reduction after the FFMA kernel.
+//
+// The model driver's bf16 path asks the attention kernel for the q section only (cs_sections = 1) when
+// attn_bias_split_supported(): with attention dropout 0 (timm's attn_drop, the reference never sets it) every softmax row
+// sums to one and every row of dS to zero, so
+//     sum_keys dV[key, :] = sum_q (sum_key P[q, key]) dO[q, :] = sum_q dO[q, :]     -> the v section is the column sum of the
+//                                                                                    proj dgrad output (fused in its epilogue)
+//     sum_keys dK[key, :] = sum_q (sum_key dS[q, key]) Q[q, :] * scale = 0           -> the k section stays zero
+// (softmax is invariant to a shift of all keys: the k bias has no gradient).  The attention kernel's epilogue warps,
+// which gate the recycling of its dV / dK / dQ accumulators, then sum 4 instead of 12 slabs per item.
+bool attn_bias_split_supported(int dtype) {
+  return dtype == VITK_BF16 && default_engine() != VITK_ENGINE_SIMT && attn_debug_variant() == 0 && debug_knob(12) != 1;
+}
 int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                      float* dqkv_colsum, int batch, int dtype, cudaStream_t st) {
+                      float* dqkv_colsum, int batch, int dtype, cudaStream_t st, int cs_sections) {
   if (dtype == VITK_BF16 && default_engine() != VITK_ENGINE_SIMT)
-    return attn_bwd_mma(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, st);
+    return attn_bwd_mma(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, st, cs_sections);
   VITK_TRY(attn_bwd_simt(qkv, out, dout, lse, dqkv, batch, dtype, st));
   if (dqkv_colsum) VITK_TRY(colsum_headmajor(dqkv, dtype, batch * VITK_NTOK, 3 * VITK_DIM, dqkv_colsum, st));
   return VITK_OK;
@@ -35,5 +49,5 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int batch, 
 extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                              float* dqkv_colsum, int batch, int dtype, void* stream) {
   VITK_CHECK_ARG(qkv && out && dout && lse && dqkv && batch > 0 && (dtype == VITK_F32 || dtype == VITK_BF16));
-  return attn_bwd_dispatch(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, dtype, (cudaStream_t)stream);
+  return attn_bwd_dispatch(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, dtype, (cudaStream_t)stream, 7);
 }

@@ -409,7 +409,7 @@ attn_bwd_mma2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
 int colsum_headmajor(const void* x, int dtype, int M, int C, float* db, cudaStream_t st);
 int attn_fwd_tc(const void* qkv, void* out, float* lse, int batch, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum, int batch,
-                cudaStream_t st);
+                cudaStream_t st, int cs_sections);
 
 // vitk_debug_set(3, 0): tcgen05 kernels (attention_tc.cu, default); (3, 1): the mma.sync kernels of this file
 int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t st) {
@@ -425,12 +425,11 @@ int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t
 }
 
 int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum,
-                 int batch, cudaStream_t st) {
+                 int batch, cudaStream_t st, int cs_sections) {
   if (attn_debug_variant() == 0) {
     // the tcgen05 kernel's epilogue warps add the qkv bias gradient (column sums of dqkv) from their staging tiles
-    // (vitk_debug_set(12, 1): A/B -- stand-alone column-sum pass instead)
-    if (debug_knob(12) != 1) return attn_bwd_tc(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, st);
-    VITK_TRY(attn_bwd_tc(qkv, out, dout, lse, dqkv, nullptr, batch, st));
+    // (cs_sections: which of the q | k | v sections -- bits 0 | 1 | 2 -- this launch is asked for)
+    return attn_bwd_tc(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, st, cs_sections);
   } else {
     static bool configured = false;
     if (!configured) {

@@ -504,7 +504,7 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t lbo) { r
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
                    const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ out, const float* __restrict__ lse,
-                   bf16* __restrict__ dqkv, float* __restrict__ dqkv_colsum, int batch, int n_items, int dbg) {
+                   bf16* __restrict__ dqkv, float* __restrict__ dqkv_colsum, int cs_sections, int batch, int n_items, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -824,9 +824,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
         // ---- dV_t, dK_t (lane = key)
         mbar_wait(dvk_full, (it * 2 + t) & 1);
         tc_fence_after();
-        float* csb = dqkv_colsum ? dqkv_colsum + h * 64 : nullptr;      // [3][12][64]: q | k | v sections
-        drain_tile(T_DV, dqkv + hm + 2 * hstride, t * 128, 1.0f, csb ? csb + 2 * VITK_DIM : nullptr);
-        drain_tile(T_DK, dqkv + hm + hstride, t * 128, SCALE, csb ? csb + VITK_DIM : nullptr);
+        float* csb = dqkv_colsum ? dqkv_colsum + h * 64 : nullptr;      // [3][12][64]: q | k | v sections (cs_sections: bits 0 | 1 | 2)
+        drain_tile(T_DV, dqkv + hm + 2 * hstride, t * 128, 1.0f, (csb && (cs_sections & 4)) ? csb + 2 * VITK_DIM : nullptr);
+        drain_tile(T_DK, dqkv + hm + hstride, t * 128, SCALE, (csb && (cs_sections & 2)) ? csb + VITK_DIM : nullptr);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dvk_free);
@@ -837,8 +837,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
       // ---- dQ (lane = query), two 128-query tiles
       mbar_wait(dq_full, ipar);
       tc_fence_after();
-      drain_tile(T_DQ, dqkv + hm, 0, SCALE, dqkv_colsum ? dqkv_colsum + h * 64 : nullptr);
-      drain_tile(T_DQ + 64, dqkv + hm, 128, SCALE, dqkv_colsum ? dqkv_colsum + h * 64 : nullptr);
+      float* csq = (dqkv_colsum && (cs_sections & 1)) ? dqkv_colsum + h * 64 : nullptr;
+      drain_tile(T_DQ, dqkv + hm, 0, SCALE, csq);
+      drain_tile(T_DQ + 64, dqkv + hm, 128, SCALE, csq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
@@ -894,7 +895,7 @@ int attn_fwd_tc(const void* qkv, void* out, float* lse, int batch, cudaStream_t 
 }
 
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum, int batch,
-                cudaStream_t st) {
+                cudaStream_t st, int cs_sections) {
   static bool configured = false;
   if (!configured) {
     VITK_CUDA(cudaFuncSetAttribute(atc::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atc::BWD_SMEM));
@@ -907,7 +908,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   VITK_TRY(atc::make_dout_map(dout, M, &map_do));
   const int items = batch * VITK_HEADS, sms = sm_count();
   VITK_LAUNCH((atc::attn_bwd_tc_kernel), (items < sms ? items : sms), atc::BWD_THREADS, atc::BWD_SMEM, st, map_kv, map_q, map_do,
-              (const bf16*)out, lse, (bf16*)dqkv, dqkv_colsum, batch, items, debug_knob(7));
+              (const bf16*)out, lse, (bf16*)dqkv, dqkv_colsum, cs_sections, batch, items, debug_knob(7));
   return VITK_OK;
 }
 

@@ -444,6 +444,34 @@ struct TcWorkIter {
 __device__ __forceinline__ uint32_t row_off_64(int r, int k4) { return (uint32_t)(r * 64 + ((k4 ^ ((r >> 1) & 3)) << 4)); }   // bf16, SWIZZLE_64B
 __device__ __forceinline__ uint32_t row_off_128(int r, int k8) { return (uint32_t)(r * 128 + ((k8 ^ (r & 7)) << 4)); }        // fp32, SWIZZLE_128B
 
+// += column sums of one staged 32 x 32 bf16 tile (SWIZZLE_64B rows, row_off_64) into colsum[0..31] (32-byte aligned):
+// lane reads the 16-byte chunk (lane & 3) of rows (lane >> 2) + 8 j -- four conflict-free 128-bit loads cover the tile --
+// the 8 lanes sharing a chunk are summed with three shuffle stages, lanes 0..3 issue two vector reductions each.
+__device__ __forceinline__ void tile_colsum_bf16(uint32_t t0, int lane, float* colsum) {
+  float cs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 w = lds128(t0 + row_off_64((lane >> 2) + 8 * j, lane & 3));
+    cs[0] += __uint_as_float(w.x << 16); cs[1] += __uint_as_float(w.x & 0xFFFF0000u);
+    cs[2] += __uint_as_float(w.y << 16); cs[3] += __uint_as_float(w.y & 0xFFFF0000u);
+    cs[4] += __uint_as_float(w.z << 16); cs[5] += __uint_as_float(w.z & 0xFFFF0000u);
+    cs[6] += __uint_as_float(w.w << 16); cs[7] += __uint_as_float(w.w & 0xFFFF0000u);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 4);
+    cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+    cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+  }
+  if (lane < 4) {
+    float* d = colsum + lane * 8;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
+  }
+}
+
 template <int BN, int CG, int EK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -730,6 +758,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             slot_ready();
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) sts128(t0 + row_off_64(lane, k4), ob[k4 * 4], ob[k4 * 4 + 1], ob[k4 * 4 + 2], ob[k4 * 4 + 3]);
+            if constexpr (EK == EK_STORE_BF16) {
+              // optional column sums of the bf16 output (no bias in this mode: rows past the end of the matrix are zero)
+              if (p.ep.colsum) { __syncwarp(); tile_colsum_bf16(t0, lane, p.ep.colsum + col); }
+            }
           } else if constexpr (EK == EK_STORE_F32 || EK == EK_ACCUM) {
             slot_ready();
 #pragma unroll
@@ -773,16 +805,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if (p.ep.colsum) {
               // bias gradient of fc1 = column sums of the bf16 values just written (rows past the end are zero: their
-              // gelu' tile was zero-filled by the TMA load).  Lane = column; 32 conflict-free 2-byte reads.
+              // gelu' tile was zero-filled by the TMA load)
               __syncwarp();
-              float cs = 0.f;
-#pragma unroll
-              for (int r = 0; r < 32; ++r) {
-                uint16_t h;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(t0 + row_off_64(r, lane >> 3) + (lane & 7) * 2));
-                cs += __uint_as_float((uint32_t)h << 16);
-              }
-              atomicAdd(p.ep.colsum + col + lane, cs);
+              tile_colsum_bf16(t0, lane, p.ep.colsum + col);
             }
           }
           fence_proxy_async_smem();
@@ -1102,6 +1127,10 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
   }
   if (bn == 0 || pr.J % bn != 0) { set_error("gemm_tc: no BLOCK_N divides J=%d", pr.J); return VITK_ERR_UNSUPPORTED; }
   const int ek = epilogue_kind(pr.ep);
+  if (pr.ep.colsum && !(ek == EK_GELU_BWD || (ek == EK_STORE_BF16 && !pr.ep.bias) || pr.ep.mode == E_GELU_BWD)) {
+    set_error("gemm_tc: fused column sums need the TMA epilogue of a bias-free bf16 store or of the GELU' multiply");
+    return VITK_ERR_UNSUPPORTED;
+  }
   if (cg == 2) {
     if (bn == 256) return launch_tc_kind<256, 2>(pr, ek, st);
     if (bn == 192) return launch_tc_kind<192, 2>(pr, ek, st);

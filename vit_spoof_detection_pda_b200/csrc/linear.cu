@@ -227,7 +227,6 @@ extern "C" int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, v
   VITK_CHECK_ARG(dy && w && dx && M > 0 && N > 0 && K > 0);
   VITK_CHECK_ARG(dtype == VITK_F32 || dtype == VITK_BF16);
   VITK_CHECK_ARG(dy_layout != VITK_LAYOUT_HEADMAJOR || N % 64 == 0);
-  VITK_CHECK_ARG(dx_colsum == nullptr || gelu_grad != nullptr);
   GemmProblem p{};
   p.I = M; p.J = K; p.R = N;
   p.A = dy; p.B = w; p.in_dtype = dtype;
@@ -236,8 +235,9 @@ extern "C" int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, v
   p.ep.out = dx; p.ep.ldc = K; p.ep.out_dtype = dtype;
   p.ep.mode = gelu_grad ? E_GELU_BWD : E_STORE;
   p.ep.aux = const_cast<void*>(gelu_grad);
-  // column sums of dX (= bias gradient of the Linear in front of the GELU): fused into the tcgen05 epilogue;
-  // the SIMT engine (fp32-validate) runs the reduction kernel on the finished output instead
+  // column sums of dX (with gelu_grad: the bias gradient of the Linear in front of the GELU; without: e.g. the v section
+  // of the qkv bias gradient from the proj dgrad, attention.cu): fused into the tcgen05 epilogue; the SIMT engine
+  // (fp32-validate) runs the reduction kernel on the finished output instead
   int eng = engine == VITK_ENGINE_AUTO ? default_engine() : engine;
   if (dtype == VITK_F32) eng = VITK_ENGINE_SIMT;
   if (eng == VITK_ENGINE_AUTO) eng = VITK_ENGINE_TCGEN05;

@@ -7,7 +7,8 @@ namespace vitk {
 
 int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dtype, cudaStream_t st);
 int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                      float* dqkv_colsum, int batch, int dtype, cudaStream_t st);
+                      float* dqkv_colsum, int batch, int dtype, cudaStream_t st, int cs_sections);
+bool attn_bias_split_supported(int dtype);
 
 int debug_knob(int key);   // gemm_tc.cu: vitk_debug_set(8, 1) keeps the weight-gradient GEMMs on the main stream
 
@@ -351,9 +352,15 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   VITK_TRY(after(3, ms, ss ? ss->s : ms));   // dx16 (gradient of x_mid) ready
   VITK_TRY(vitk_linear_wgrad(dxa, VITK_LAYOUT_ROWMAJOR, ao, c.G(b.projw), nullptr, M, D, D, dt, eng, wst));
   if (ss) VITK_CUDA(cudaEventRecord(ss->ev[4], ss->s));                  // proj wgrad has read dx16
-  VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.projw), dh, nullptr, nullptr, M, D, D, dt, eng, st));
-  // the qkv bias gradient (column sums of dqkv) comes out of the attention backward's epilogue warps
-  VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, c.G(b.qkvb), m->batch, dt, c.st));
+  // the qkv bias gradient = column sums of dqkv.  bf16 path (attention.cu, attn_bias_split_supported): the v section is the
+  // column sum of dh (softmax rows sum to one), taken in the epilogue of the GEMM that produces dh; the k section is zero
+  // (rows of dS sum to zero); only the q section is summed by the attention backward's epilogue warps.  fp32 path: a
+  // column-sum pass over dqkv.
+  const bool split_bias = attn_bias_split_supported(dt) && eng != VITK_ENGINE_SIMT;
+  VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.projw), dh, nullptr, split_bias ? c.G(b.qkvb) + 2 * D : nullptr,
+                             M, D, D, dt, eng, st));
+  VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, c.G(b.qkvb), m->batch, dt, c.st,
+                             split_bias ? 1 : 7));
   VITK_TRY(after(5, ms, ss ? ss->s : ms));   // dqkv ready
   VITK_TRY(vitk_linear_wgrad(dqkv, VITK_LAYOUT_HEADMAJOR, ln1, c.G(b.qkvw), nullptr, M, 3 * D, D, dt, eng, wst));
   VITK_TRY(vitk_linear_dgrad(dqkv, VITK_LAYOUT_HEADMAJOR, c.W(b.qkvw), dh, nullptr, nullptr, M, 3 * D, D, dt, eng, st));
