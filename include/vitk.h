@@ -253,6 +253,17 @@ int vitk_debug_set(int key, int value);
  * data-parallel wrapper lowers it during backward so the NCCL all-reduce CTAs and the persistent GEMM CTAs
  * (one per SM, ~225 KB of shared memory each) can all be resident at once.  Returns the previous value. */
 int vitk_set_sm_budget(int n);
+/* Host-only view of the tcgen05 GEMM's work decomposition for C[I][J] += over R (no launch; only the SM count / budget is
+ * consulted): tile width BLOCK_N, CTA group (1 single CTAs with 128-row tiles, 2 CTA pairs with 256-row tiles), mode
+ * (0 whole-K tiles strided over the persistent clusters, 1 contiguous stream-K ranges, 2 sliced split-K: one k-slice of
+ * one tile per cluster), number of clusters launched, tile grid and number of 64-deep k-blocks.  accumulate != 0 is the
+ * weight-gradient epilogue (fp32 +=); b_mn_major != 0 says the B operand is stored with its row index contiguous
+ * (dgrad's W, wgrad's X).  vitk_gemm_plan_items writes the (tile, first k-block, end k-block) triples cluster `cluster`
+ * walks -- the same iterator code the kernel's warps run -- and returns their count (negative VITK_ERR_* on bad
+ * arguments); tests/test_host_logic.py checks that all clusters together cover every (tile, k-block) exactly once. */
+int vitk_gemm_plan(int I, int J, int R, int accumulate, int b_mn_major, int* block_n, int* cta_group, int* mode,
+                   int* n_clusters, int* n_tiles_m, int* n_tiles_n, int* kb_total);
+int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_mn_major, int cluster, int* items, int max_items);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long vitk_launch_count(void);
 /* per-launch GEMM timing with CUDA events on the launching stream (bench.py's live roofline):

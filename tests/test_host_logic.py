@@ -121,3 +121,85 @@ def test_bucketed_allreduce_gloo_world2(pkg):
     mp.spawn(_gloo_worker, args=(2, _free_port(), ranges, total, out), nprocs=2, join=True)
     assert out[0][0] and out[1][0]
     assert out[0][1] == out[1][1] >= 2
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMM work decomposition (host logic of csrc/gemm_tc.cu, queried through the C-ABI; no GPU needed: without a device
+# the library plans for 148 SMs).  Every (tile, k-block) unit must be produced exactly once, whatever the mode.
+# ---------------------------------------------------------------------------------------------
+def _plan(lib, I, J, R, accumulate, b_mn):
+    import ctypes as C
+    out = [C.c_int() for _ in range(7)]
+    rc = lib.vitk_gemm_plan(I, J, R, accumulate, b_mn, *[C.byref(o) for o in out])
+    assert rc == 0
+    bn, cg, mode, ncl, tm, tn, kb = [o.value for o in out]
+    items = []
+    buf = (C.c_int * (3 * 4096))()
+    for c in range(ncl):
+        n = lib.vitk_gemm_plan_items(I, J, R, accumulate, b_mn, c, buf, 4096)
+        assert 0 < n <= 4096, (c, n)
+        items.append([(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(n)])
+    return dict(bn=bn, cg=cg, mode=mode, clusters=ncl, tm=tm, tn=tn, kb=kb), items
+
+
+M64 = 64 * 197
+GEMM_SHAPES = [   # (I, J, R, accumulate, B MN-major): the twelve GEMMs of a bs-64 step + small / ragged ones
+    (M64, 2304, 768, 0, 0), (M64, 768, 768, 0, 0), (M64, 3072, 768, 0, 0), (M64, 768, 3072, 0, 0),
+    (M64, 3072, 768, 0, 1), (M64, 768, 3072, 0, 1), (M64, 768, 768, 0, 1), (M64, 768, 2304, 0, 1),
+    (768, 3072, M64, 1, 1), (3072, 768, M64, 1, 1), (768, 768, M64, 1, 1), (2304, 768, M64, 1, 1),
+    (197, 768, 768, 0, 0), (100, 128, 64, 0, 0), (768, 768, 197, 1, 1), (2304, 768, 8 * 197, 1, 1), (512, 128, 100, 1, 1),
+]
+
+
+@pytest.mark.parametrize("budget", [0, 140, 132, 116])
+def test_gemm_plan_covers_every_tile_and_kblock_once(budget):
+    from vit_spoof_detection_pda_b200 import _lib as L
+    lib = L.load()
+    prev = lib.vitk_set_sm_budget(budget)
+    try:
+        for I, J, R, acc, bmn in GEMM_SHAPES:
+            plan, items = _plan(lib, I, J, R, acc, bmn)
+            assert J % plan["bn"] == 0 and plan["cg"] in (1, 2) and plan["mode"] in (0, 1, 2)
+            assert plan["tm"] == -(-I // (128 * plan["cg"])) and plan["tn"] == J // plan["bn"] and plan["kb"] == -(-R // 64)
+            sms = budget if budget else 148
+            assert plan["clusters"] * plan["cg"] <= sms, "more CTAs than SMs: a persistent CTA would wait for a slot"
+            if not acc:
+                assert plan["mode"] == 0
+            cover = {}
+            for cl in items:
+                for tile, kb0, kb1 in cl:
+                    assert 0 <= tile < plan["tm"] * plan["tn"] and 0 <= kb0 < kb1 <= plan["kb"], (I, J, R, tile, kb0, kb1)
+                    for kb in range(kb0, kb1):
+                        cover[(tile, kb)] = cover.get((tile, kb), 0) + 1
+            assert len(cover) == plan["tm"] * plan["tn"] * plan["kb"], (I, J, R, plan)
+            assert set(cover.values()) == {1}, (I, J, R, plan)
+            if plan["mode"] == 2:      # sliced split-K: one item per cluster, slices of one tile differ by at most one k-block
+                assert all(len(cl) == 1 for cl in items)
+                lens = [cl[0][2] - cl[0][1] for cl in items]
+                assert max(lens) - min(lens) <= 1
+            if plan["mode"] == 1:      # stream-K: equal contiguous ranges (the last cluster may be short)
+                lens = [sum(k1 - k0 for _, k0, k1 in cl) for cl in items]
+                assert max(lens[:-1] or lens) - min(lens[:-1] or lens) == 0 and lens[-1] <= lens[0]
+    finally:
+        lib.vitk_set_sm_budget(prev)
+
+
+def test_gemm_plan_bench_shapes_pick_documented_decompositions():
+    """fc1 / fc2 / proj weight gradients run sliced split-K (36 x 2, 36 x 2, 9 x 8 items on 74 CTA pairs),
+    the qkv weight gradient (27 tiles) contiguous stream-K ranges; J = 768 forward shapes take 256 x 192 pair tiles."""
+    from vit_spoof_detection_pda_b200 import _lib as L
+    lib = L.load()
+    prev = lib.vitk_set_sm_budget(0)
+    try:
+        for (I, J, R), clusters in (((768, 3072, M64), 72), ((3072, 768, M64), 72), ((768, 768, M64), 72)):
+            plan, _ = _plan(lib, I, J, R, 1, 1)
+            assert (plan["mode"], plan["clusters"], plan["bn"], plan["cg"]) == (2, clusters, 256, 2)
+        plan, _ = _plan(lib, 2304, 768, M64, 1, 1)
+        assert (plan["mode"], plan["clusters"]) == (1, 74)
+        plan, _ = _plan(lib, M64, 768, 3072, 0, 0)
+        assert (plan["bn"], plan["cg"], plan["clusters"]) == (192, 2, 74)
+        plan, _ = _plan(lib, M64, 2304, 768, 0, 0)
+        assert (plan["bn"], plan["cg"]) == (256, 2)
+    finally:
+        lib.vitk_set_sm_budget(prev)
+

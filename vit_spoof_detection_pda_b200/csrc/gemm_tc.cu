@@ -392,11 +392,12 @@ struct TcWork {
 struct TcWorkIter {
   int64_t cur, end;  // stream-K: unit cursor / end ; tile-strided: next tile / number of tiles
   int stride;
-  // `cg` CTAs (one cluster) walk the same sequence
-  __device__ __forceinline__ void init(const TcParams& p, int cg) {
+  // the CTAs of one cluster (CTA pair) walk the same sequence; `cluster` of `n_clusters`.  Host-callable: the plan query of
+  // the C-ABI (vitk_gemm_plan_items) walks the very same code, and tests/test_host_logic.py checks that the items of all
+  // clusters cover every (tile, k-block) unit exactly once.
+  __host__ __device__ __forceinline__ void init(const TcParams& p, int cluster, int n_clusters) {
     const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n;
-    const int cluster = blockIdx.x / cg;
-    stride = gridDim.x / cg;
+    stride = n_clusters;
     if (p.streamk == 2) {          // sliced split-K: exactly one (tile, k-slice) item per CTA (pair)
       cur = cluster;
       end = cur + 1;
@@ -409,13 +410,13 @@ struct TcWorkIter {
       end = tiles;
     }
   }
-  __device__ __forceinline__ bool next(const TcParams& p, TcWork& w) {
+  __host__ __device__ __forceinline__ bool next(const TcParams& p, TcWork& w) {
     if (!next_raw(p, w)) return false;
     w.tm = w.tile / p.n_tiles_n;     // consecutive CTAs walk along a tile row (column-first order measured identical)
     w.tn = w.tile % p.n_tiles_n;
     return true;
   }
-  __device__ __forceinline__ bool next_raw(const TcParams& p, TcWork& w) {
+  __host__ __device__ __forceinline__ bool next_raw(const TcParams& p, TcWork& w) {
     if (cur >= end) return false;
     if (p.streamk == 2) {
       const int tiles = p.n_tiles_m * p.n_tiles_n, S = (int)p.units_per_cta;
@@ -537,7 +538,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       TcWorkIter wi;
-      wi.init(p, CG);
+      wi.init(p, (int)blockIdx.x / CG, (int)gridDim.x / CG);
       TcWork w;
       const bool leader = elect_one();
       while (wi.next(p, w)) {
@@ -586,7 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       TcWorkIter wi;
-      wi.init(p, CG);
+      wi.init(p, (int)blockIdx.x / CG, (int)gridDim.x / CG);
       TcWork w;
       const bool leader = elect_one();
       const uint32_t a_hi = ((p.a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
@@ -629,7 +630,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     TcWorkIter wi;
-    wi.init(p, CG);
+    wi.init(p, (int)blockIdx.x / CG, (int)gridDim.x / CG);
     TcWork w;
     auto release_tmem = [&]() {
       tc_fence_before();
@@ -969,6 +970,77 @@ static int epilogue_kind(const EpiParams& ep) {
   }
 }
 
+// ---- work decomposition (pure host logic; p.I / p.J / p.R set).  Returns the number of clusters (CTAs / CG) to launch.
+static int tc_decompose(TcParams& p, bool accumulate, int BN, int CG) {
+  p.n_tiles_m = (p.I + TC_BM * CG - 1) / (TC_BM * CG);
+  p.n_tiles_n = p.J / BN;
+  p.kb_total = (p.R + TC_BK - 1) / TC_BK;
+  const int tiles = p.n_tiles_m * p.n_tiles_n;
+  const int slots = sm_count() / CG;            // persistent CTAs (CTA pairs)
+  int grid = tiles < slots ? tiles : slots;
+  p.streamk = 0;
+  p.units_per_cta = 0;
+  if (accumulate && g_tc_debug[1] != 1) {
+    const int64_t total = (int64_t)tiles * p.kb_total;
+    grid = total < slots ? (int)total : slots;
+    // knob 11 (A/B): at most this many partial sums per output tile -- fewer, longer-lived CTAs and less atomic traffic
+    // for the small weight-gradient GEMMs that run next to the dgrad chain
+    if (g_tc_debug[11] > 0 && grid > tiles * g_tc_debug[11]) grid = tiles * g_tc_debug[11];
+    p.streamk = 1;
+    p.units_per_cta = (total + grid - 1) / grid;
+    grid = (int)((total + p.units_per_cta - 1) / p.units_per_cta);
+    // Sliced split-K (knob 13 = 1 disables; 13 = p > 1: fill threshold in percent): when tiles x S fills >= 90 % of the
+    // slots, every CTA takes ONE k-slice of ONE tile.  All CTAs of a slice then sweep the same k range in lock-step -- the
+    // A panel of a tile row and the B panel of a tile column are fetched from DRAM once and hit in L2 for the other tiles
+    // -- and each CTA drains one accumulator instead of the two or three partial tiles a contiguous stream-K range straddles.
+    const int S = tiles > 0 ? slots / tiles : 0;
+    const int fill_pct = g_tc_debug[13] > 1 ? g_tc_debug[13] : 90;
+    if (g_tc_debug[13] != 1 && S >= 1 && tiles * S * 100 >= slots * fill_pct && p.kb_total >= 2 * S) {
+      p.streamk = 2;
+      p.units_per_cta = S;
+      grid = tiles * S;
+    }
+  }
+  return grid;
+}
+
+// ---- tile shape (pure host logic): CTA pair (CG = 2, 256 x BN) or single CTA (128 x BN), BN in {256, 192, 128}: minimise
+//   (waves of the persistent grid) x (k-blocks x max(tensor clocks, operand-ingest clocks) + per-tile overhead).
+// A 64-deep k-block costs 2*BN tensor clocks and pulls (128 + BN/CG) x 128 B into the SM; measured with the epilogue
+// and the loads switched off in turn (vitk_debug_set(7, .)), the mainloop sustains ~36 B/clk/SM of operand traffic
+// -- it, not the tensor pipe, bounds every shape here -- so wider tiles win unless they cost a whole extra wave: with
+// M = B*197 the tile count is rarely a multiple of the slot count (12608 x 768 on 74 CTA pairs: 150 tiles of 256x256 =
+// 3 waves for 2.03 waves of work, 200 tiles of 256x192 = 3 waves of 7/8 the bytes).
+static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* bn_out, int* cg_out) {
+  int cg = 0, bn = 0;
+  const int forced_bn = (g_tc_debug[2] == 128 || g_tc_debug[2] == 192 || g_tc_debug[2] == 256) ? g_tc_debug[2] : 0;
+  if (accumulate) {
+    bn = forced_bn ? forced_bn : (J % 256 == 0 ? 256 : 128);  // split-K / stream-K balance by themselves
+    cg = (I > TC_BM && g_tc_debug[4] != 1 && !(b_mn && (bn / 2) % 64 != 0)) ? 2 : 1;
+  } else {
+    const long kb = (R + TC_BK - 1) / TC_BK;
+    double best = -1.0;
+    for (int c : {2, 1}) {
+      if (c == 2 && (I <= TC_BM || g_tc_debug[4] == 1)) continue;
+      if (c == 1 && g_tc_debug[4] == 2 && best >= 0.0) continue;   // debug: pairs forced (when expressible)
+      const long slots = sm_count() / c;
+      const long tiles_m = (I + TC_BM * c - 1) / (TC_BM * c);
+      for (int cand : {256, 192, 128}) {
+        if (J % cand != 0) continue;
+        if (b_mn && (cand / c) % 64 != 0) continue;
+        if (forced_bn && forced_bn != cand) continue;
+        const long tiles = tiles_m * (J / cand);
+        const long waves = (tiles + slots - 1) / slots;
+        const double ingest = (128.0 + cand / c) * 128.0 / 36.0, mma = 2.0 * cand;
+        const double cost = (double)waves * ((double)kb * (ingest > mma ? ingest : mma) + 1200.0);
+        if (best < 0.0 || cost < best) { best = cost; bn = cand; cg = c; }
+      }
+    }
+  }
+  *bn_out = bn;
+  *cg_out = cg;
+}
+
 template <int BN, int CG, int EK>
 static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
   using Cfg = TcCfg<BN, CG, EK>;
@@ -1018,35 +1090,7 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
     if (a_mn) { p.a_sbo = TC_BK * 128; p.a_lbo = 1024; }
     if (b_mn) { p.b_sbo = TC_BK * 128; p.b_lbo = 1024; }
   }
-  p.n_tiles_m = (pr.I + TC_BM * CG - 1) / (TC_BM * CG);
-  p.n_tiles_n = pr.J / BN;
-  p.kb_total = (pr.R + TC_BK - 1) / TC_BK;
-  const int tiles = p.n_tiles_m * p.n_tiles_n;
-  const int slots = sm_count() / CG;            // persistent CTAs (CTA pairs)
-  int grid = tiles < slots ? tiles : slots;
-  p.streamk = 0;
-  p.units_per_cta = 0;
-  if (pr.ep.mode == E_ACCUM && g_tc_debug[1] != 1) {
-    const int64_t total = (int64_t)tiles * p.kb_total;
-    grid = total < slots ? (int)total : slots;
-    // knob 11 (A/B): at most this many partial sums per output tile -- fewer, longer-lived CTAs and less atomic traffic
-    // for the small weight-gradient GEMMs that run next to the dgrad chain
-    if (g_tc_debug[11] > 0 && grid > tiles * g_tc_debug[11]) grid = tiles * g_tc_debug[11];
-    p.streamk = 1;
-    p.units_per_cta = (total + grid - 1) / grid;
-    grid = (int)((total + p.units_per_cta - 1) / p.units_per_cta);
-    // Sliced split-K (knob 13 = 1 disables; 13 = p > 1: fill threshold in percent): when tiles x S fills >= 90 % of the slots, every CTA takes ONE k-slice of ONE
-    // tile.  All CTAs of a slice then sweep the same k range in lock-step -- the A panel of a tile row and the B panel of a
-    // tile column are fetched from DRAM once and hit in L2 for the other tiles -- and each CTA drains one accumulator
-    // instead of the two or three partial tiles a contiguous stream-K range straddles.
-    const int S = tiles > 0 ? slots / tiles : 0;
-    const int fill_pct = g_tc_debug[13] > 1 ? g_tc_debug[13] : 90;
-    if (g_tc_debug[13] != 1 && S >= 1 && tiles * S * 100 >= slots * fill_pct && p.kb_total >= 2 * S) {
-      p.streamk = 2;
-      p.units_per_cta = S;
-      grid = tiles * S;
-    }
-  }
+  const int grid = tc_decompose(p, pr.ep.mode == E_ACCUM, BN, CG);
   p.ep = pr.ep;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid * CG, 1, 1);
@@ -1092,39 +1136,9 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
   if (pr.ep.mode != E_STORE && pr.ep.mode != E_ACCUM && pr.ep.mode != E_BIAS_RESIDUAL && pr.ep.mode != E_PATCH &&
       pr.ep.out_dtype != VITK_BF16) { set_error("gemm_tc: epilogue expects bf16 output"); return VITK_ERR_UNSUPPORTED; }
   if (pr.J % 128 != 0 || pr.ep.ldc % 8 != 0) { set_error("gemm_tc: J must be a multiple of 128 (got %d)", pr.J); return VITK_ERR_UNSUPPORTED; }
-  // Tile shape: CTA pair (CG = 2, 256 x BN) or single CTA (128 x BN), BN in {256, 192, 128}: minimise
-  //   (waves of the persistent grid) x (k-blocks x max(tensor clocks, operand-ingest clocks) + per-tile overhead).
-  // A 64-deep k-block costs 2*BN tensor clocks and pulls (128 + BN/CG) x 128 B into the SM; measured with the epilogue
-  // and the loads switched off in turn (vitk_debug_set(7, .)), the mainloop sustains ~36 B/clk/SM of operand traffic
-  // -- it, not the tensor pipe, bounds every shape here -- so wider tiles win unless they cost a whole extra wave: with
-  // M = B*197 the tile count is rarely a multiple of the slot count (12608 x 768 on 74 CTA pairs: 150 tiles of 256x256 =
-  // 3 waves for 2.03 waves of work, 200 tiles of 256x192 = 3 waves of 7/8 the bytes).
   const bool b_mn = pr.lb.s_row == 1 && pr.lb.s_col != 1;   // MN-major B: staged in 64-row atoms
   int cg = 0, bn = 0;
-  const int forced_bn = (g_tc_debug[2] == 128 || g_tc_debug[2] == 192 || g_tc_debug[2] == 256) ? g_tc_debug[2] : 0;
-  if (pr.ep.mode == E_ACCUM) {
-    bn = forced_bn ? forced_bn : (pr.J % 256 == 0 ? 256 : 128);  // stream-K balances by itself
-    cg = (pr.I > TC_BM && g_tc_debug[4] != 1 && !(b_mn && (bn / 2) % 64 != 0)) ? 2 : 1;
-  } else {
-    const long kb = (pr.R + TC_BK - 1) / TC_BK;
-    double best = -1.0;
-    for (int c : {2, 1}) {
-      if (c == 2 && (pr.I <= TC_BM || g_tc_debug[4] == 1)) continue;
-      if (c == 1 && g_tc_debug[4] == 2 && best >= 0.0) continue;   // debug: pairs forced (when expressible)
-      const long slots = sm_count() / c;
-      const long tiles_m = (pr.I + TC_BM * c - 1) / (TC_BM * c);
-      for (int cand : {256, 192, 128}) {
-        if (pr.J % cand != 0) continue;
-        if (b_mn && (cand / c) % 64 != 0) continue;
-        if (forced_bn && forced_bn != cand) continue;
-        const long tiles = tiles_m * (pr.J / cand);
-        const long waves = (tiles + slots - 1) / slots;
-        const double ingest = (128.0 + cand / c) * 128.0 / 36.0, mma = 2.0 * cand;
-        const double cost = (double)waves * ((double)kb * (ingest > mma ? ingest : mma) + 1200.0);
-        if (best < 0.0 || cost < best) { best = cost; bn = cand; cg = c; }
-      }
-    }
-  }
+  tc_pick_tile(pr.I, pr.J, pr.R, pr.ep.mode == E_ACCUM, b_mn, &bn, &cg);
   if (bn == 0 || pr.J % bn != 0) { set_error("gemm_tc: no BLOCK_N divides J=%d", pr.J); return VITK_ERR_UNSUPPORTED; }
   const int ek = epilogue_kind(pr.ep);
   if (pr.ep.colsum && !(ek == EK_GELU_BWD || (ek == EK_STORE_BF16 && !pr.ep.bias) || pr.ep.mode == E_GELU_BWD)) {
@@ -1144,6 +1158,49 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
 }  // namespace vitk
 
 namespace vitk { void set_pdl(int on); }
+
+// Host-only view of the tcgen05 GEMM's work decomposition (no launch, no device access beyond the SM count): tile shape,
+// decomposition mode (0 whole-K tiles strided over the persistent clusters, 1 contiguous stream-K ranges, 2 sliced
+// split-K) and, for one cluster, the (tile, first k-block, end k-block) items it walks -- produced by the same
+// TcWorkIter the kernel's warps run.
+extern "C" int vitk_gemm_plan(int I, int J, int R, int accumulate, int b_mn_major, int* block_n, int* cta_group, int* mode,
+                              int* n_clusters, int* n_tiles_m, int* n_tiles_n, int* kb_total) {
+  VITK_CHECK_ARG(I > 0 && J > 0 && R > 0 && J % 128 == 0);
+  int bn = 0, cg = 0;
+  vitk::tc_pick_tile(I, J, R, accumulate != 0, b_mn_major != 0, &bn, &cg);
+  if (bn == 0 || J % bn != 0) { vitk::set_error("vitk_gemm_plan: no BLOCK_N divides J=%d", J); return VITK_ERR_UNSUPPORTED; }
+  vitk::TcParams p{};
+  p.I = I; p.J = J; p.R = R;
+  const int grid = vitk::tc_decompose(p, accumulate != 0, bn, cg);
+  if (block_n) *block_n = bn;
+  if (cta_group) *cta_group = cg;
+  if (mode) *mode = p.streamk;
+  if (n_clusters) *n_clusters = grid;
+  if (n_tiles_m) *n_tiles_m = p.n_tiles_m;
+  if (n_tiles_n) *n_tiles_n = p.n_tiles_n;
+  if (kb_total) *kb_total = p.kb_total;
+  return VITK_OK;
+}
+// items: [max_items][3] ints (tile, kb0, kb1); returns the number of items of `cluster` (or a negative VITK_ERR_*)
+extern "C" int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_mn_major, int cluster, int* items, int max_items) {
+  if (!(I > 0 && J > 0 && R > 0 && J % 128 == 0 && items && max_items > 0)) return -VITK_ERR_ARG;
+  int bn = 0, cg = 0;
+  vitk::tc_pick_tile(I, J, R, accumulate != 0, b_mn_major != 0, &bn, &cg);
+  if (bn == 0 || J % bn != 0) return -VITK_ERR_UNSUPPORTED;
+  vitk::TcParams p{};
+  p.I = I; p.J = J; p.R = R;
+  const int grid = vitk::tc_decompose(p, accumulate != 0, bn, cg);
+  if (cluster < 0 || cluster >= grid) return -VITK_ERR_ARG;
+  vitk::TcWorkIter wi;
+  wi.init(p, cluster, grid);
+  vitk::TcWork w;
+  int n = 0;
+  while (wi.next(p, w)) {
+    if (n < max_items) { items[3 * n] = w.tile; items[3 * n + 1] = w.kb0; items[3 * n + 2] = w.kb1; }
+    ++n;
+  }
+  return n;
+}
 extern "C" int vitk_debug_set(int key, int value) {
   if (key < 0 || key >= 16) return VITK_ERR_ARG;
   vitk::g_tc_debug[key] = value;
