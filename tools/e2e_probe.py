@@ -27,6 +27,9 @@ def step(x, y):
     return loss, met
 
 
+reader = pkg.HostScalars(dev)
+
+
 def run(name, prefetch, sync):
     def batches():
         for i in range(N):
@@ -39,10 +42,14 @@ def run(name, prefetch, sync):
     e0.record()
     for x, y in it:
         loss, met = step(x, y)
-        if sync == 2:
+        if sync == 3:
+            reader.push(loss, met["ncorrect"])
+        elif sync == 2:
             loss.item(); met["ncorrect"].item()
         elif sync == 1:
             loss.item()
+    if sync == 3:
+        reader.flush()
     e1.record()
     torch.cuda.synchronize()
     print(f"{name:46s} {e0.elapsed_time(e1) / N:7.3f} ms/step", flush=True)
@@ -53,3 +60,7 @@ run("device-resident, loss.item()", False, 1)
 run("device-resident, loss.item() + ncorrect.item()", False, 2)
 run("pinned host batches (prefetcher), no sync", True, 0)
 run("pinned host batches + both .item()", True, 2)
+run("device-resident + HostScalars", False, 3)
+run("pinned host batches + HostScalars (bench e2e)", True, 3)
+run("device-resident, no sync (again)", False, 0)
+
