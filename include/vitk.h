@@ -246,8 +246,13 @@ int vitk_model_fwd(const vitk_model* m, void* stream);
 int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream);
 int vitk_model_num_bwd_stages(int depth);
 
-/* debug knobs of the tcgen05 engine (tests only): key 0 = swap LBO/SBO of MN-major operands,
- * key 1 = 1 disables stream-K for accumulate (wgrad) GEMMs, key 2 = force BLOCK_N (128/192/256) */
+/* debug / A-B knobs (tests and timing experiments only; 0 = default everywhere): key 0 = swap LBO/SBO of MN-major
+ * operands, 1 = whole-K tiles for accumulate (wgrad) GEMMs, 2 = force BLOCK_N (128/192/256), 3 = attention variant
+ * (1 = mma.sync kernels), 4 = CTA group (1 single CTAs, 2 pairs), 5 = per-thread epilogue IO, 6 = no programmatic dependent
+ * launch, 7 = timing-only bit mask (skip epilogue body / operand loads / ...: results invalid), 8 = weight gradients on the
+ * caller's stream, 9 = LayerNorm forward CTAs per SM, 10 = low-priority weight-gradient stream, 11 = cap on stream-K partials
+ * per tile, 12 = whole qkv bias gradient from the attention kernel, 13 = 1 stream-K instead of sliced split-K (> 1: fill
+ * threshold in percent), 14 = TMA reduce-add epilogue for weight-gradient partial tiles.  INTEGRATION.md lists them. */
 int vitk_debug_set(int key, int value);
 /* Number of SMs the persistent kernels (GEMM, LayerNorm backward, ...) size their grids for; 0 = all.  The
  * data-parallel wrapper lowers it during backward so the NCCL all-reduce CTAs and the persistent GEMM CTAs

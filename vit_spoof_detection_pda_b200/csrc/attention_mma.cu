@@ -427,7 +427,7 @@ int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t
 int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum,
                  int batch, cudaStream_t st, int cs_sections) {
   if (attn_debug_variant() == 0) {
-    // the tcgen05 kernel's epilogue warps add the qkv bias gradient (column sums of dqkv) from their staging tiles
+    // the tcgen05 kernel's epilogue warps add the requested sections of the qkv bias gradient from their staging tiles
     // (cs_sections: which of the q | k | v sections -- bits 0 | 1 | 2 -- this launch is asked for)
     return attn_bwd_tc(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, st, cs_sections);
   } else {

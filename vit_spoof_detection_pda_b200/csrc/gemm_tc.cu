@@ -21,9 +21,11 @@
 // Per CTA and k-block that is 128 + BN/2 operand rows instead of 128 + BN: what bounds the kernel is the rate at which
 // one SM can take operand bytes in (~45 B/clk through TMA, tools/micro/tma_ingest.cu), not the tensor
 // pipe, so halving the B traffic is what moves it.
-// Work: output tiles strided over the persistent CTAs (CTA pairs); accumulate epilogues (wgrad) instead use stream-K --
-// the (tile, k-block) space is cut into one equal contiguous range per CTA and partial tiles are summed
-// with fp32 vector atomics, so 18..72-tile weight-gradient GEMMs still load all 148 SMs evenly.
+// Work: output tiles strided over the persistent CTAs (CTA pairs).  Accumulate epilogues (wgrad: 9..36 output tiles, a
+// 12,608-deep reduction) split K and sum partial tiles with fp32 vector atomics: sliced split-K -- cluster c owns k-slice
+// c / tiles of tile c % tiles, so all clusters of a slice sweep the same k range in lock-step and drain one accumulator
+// each -- when tiles x slices fill >= 90 % of the clusters, contiguous stream-K ranges over the (tile, k-block) space
+// otherwise (tc_decompose; the plan is queryable on the host: vitk_gemm_plan).
 // Every launch carries the programmatic-dependent-launch attribute: barrier init, TMEM allocation and tensor-map
 // prefetch run before pdl_sync(), i.e. under the tail of the previous kernel.
 //
