@@ -182,7 +182,10 @@ def run_ours(args):
     torch.manual_seed(42)
     model = pkg.ViTFaceAntiSpoofing(dropout=0.1, depth=12, precision="bf16").to(dev)
     model.train()
-    net = pkg.DataParallel(model, bucket_mb=float(os.environ.get("VITK_BUCKET_MB", "50"))) if world > 1 else model
+    # VITK_GRAD_COMM=bf16 (opt-in, not the reported configuration): 16-bit gradient all-reduce, torch DDP's bf16_compress_hook
+    comm_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(os.environ.get("VITK_GRAD_COMM", ""), None)
+    net = pkg.DataParallel(model, bucket_mb=float(os.environ.get("VITK_BUCKET_MB", "50")),
+                           grad_comm_dtype=comm_dtype) if world > 1 else model
     crit = pkg.FocalLoss(alpha=0.25, gamma=2.0)
     opt = pkg.FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4, adamw=False)
     total_sched_steps = 2 * (args.warmup + args.steps) + 64

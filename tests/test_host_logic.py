@@ -93,7 +93,7 @@ def _free_port():
     return p
 
 
-def _gloo_worker(rank, world, port, ranges, total, out):
+def _gloo_worker(rank, world, port, ranges, total, out, comm_dtype=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -101,24 +101,29 @@ def _gloo_worker(rank, world, port, ranges, total, out):
     g = torch.Generator().manual_seed(100 + rank)
     flat = torch.randn(total, generator=g)
     local = flat.clone()
-    b = GradBucketer(bucket_elems=total // 4)
+    b = GradBucketer(bucket_elems=total // 4, comm_dtype=comm_dtype)
     for lo, hi in ranges:
         b.add(flat, lo, hi)
     b.finish(flat)
     gathered = [torch.empty_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
-    expect = sum(gathered) / world
-    ok = torch.allclose(flat, expect, rtol=1e-6, atol=1e-7)
+    if comm_dtype is None:
+        expect = sum(gathered) / world
+        ok = torch.allclose(flat, expect, rtol=1e-6, atol=1e-7)
+    else:   # torch DDP's bf16_compress_hook arithmetic: cast, reduce in 16 bit, cast back, average
+        expect = sum(t.to(comm_dtype) for t in gathered).to(torch.float32) / world
+        ok = torch.allclose(flat, expect, rtol=1e-2, atol=1e-2) and flat.dtype == torch.float32
     out[rank] = (bool(ok), len(b.launched))
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_gloo_world2(pkg):
+@pytest.mark.parametrize("comm_dtype", [None, torch.bfloat16], ids=["fp32", "bf16-compressed"])
+def test_bucketed_allreduce_gloo_world2(pkg, comm_dtype):
     total = 10_000
     ranges = [(9_000, 10_000), (6_000, 9_000), (3_000, 6_000), (500, 3_000), (0, 500)]
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_gloo_worker, args=(2, _free_port(), ranges, total, out), nprocs=2, join=True)
+    mp.spawn(_gloo_worker, args=(2, _free_port(), ranges, total, out, comm_dtype), nprocs=2, join=True)
     assert out[0][0] and out[1][0]
     assert out[0][1] == out[1][1] >= 2
 

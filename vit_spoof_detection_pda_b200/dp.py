@@ -22,9 +22,13 @@ class GradBucketer:
     """Greedy merge of consecutive (descending, adjacent) flat ranges into buckets of >= bucket_elems,
     all-reduced (average) as soon as they close.  Device- and backend-agnostic (tested with gloo on CPU)."""
 
-    def __init__(self, bucket_elems: int, group=None):
+    def __init__(self, bucket_elems: int, group=None, comm_dtype: Optional[torch.dtype] = None):
         self.bucket_elems = int(bucket_elems)
         self.group = group
+        # None: the fp32 slices are all-reduced in place.  torch.bfloat16 / torch.float16 (opt-in): every bucket is cast to
+        # a 16-bit copy, that copy is all-reduced and written back into the fp32 slice at finish() -- the semantics of
+        # torch DDP's bf16_compress_hook / fp16_compress_hook: half the bytes on NVLink for two extra HBM passes.
+        self.comm_dtype = comm_dtype
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._open: Optional[Tuple[int, int]] = None
         self._works: List = []
@@ -40,11 +44,14 @@ class GradBucketer:
         if self.world == 1:
             return
         view = flat[lo:hi]
+        buf = view if self.comm_dtype is None else view.to(self.comm_dtype)
         backend = dist.get_backend(self.group)
         if backend == "nccl":
-            self._works.append((dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True), None))
+            work = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self._works.append((work, view, buf, False))
         else:  # gloo has no AVG
-            self._works.append((dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True), view))
+            work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._works.append((work, view, buf, True))
 
     def add(self, flat: torch.Tensor, lo: int, hi: int):
         """Register that flat[lo:hi] is final. Ranges must arrive adjacent and descending (or be disjoint)."""
@@ -65,9 +72,11 @@ class GradBucketer:
         if self._open is not None:
             self._launch(flat, *self._open)
             self._open = None
-        for work, view in self._works:
+        for work, view, buf, divide in self._works:
             work.wait()   # stream-ordered for NCCL (no host block), blocking for gloo
-            if view is not None:
+            if buf is not view:
+                view.copy_(buf)          # decompress: the reduced 16-bit bucket back into the fp32 gradient slice
+            if divide:
                 view.div_(self.world)
         self._works = []
 
@@ -77,13 +86,13 @@ class DataParallel(nn.Module):
     gradients averaged over ranks during backward."""
 
     def __init__(self, module: nn.Module, process_group=None, bucket_mb: float = 50.0, broadcast: bool = True,
-                 comm_sms: Optional[int] = None):
+                 comm_sms: Optional[int] = None, grad_comm_dtype: Optional[torch.dtype] = None):
         super().__init__()
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU, backend 'nccl')")
         self.module = module
         self.group = process_group
-        self.bucketer = GradBucketer(int(bucket_mb * 1e6 / 4), process_group)
+        self.bucketer = GradBucketer(int(bucket_mb * 1e6 / 4), process_group, comm_dtype=grad_comm_dtype)
         # SMs left to the NCCL all-reduce kernels while backward runs.  The persistent GEMM CTAs need a whole SM
         # each (~225 KB smem); if NCCL's CTAs hold some SMs the GEMM grid must shrink by that many, or the CTAs
         # that cannot become resident stall their tiles until the collective ends.  Set NCCL_MAX_CTAS (before
