@@ -208,3 +208,48 @@ def test_gemm_plan_bench_shapes_pick_documented_decompositions():
     finally:
         lib.vitk_set_sm_budget(prev)
 
+
+
+# ---------------------------------------------------------------------------------------------
+# checkpoint container of the reference (train_advanced.py:475-489 / test.py:167-188): written and read unchanged, on CPU
+# ---------------------------------------------------------------------------------------------
+def test_checkpoint_container_roundtrip_with_reference_model(pkg, tmp_path):
+    class Cfg:
+        model_name = "vit_base_patch16_224"
+        pretrained = False
+        num_classes = 2
+        dropout = 0.1
+
+    cfg = Cfg()
+    cfg.save_dir = str(tmp_path / "checkpoints_advanced")
+    ref = vo.OracleViTFaceAntiSpoofing(depth=12)
+    vo.seeded_init_(ref, seed=7)
+    opt = torch.optim.AdamW(ref.parameters(), lr=3e-4, weight_decay=0.05)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=10)
+    scaler = torch.amp.GradScaler("cuda", enabled=False)
+    # the reference side writes (its own save_checkpoint body == pkg.save_checkpoint), our module reads
+    path = pkg.save_checkpoint(ref, opt, sched, scaler, 3, {"val_acc": 0.9}, cfg, "best_model_run_test.pth")
+    ck = torch.load(path, weights_only=False)
+    assert list(ck.keys()) == ["epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict",
+                               "scaler_state_dict", "metrics", "config"]
+    assert ck["config"]["save_dir"] == cfg.save_dir          # vars(config), as the reference stores it
+    m = pkg.ViTFaceAntiSpoofing(Cfg)
+    m2, ck2 = pkg.load_checkpoint(str(path), m, "cpu")
+    assert m2 is m and ck2["epoch"] == 3 and ck2["metrics"] == {"val_acc": 0.9}
+    for (n, a), (_, b) in zip(m.state_dict().items(), ref.state_dict().items()):
+        assert torch.equal(a, b), n
+    # the published-weights variants evaluate_all_models.py:293-298 tolerates: 'state_dict' wrapper and a bare state dict
+    for i, obj in enumerate(({"state_dict": ref.state_dict()}, ref.state_dict())):
+        p2 = tmp_path / f"variant{i}.pth"
+        torch.save(obj, p2)
+        mm = pkg.ViTFaceAntiSpoofing(Cfg)
+        pkg.load_checkpoint(str(p2), mm, "cpu")
+        assert torch.equal(mm.state_dict()["classifier.5.weight"], ref.state_dict()["classifier.5.weight"])
+    # wrong architecture fails loudly (strict), a missing file raises the reference's exception type
+    bad = dict(ref.state_dict())
+    bad.pop("vit.norm.weight")
+    torch.save({"model_state_dict": bad}, tmp_path / "bad.pth")
+    with pytest.raises(RuntimeError):
+        pkg.load_checkpoint(str(tmp_path / "bad.pth"), pkg.ViTFaceAntiSpoofing(Cfg), "cpu")
+    with pytest.raises(FileNotFoundError):
+        pkg.load_checkpoint(str(tmp_path / "nope.pth"), m, "cpu")

@@ -5,6 +5,7 @@ Public API mirrors the reference's own objects for this path (/root/reference/tr
 ``torch.optim.AdamW`` (:592-597) and ``torch.nn.utils.clip_grad_norm_`` (:334).
 """
 from . import _lib
+from .checkpoint import extract_model_state_dict, load_checkpoint, save_checkpoint
 from .dp import DataParallel, DevicePrefetcher, HostScalars
 from .loss import FocalLoss, eval_postprocess
 from .metrics import ThresholdSweep, confusion_counts, find_optimal_threshold
@@ -12,4 +13,4 @@ from .module import ViTFaceAntiSpoofing
 from .optim import FusedAdam, FusedGradScaler, clip_grad_norm_
 
 __all__ = ["ViTFaceAntiSpoofing", "FocalLoss", "FusedAdam", "FusedGradScaler", "clip_grad_norm_", "DataParallel", "DevicePrefetcher", "HostScalars", "eval_postprocess", "ThresholdSweep",
-           "find_optimal_threshold", "confusion_counts", "_lib"]
+           "find_optimal_threshold", "confusion_counts", "save_checkpoint", "load_checkpoint", "extract_model_state_dict", "_lib"]
