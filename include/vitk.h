@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VITK_VERSION 100
+#define VITK_VERSION 101
 
 /* model constants (timm vit_base_patch16_224, train_advanced.py:33,190) */
 #define VITK_IMG 224
@@ -67,8 +67,8 @@ int vitk_version(void);
 const char* vitk_last_error_string(void);
 /* number of SMs / compute capability of the current device (host query; 0 on failure) */
 int vitk_device_info(int* sm_count, int* cc_major, int* cc_minor);
-/* process-wide default GEMM engine for VITK_PREC_BF16 (tests sweep both); returns previous value */
-int vitk_set_gemm_engine(int engine);
+/* 1 when this library is the development build (libvitk_dev.so: device-side tracer + timing experiments), else 0 */
+int vitk_is_dev_build(void);
 
 /* ---------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (768).  Replaces ATen native_layer_norm reached from timm
@@ -204,6 +204,10 @@ int vitk_grad_sumsq(const float* g, size_t n, float* partial, float* sumsq, void
 int vitk_adam_step(float* p, const float* g, float* m, float* v, void* p16, size_t n, double lr,
                    double beta1, double beta2, double eps, double weight_decay, int mode, int step,
                    float grad_mult, const float* sumsq, float max_norm, void* stream);
+/* g *= grad_mult * clipcoef in place, clipcoef as in vitk_adam_step (1 when sumsq == NULL or max_norm <= 0): the eager
+ * form of GradScaler.unscale_ (train_advanced.py:333) and clip_grad_norm_ (:334) for callers that pair them with stock
+ * torch pieces instead of the fused Adam pass */
+int vitk_grad_scale(float* g, size_t n, float grad_mult, const float* sumsq, float max_norm, void* stream);
 /* p16 = bf16(p) over a flat buffer (after load_state_dict / external optimizers) */
 int vitk_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 
@@ -227,13 +231,19 @@ typedef struct vitk_model {
   const float* mask2;
   const float* dlogits;                         /* [B][C] fp32, input of backward                     */
   int32_t frozen_backbone;                      /* 1: backward stops after the head (config 4)        */
-  int32_t reserved;
+  int32_t sm_budget;                            /* > 0: SMs the persistent kernels of THIS call may occupy (the rest is
+                                                   left to a collective in flight, see dp.py); 0 = all                 */
   /* input edge: when images_u8 != NULL the patch loader reads uint8 HWC pixels [B][224][224][3]
    * and applies ToTensor + Normalize (train_advanced.py:174-175 / 180-181: x/255, (x - mean[c]) / std[c], fp32, in that
    * order) itself; `images` is then ignored */
   const uint8_t* images_u8;
   float norm_mean[3], norm_std[3];
+  int32_t flags;                                /* VITK_FLAG_* */
+  int32_t reserved;
 } vitk_model;
+/* keep the weight-gradient GEMMs on the caller's stream instead of the library's side stream (bench.py's per-launch
+ * timing: kernels must not overlap while they are bracketed by events) */
+#define VITK_FLAG_WGRAD_INLINE 1
 
 /* n_tensors = 4 + 12*depth + 8; offsets/sizes in elements, state_dict order. returns total elements */
 int64_t vitk_param_layout(int depth, int num_classes, int64_t* offsets, int64_t* sizes, int max_tensors);
@@ -246,18 +256,23 @@ int vitk_model_fwd(const vitk_model* m, void* stream);
 int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream);
 int vitk_model_num_bwd_stages(int depth);
 
-/* debug / A-B knobs (tests and timing experiments only; 0 = default everywhere): key 0 = swap LBO/SBO of MN-major
- * operands, 1 = whole-K tiles for accumulate (wgrad) GEMMs, 2 = force BLOCK_N (128/192/256), 3 = attention variant
- * (1 = mma.sync kernels), 4 = CTA group (1 single CTAs, 2 pairs), 5 = per-thread epilogue IO, 6 = no programmatic dependent
- * launch, 7 = timing-only bit mask (skip epilogue body / operand loads / ...: results invalid), 8 = weight gradients on the
- * caller's stream, 9 = LayerNorm forward CTAs per SM, 10 = low-priority weight-gradient stream, 11 = cap on stream-K partials
- * per tile, 12 = whole qkv bias gradient from the attention kernel, 13 = 1 stream-K instead of sliced split-K (> 1: fill
- * threshold in percent), 14 = TMA reduce-add epilogue for weight-gradient partial tiles.  INTEGRATION.md lists them. */
+/* Tuning overrides for tests and A/B timing -- process-wide, 0 = default everywhere, every one of them yields valid
+ * results: key 1 = whole-K tiles for accumulate (wgrad) GEMMs, 2 = force BLOCK_N (128/192/256), 4 = CTA group (1 single
+ * CTAs, 2 pairs), 5 = per-thread epilogue IO, 6 = no programmatic dependent launch, 13 = 1 stream-K instead of sliced
+ * split-K (> 1: fill threshold in percent).  The development build (libvitk_dev.so) adds: 0 = swap LBO/SBO of MN-major
+ * operands, 7 = timing-only bit mask (skip epilogue body / operand loads / ...: RESULTS INVALID), 12 = whole qkv bias
+ * gradient from the attention kernel.  The release library rejects those keys: it contains no result-invalidating path. */
 int vitk_debug_set(int key, int value);
-/* Number of SMs the persistent kernels (GEMM, LayerNorm backward, ...) size their grids for; 0 = all.  The
- * data-parallel wrapper lowers it during backward so the NCCL all-reduce CTAs and the persistent GEMM CTAs
- * (one per SM, ~225 KB of shared memory each) can all be resident at once.  Returns the previous value. */
+/* SM budget of the CALLING THREAD for stand-alone kernel calls and the plan queries below (thread-local; 0 = all SMs;
+ * returns the previous value).  The whole-model drivers take theirs per call from vitk_model.sm_budget. */
 int vitk_set_sm_budget(int n);
+/* Device-side tracer (development build only; VITK_ERR_UNSUPPORTED otherwise): thread 0 of every CTA of every libvitk
+ * kernel appends (globaltimer ns, kernel id << 48 | phase << 40 | SM id << 24 | block index, aux) -- three 64-bit words
+ * -- to `buf` (device memory, `bytes` bytes: word 0 = number of marks, word 1 = capacity, marks from word 2).  Phase 0 = CTA
+ * started, 1 = stream dependencies satisfied, 2 = CTA finished.  tools/step_timeline.py turns that into a per-kernel
+ * timeline of a real training step (side stream and programmatic dependent launch left on). */
+int vitk_trace_start(void* buf, size_t bytes);
+int vitk_trace_stop(void);
 /* Host-only view of the tcgen05 GEMM's work decomposition for C[I][J] += over R (no launch; only the SM count / budget is
  * consulted): tile width BLOCK_N, CTA group (1 single CTAs with 128-row tiles, 2 CTA pairs with 256-row tiles), mode
  * (0 whole-K tiles strided over the persistent clusters, 1 contiguous stream-K ranges, 2 sliced split-K: one k-slice of

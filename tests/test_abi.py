@@ -36,7 +36,10 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_version_and_error_string(lib):
     l = lib.load()
-    assert l.vitk_version() == 100
+    assert l.vitk_version() == 101
+    assert l.vitk_is_dev_build() == 0
+    assert l.vitk_trace_start(None, 0) != 0          # the tracer exists only in libvitk_dev.so
+    assert l.vitk_debug_set(7, 1) != 0               # the release build has no result-invalidating knob
     assert isinstance(l.vitk_last_error_string(), bytes)
 
 

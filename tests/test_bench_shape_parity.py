@@ -1,0 +1,171 @@
+"""Parity at the BENCHMARKED configuration (BASELINE configs[1]: depth 12, batch 64 -> M = 12,608 token rows), where the
+sliced split-K weight gradients, the 2-wave forward / dgrad tile grids and the full-size attention grids take the
+decompositions bench.py times ("missing 2"):
+
+  * bf16 path: logits and ALL 156 gradients against the fp32 validation path of the same weights
+    (north_star: <= 2e-2 max-abs; and <= 0.1 of each tensor's scale);
+  * fp32 validation path against the oracle executed on the GPU in fp32 with TF32 off (<= 1e-4 relative);
+  * the twelve GEMM shapes of one training step (profiles/r1_cublas_yardstick.md) through the C-ABI against
+    x.float() @ w.float().T, including the head-major qkv operands and every fused epilogue.
+Reference call sites: /root/reference/train_advanced.py:322-338 (step), :203 (encoder forward).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vit_oracle as vo  # checker only
+
+if torch.cuda.is_available():
+    import vit_spoof_detection_pda_b200 as pkg
+    from vit_spoof_detection_pda_b200 import _lib as L
+    import kernels_api as K
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    DEV = torch.device("cuda:0")
+else:
+    pkg = L = K = DEV = None
+
+B = 64
+M = B * 197
+
+
+def _pair(precision, seed=42):
+    ref = vo.OracleViTFaceAntiSpoofing(dropout=0.0, depth=12)
+    vo.seeded_init_(ref, seed=seed)
+    m = pkg.ViTFaceAntiSpoofing(dropout=0.0, depth=12, precision=precision)
+    m.load_state_dict(ref.state_dict(), strict=True)
+    return ref, m.to(DEV).train()
+
+
+def _fwd_bwd(m, images, labels):
+    out = m(images)
+    loss = pkg.FocalLoss(0.25, 2.0)(out, labels)
+    loss.backward()
+    torch.cuda.synchronize()
+    return out.detach().clone(), {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+
+
+def test_bf16_step_bs64_all_gradients_vs_fp32_validation_path():
+    images, labels = vo.synthetic_batch(B, seed=21)
+    images, labels = images.to(DEV), labels.to(DEV)
+    _, m32 = _pair("fp32")
+    out32, g32 = _fwd_bwd(m32, images, labels)
+    del m32
+    torch.cuda.empty_cache()
+    _, m16 = _pair("bf16")
+    out16, g16 = _fwd_bwd(m16, images, labels)
+    err = float((out16 - out32).abs().max())
+    assert err < 2e-2, err
+    margin = (out32[:, 1] - out32[:, 0]).abs()
+    decided = margin > 2 * err
+    assert torch.equal(out16.argmax(1)[decided], out32.argmax(1)[decided])
+    assert len(g16) == 156
+    worst_abs, worst_rel = ("", 0.0), ("", 0.0)
+    for n in g32:
+        a, b = g16[n].double(), g32[n].double()
+        e_abs = float((a - b).abs().max())
+        e_rel = e_abs / max(float(b.abs().max()), 1e-30)
+        if e_abs > worst_abs[1]:
+            worst_abs = (n, e_abs)
+        if e_rel > worst_rel[1]:
+            worst_rel = (n, e_rel)
+    print(f"bs64 bf16 vs fp32-validate: logits max-abs {err:.3e}; grads worst max-abs {worst_abs}, worst rel-to-scale {worst_rel}")
+    assert worst_abs[1] < 2e-2, worst_abs
+    assert worst_rel[1] < 0.1, worst_rel
+
+
+def test_fp32_step_bs64_vs_oracle_on_gpu():
+    ref, m = _pair("fp32")
+    ref = ref.to(DEV).train()
+    images, labels = vo.synthetic_batch(B, seed=22)
+    images, labels = images.to(DEV), labels.to(DEV)
+    out_r = ref(images)
+    vo.OracleFocalLoss(0.25, 2.0)(out_r, labels).backward()
+    out, g = _fwd_bwd(m, images, labels)
+    scale = float(out_r.abs().max())
+    assert float((out - out_r).abs().max()) <= 1e-4 * scale
+    worst = ("", 0.0)
+    for n, q in ref.named_parameters():
+        e = float((g[n].double() - q.grad.double()).abs().max() / q.grad.double().abs().max().clamp_min(1e-30))
+        if e > worst[1]:
+            worst = (n, e)
+    print(f"bs64 fp32-validate vs oracle(GPU, TF32 off): worst gradient rel err {worst}")
+    assert worst[1] < 1e-4, worst
+
+
+def _randn(*shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, generator=g, device=DEV) * scale
+
+
+# (name, N = out features, K = in features) of the four Linear layers of a block
+LINEARS = [("qkv", 2304, 768), ("proj", 768, 768), ("fc1", 3072, 768), ("fc2", 768, 3072)]
+
+
+@pytest.mark.parametrize("name,N,Kd", LINEARS, ids=[l[0] for l in LINEARS])
+def test_bench_gemm_shapes_m12608(name, N, Kd):
+    """forward (with the epilogue the model uses), dgrad and wgrad of each Linear at M = 12,608 on the tcgen05 engine."""
+    E = L.ENGINE_TCGEN05
+    x = _randn(M, Kd, seed=31).to(torch.bfloat16)
+    w = _randn(N, Kd, seed=32, scale=0.03).to(torch.bfloat16)
+    b = _randn(N, seed=33, scale=0.5)
+    dy = _randn(M, N, seed=34).to(torch.bfloat16)
+    ref = x.float() @ w.float().t() + b
+    tol = 2e-2
+    if name == "qkv":
+        y = K.linear_fwd(x, w, b, L.EPI_QKV_SCATTER, E)
+        assert K.rel_err(K.from_headmajor(y).float(), ref) < tol
+    elif name == "fc1":
+        g, dg = K.linear_fwd(x, w, b, L.EPI_BIAS_GELU, E)
+        ur = ref.to(torch.bfloat16).float().requires_grad_(True)
+        gr = F.gelu(ur)
+        gr.sum().backward()
+        assert K.rel_err(g.float(), gr) < tol and K.rel_err(dg.float(), ur.grad) < tol
+    else:
+        res = _randn(M, N, seed=35)
+        y = K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, E, residual=res)
+        assert K.rel_err(y, ref + res) < tol
+    del ref
+    # dgrad: dX = dY W  (qkv: head-major dY; fc2: x GELU' with the fused fc1 bias-gradient column sums; proj: fused column sums)
+    dref = dy.float() @ w.float()
+    if name == "qkv":
+        dx = K.linear_dgrad(K.to_headmajor(dy), w, E, dy_layout=L.LAYOUT_HEADMAJOR)
+        assert K.rel_err(dx.float(), dref) < tol
+    elif name == "fc2":
+        u = _randn(M, Kd, seed=36).to(torch.bfloat16)
+        dx, cs = K.linear_dgrad(dy, w, E, gelu_grad=u, want_colsum=True)
+        assert K.rel_err(dx.float(), dref * u.float()) < tol
+        assert K.rel_err(cs, dx.float().sum(0)) < 2e-3
+    elif name == "proj":
+        dx, cs = K.linear_dgrad(dy, w, E, want_colsum=True)
+        assert K.rel_err(dx.float(), dref) < tol
+        assert K.rel_err(cs, dx.float().sum(0)) < 2e-3
+    else:
+        dx = K.linear_dgrad(dy, w, E)
+        assert K.rel_err(dx.float(), dref) < tol
+    del dref
+    # wgrad: dW = dY^T X over 12,608 rows (sliced split-K where it fills the machine, stream-K ranges for qkv)
+    wref = dy.float().t() @ x.float()
+    if name == "qkv":
+        dw, _ = K.linear_wgrad(K.to_headmajor(dy), x, N, Kd, E, dy_layout=L.LAYOUT_HEADMAJOR)
+    else:
+        dw, _ = K.linear_wgrad(dy, x, N, Kd, E)
+    assert K.rel_err(dw, wref) < 5e-3      # fp32 accumulation of exact bf16 products: only the summation order differs
+
+
+def test_attention_bs64_vs_sdpa():
+    """the full-size attention grids (768 (batch, head) items on 148 persistent CTAs: 5.2 items per CTA)."""
+    qkv = _randn(M, 2304, seed=41, scale=1.0).to(torch.bfloat16)
+    dout = _randn(M, 768, seed=42).to(torch.bfloat16)
+    q, k, v = [t.reshape(B, 197, 12, 64).permute(0, 2, 1, 3).float().requires_grad_(True) for t in qkv.split(768, dim=1)]
+    o = F.scaled_dot_product_attention(q, k, v)
+    o.backward(dout.float().reshape(B, 197, 12, 64).permute(0, 2, 1, 3))
+    out, lse = K.attn_fwd(K.to_headmajor(qkv), B)
+    ref_o = o.permute(0, 2, 1, 3).reshape(M, 768)
+    assert K.rel_err(out.float(), ref_o) < 2e-2
+    dqkv, cs = K.attn_bwd(K.to_headmajor(qkv), out, dout, lse, B)
+    ref_d = torch.cat([t.grad.permute(0, 2, 1, 3).reshape(M, 768) for t in (q, k, v)], dim=1)
+    assert K.rel_err(K.from_headmajor(dqkv).float(), ref_d) < 3e-2
+    assert K.rel_err(cs, K.from_headmajor(dqkv).float().sum(0)) < 5e-3

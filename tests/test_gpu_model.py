@@ -59,6 +59,10 @@ def test_state_dict_contract_and_roundtrip(tmp_path):
 
 @pytest.mark.parametrize("depth", [2, 12])
 def test_fp32_forward_matches_reference_golden(golden_dir, depth):
+    """Golden from the REAL reference wrapper / head / loss classes run over ``OracleViTEncoder`` (timm is stubbed,
+    oracle/make_golden.py): this pins wrapper + classifier head + focal loss against the reference's own code.  For the
+    encoder it is circular (the oracle checks itself); the encoder restatement is pinned separately by the live
+    torchvision cross-check (tests/test_oracle_golden.py) and the CUDA encoder by the gradient-level tests below."""
     g = torch.load(os.path.join(golden_dir, "model_golden.pt"), weights_only=False)[f"depth{depth}"]
     _, m = make_pair(depth, "fp32")
     images, labels = vo.synthetic_batch(g["batch"], seed=g["seed"])

@@ -31,9 +31,17 @@ def test_fused_grad_scaler_state_machine_without_gpu():
     assert s2.state_dict() == sd and set(sd) == set(t.state_dict())
 
 
+# (lazy unscale, this package's clip, FusedAdam): every mix of fused and stock pieces the reference loop can be run with
+# must give the reference's result (the lazy variants silently mis-clipped when mixed with stock pieces)
+COMBOS = [("eager", "pkgclip", "fused"), ("lazy", "pkgclip", "fused"), ("eager", "stockclip", "fused"),
+          ("eager", "pkgclip", "stockopt"), ("eager", "stockclip", "stockopt")]
+
+
 @pytest.mark.gpu
-def test_fused_grad_scaler_follows_torch_grad_scaler():
+@pytest.mark.parametrize("combo", COMBOS, ids=lambda c: "-".join(c))
+def test_fused_grad_scaler_follows_torch_grad_scaler(combo):
     import vit_spoof_detection_pda_b200 as pkg
+    unscale_mode, clip_mode, opt_mode = combo
     dev = torch.device("cuda:0")
     ref = vo.OracleViTFaceAntiSpoofing(dropout=0.0, depth=2)
     vo.seeded_init_(ref, seed=11)
@@ -43,9 +51,13 @@ def test_fused_grad_scaler_follows_torch_grad_scaler():
     ref.train()
     crit_ref, crit = vo.OracleFocalLoss(0.25, 2.0), pkg.FocalLoss(0.25, 2.0)
     opt_ref = torch.optim.AdamW(ref.parameters(), lr=3e-4, weight_decay=0.05)
-    opt = pkg.FusedAdam(m.parameters(), lr=3e-4, weight_decay=0.05, adamw=True)
+    if opt_mode == "fused":
+        opt = pkg.FusedAdam(m.parameters(), lr=3e-4, weight_decay=0.05, adamw=True)
+    else:
+        opt = torch.optim.AdamW(m.parameters(), lr=3e-4, weight_decay=0.05)
+    clip = pkg.clip_grad_norm_ if clip_mode == "pkgclip" else torch.nn.utils.clip_grad_norm_
     sc_ref = torch.amp.GradScaler("cpu", init_scale=1024.0, growth_interval=2)
-    sc = pkg.FusedGradScaler(init_scale=1024.0, growth_interval=2)
+    sc = pkg.FusedGradScaler(init_scale=1024.0, growth_interval=2, lazy_unscale=(unscale_mode == "lazy"))
     for step in range(7):
         images, labels = vo.synthetic_batch(4, seed=100 + step)
         poison = step in (2, 3)
@@ -65,7 +77,7 @@ def test_fused_grad_scaler_follows_torch_grad_scaler():
         if poison:
             next(m.parameters()).grad.view(-1)[0] = float("inf")
         sc.unscale_(opt)
-        norm = pkg.clip_grad_norm_(m.parameters(), 1.0)
+        norm = clip(m.parameters(), 1.0)
         sc.step(opt)
         sc.update()
         opt.zero_grad(set_to_none=True)
@@ -78,4 +90,32 @@ def test_fused_grad_scaler_follows_torch_grad_scaler():
         err = float((p.detach().cpu() - q.detach()).abs().max())
         # 5 applied AdamW steps of lr 3e-4 move a weight by up to 1.5e-3; Adam's sign-like update amplifies the fp32
         # summation-order noise of near-zero gradients, so the bound is relative to that total movement (3 %)
-        assert err <= 5e-5, (n, err)
+        assert err <= 5e-5, (combo, n, err)
+
+
+@pytest.mark.gpu
+def test_lazy_unscale_rejects_stock_optimizer():
+    import vit_spoof_detection_pda_b200 as pkg
+    m = pkg.ViTFaceAntiSpoofing(dropout=0.0, depth=1, precision="fp32").to("cuda:0").train()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    sc = pkg.FusedGradScaler(lazy_unscale=True)
+    images, labels = vo.synthetic_batch(2, seed=1)
+    sc.scale(pkg.FocalLoss()(m(images.cuda()), labels.cuda())).backward()
+    with pytest.raises(TypeError):
+        sc.unscale_(opt)
+
+
+@pytest.mark.gpu
+def test_pkg_clip_scales_in_place_without_fused_adam():
+    """clip_grad_norm_ of this package in front of a stock torch optimizer must clip right away (there is no fused pass
+    to fold it into)."""
+    import vit_spoof_detection_pda_b200 as pkg
+    m = pkg.ViTFaceAntiSpoofing(dropout=0.0, depth=1, precision="fp32").to("cuda:0").train()
+    images, labels = vo.synthetic_batch(4, seed=3)
+    (pkg.FocalLoss()(m(images.cuda()), labels.cuda()) * 1000.0).backward()
+    before = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).norm()
+    ret = pkg.clip_grad_norm_(m.parameters(), 0.5)
+    after = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).norm()
+    assert float(before) > 0.5
+    assert abs(float(ret) - float(before)) <= 1e-4 * float(before)
+    assert abs(float(after) - 0.5) <= 1e-4

@@ -35,19 +35,14 @@ def focal(logits, y, alpha=0.25, gamma=2.0):
     return (alpha * (1 - pt) ** gamma * ce).mean()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    a = ap.parse_args()
-    dev = torch.device("cuda:0")
+def run(batch=64, steps=20, warmup=5, with_inference=True, device="cuda:0"):
+    dev = torch.device(device)
     torch.manual_seed(42)
     torch.backends.cuda.matmul.allow_tf32 = True
     model = EagerPAD().to(dev).train()
     opt = torch.optim.AdamW(model.parameters(), lr=1e-5, weight_decay=1e-4, fused=True)
-    x = torch.randn(a.batch, 3, 224, 224, device=dev)
-    y = torch.randint(0, 2, (a.batch,), device=dev)
+    x = torch.randn(batch, 3, 224, 224, device=dev)
+    y = torch.randint(0, 2, (batch,), device=dev)
 
     def step():
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -59,16 +54,21 @@ def main():
         opt.zero_grad(set_to_none=True)
         return loss
 
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.steps
+    ms = e0.elapsed_time(e1) / steps
+    res = {"impl": "torch_eager", "torch": torch.__version__, "batch": batch, "steps": steps,
+           "ms_per_step": ms, "img_s": batch / (ms * 1e-3), "tflops": batch / (ms * 1e-3) * 105.150e9 / 1e12,
+           "what": "torchvision vit_b_16 + the reference head, bf16 autocast, SDPA, clip_grad_norm_, fused AdamW (library kernels only)"}
+    if not with_inference:
+        return res
 
     # batch-1 eval latency, eager launches (what test.py does) and CUDA-graph replay
     model.eval()
@@ -112,11 +112,18 @@ def main():
         infer = 256 * 10 / (e0.elapsed_time(e1) * 1e-3)
     lat.sort()
     glat.sort()
-    print(json.dumps({"impl": "torch_eager", "torch": torch.__version__, "batch": a.batch, "steps": a.steps,
-                      "ms_per_step": ms, "img_s": a.batch / (ms * 1e-3),
-                      "tflops": a.batch / (ms * 1e-3) * 105.150e9 / 1e12,
-                      "bs1_latency_ms_p50_eager": lat[len(lat) // 2], "bs1_latency_ms_p50_graph": glat[len(glat) // 2],
-                      "bs256_infer_img_s": infer}))
+    res.update({"bs1_latency_ms_p50_eager": lat[len(lat) // 2], "bs1_latency_ms_p50_graph": glat[len(glat) // 2],
+                "bs256_infer_img_s": infer})
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    a = ap.parse_args()
+    print(json.dumps(run(a.batch, a.steps, a.warmup)))
 
 
 if __name__ == "__main__":

@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvitk.so")
+# VITK_LIB=dev selects the development build (libvitk_dev.so: device-side tracer, timing experiments); tools only
+LIB_PATH = os.path.join(HERE, "libvitk_dev.so" if os.environ.get("VITK_LIB") == "dev" else "libvitk.so")
+FLAG_WGRAD_INLINE = 1
 
 # enums (mirror include/vitk.h)
 F32, BF16 = 0, 1
@@ -27,8 +29,9 @@ class VitkModel(C.Structure):
     _fields_ = [("batch", C.c_int32), ("depth", C.c_int32), ("num_classes", C.c_int32), ("precision", C.c_int32),
                 ("training", C.c_int32), ("engine", C.c_int32),
                 ("params", vp), ("params16", vp), ("grads", vp), ("workspace", vp), ("images", vp), ("logits", vp),
-                ("mask1", vp), ("mask2", vp), ("dlogits", vp), ("frozen_backbone", C.c_int32), ("reserved", C.c_int32),
-                ("images_u8", vp), ("norm_mean", C.c_float * 3), ("norm_std", C.c_float * 3)]
+                ("mask1", vp), ("mask2", vp), ("dlogits", vp), ("frozen_backbone", C.c_int32), ("sm_budget", C.c_int32),
+                ("images_u8", vp), ("norm_mean", C.c_float * 3), ("norm_std", C.c_float * 3),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/vitk.h declares
@@ -36,7 +39,9 @@ PROTOTYPES = {
     "vitk_version": (i32, []),
     "vitk_last_error_string": (C.c_char_p, []),
     "vitk_device_info": (i32, [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
-    "vitk_set_gemm_engine": (i32, [i32]),
+    "vitk_is_dev_build": (i32, []),
+    "vitk_trace_start": (i32, [vp, sz]),
+    "vitk_trace_stop": (i32, []),
     "vitk_layernorm_fwd": (i32, [vp, i64, vp, vp, vp, i32, vp, vp, i32, f32, vp]),
     "vitk_layernorm_bwd": (i32, [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "vitk_linear_fwd": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
@@ -55,6 +60,7 @@ PROTOTYPES = {
     "vitk_threshold_counts": (i32, [vp, i32, vp, vp]),
     "vitk_grad_sumsq_scratch_floats": (sz, []),
     "vitk_grad_sumsq": (i32, [vp, sz, vp, vp, vp]),
+    "vitk_grad_scale": (i32, [vp, sz, f32, vp, f32, vp]),
     "vitk_adam_step": (i32, [vp, vp, vp, vp, vp, sz, f64, f64, f64, f64, f64, i32, i32, f32, vp, f32, vp]),
     "vitk_cast_f32_to_bf16": (i32, [vp, vp, sz, vp]),
     "vitk_param_layout": (i64, [i32, i32, C.POINTER(i64), C.POINTER(i64), i32]),
@@ -89,7 +95,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.vitk_version() != 100:
+    if lib.vitk_version() != 101:
         raise RuntimeError("libvitk.so version mismatch: rebuild")
     if os.environ.get("VITK_NO_PDL") == "1":   # A/B timing: plain stream order instead of programmatic dependent launch
         lib.vitk_debug_set(6, 1)

@@ -9,6 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvitk.so")
+LIB_DEV = os.path.join(HERE, "libvitk_dev.so")   # -DVITK_DEV: device-side tracer + timing experiments (tools only)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -25,10 +26,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> str:
+def build_lib(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
+    """Release library by default; dev=True builds libvitk_dev.so (same sources, -DVITK_DEV) next to it."""
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "vitk.h"))
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_dev" if dev else "build")
+    flags = FLAGS + (["-DVITK_DEV"] if dev else [])
+    lib = LIB_DEV if dev else LIB
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     for s in sources():
@@ -39,7 +43,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        r = subprocess.run([NVCC, *flags, "-c", src, "-o", obj], capture_output=True, text=True)
         return src, r
 
     with cf.ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
@@ -49,13 +53,15 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {src}")
     objs = [os.path.join(objdir, s[:-3] + ".o") for s in sources()]
-    if force or jobs or _stale(LIB, objs):
-        r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+    if force or jobs or _stale(lib, objs):
+        r = subprocess.run([NVCC, "-shared", "-o", lib, *objs, "-lcudart"], capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--dev" in sys.argv:
+        print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv, dev=True))

@@ -17,7 +17,7 @@ constexpr int SUMSQ_MAX_CTAS = 1024;
 
 __global__ void __launch_bounds__(256)
 sumsq_partial_kernel(const float* __restrict__ g, size_t n, float* __restrict__ partial) {
-  pdl_sync();
+  pdl_sync_traced(TK_SUMSQ);
   __shared__ float red[8];
   float s = 0.f;
   const size_t n4 = n / 4;
@@ -36,11 +36,12 @@ sumsq_partial_kernel(const float* __restrict__ g, size_t n, float* __restrict__ 
     for (int w = 0; w < 8; ++w) t += red[w];
     partial[blockIdx.x] = t;
   }
+  trace_end(TK_SUMSQ);
 }
 
 __global__ void __launch_bounds__(256)
 sumsq_final_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ sumsq) {
-  pdl_sync();
+  pdl_sync_traced(TK_SUMSQ);
   __shared__ float red[8];
   float s = 0.f;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
@@ -52,6 +53,7 @@ sumsq_final_kernel(const float* __restrict__ partial, int nparts, float* __restr
     for (int w = 0; w < 8; ++w) t += red[w];
     sumsq[0] = t;
   }
+  trace_end(TK_SUMSQ);
 }
 
 struct AdamArgs {
@@ -72,7 +74,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             bf16* __restrict__ p16, size_t n, AdamArgs a, const float* __restrict__ sumsq) {
-  pdl_sync();
+  pdl_sync_traced(TK_ADAM);
   float gm = a.grad_mult;
   if (sumsq && a.max_norm > 0.f) {
     const float total = sqrtf(sumsq[0]) * a.grad_mult;
@@ -105,11 +107,33 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
       p[i] = pv; m[i] = mv; v[i] = vv;
       if (p16) p16[i] = __float2bfloat16_rn(pv);
     }
+  trace_end(TK_ADAM);
+}
+
+// g *= grad_mult * clipcoef in place (eager unscale / clip for callers that mix the fused pieces with stock torch ones:
+// optim.py FusedGradScaler.unscale_, clip_grad_norm_ without a FusedAdam)
+__global__ void __launch_bounds__(256)
+grad_scale_kernel(float* __restrict__ g, size_t n, float grad_mult, const float* __restrict__ sumsq, float max_norm) {
+  pdl_sync_traced(TK_SUMSQ);
+  float gm = grad_mult;
+  if (sumsq && max_norm > 0.f) {
+    const float total = sqrtf(sumsq[0]) * grad_mult;
+    gm *= fminf(1.0f, max_norm / (total + 1e-6f));
+  }
+  const size_t n4 = n / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(g)[i];
+    v.x *= gm; v.y *= gm; v.z *= gm; v.w *= gm;
+    reinterpret_cast<float4*>(g)[i] = v;
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) g[i] *= gm;
+  trace_end(TK_SUMSQ);
 }
 
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
-  pdl_sync();
+  pdl_sync_traced(TK_CAST);
   const size_t n4 = n / 4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(src)[i];
@@ -120,6 +144,7 @@ cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n
   }
   if (blockIdx.x == 0)
     for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
+  trace_end(TK_CAST);
 }
 
 static int stream_grid(size_t n4) {
@@ -141,6 +166,12 @@ extern "C" int vitk_grad_sumsq(const float* g, size_t n, float* partial, float* 
   if (grid > SUMSQ_MAX_CTAS) grid = SUMSQ_MAX_CTAS;
   VITK_LAUNCH((sumsq_partial_kernel), grid, 256, 0, st, g, n, partial);
   VITK_LAUNCH((sumsq_final_kernel), 1, 256, 0, st, partial, grid, sumsq);
+  return VITK_OK;
+}
+
+extern "C" int vitk_grad_scale(float* g, size_t n, float grad_mult, const float* sumsq, float max_norm, void* stream) {
+  VITK_CHECK_ARG(g && ((uintptr_t)g % 16) == 0);
+  VITK_LAUNCH((grad_scale_kernel), stream_grid(n / 4), 256, 0, (cudaStream_t)stream, g, n, grad_mult, sumsq, max_norm);
   return VITK_OK;
 }
 

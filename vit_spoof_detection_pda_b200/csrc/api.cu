@@ -18,24 +18,52 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(); }
-static std::atomic<int> g_sm_budget{0};
+static thread_local int t_sm_budget = 0;
 static int hw_sm_count() {
-  static int cached = 0;
-  if (cached) return cached;
+  static thread_local int cached_dev = -1, cached = 0;
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev == cached_dev && cached) return cached;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached_dev = dev;
   cached = n;
   return n;
 }
-// SMs the persistent kernels size their grids for: all of them, or the budget set while a communication
-// kernel (NCCL all-reduce) owns some SMs -- a persistent CTA that cannot become resident would stall its
-// statically assigned tiles until the collective finishes.
+// SMs the persistent kernels size their grids for: all of them, or the budget of the calling thread / call
+// (vitk_model.sm_budget, vitk_set_sm_budget) while a communication kernel (NCCL all-reduce) owns some SMs -- a
+// persistent CTA that cannot become resident would stall its statically assigned tiles until the collective
+// finishes.  Thread-local: no process-wide mutable state on the data path.
 int sm_count() {
-  const int hw = hw_sm_count(), b = g_sm_budget.load(std::memory_order_relaxed);
+  const int hw = hw_sm_count(), b = t_sm_budget;
   return (b > 0 && b < hw) ? b : hw;
 }
-int set_sm_budget(int n) { return g_sm_budget.exchange(n); }
+int set_sm_budget(int n) { const int prev = t_sm_budget; t_sm_budget = n; return prev; }
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to a function on ONE device: set it once per (function, device)
+int set_max_dyn_smem_once(const void* fn, int bytes) {
+  struct Done { const void* fn; int dev; };
+  static Done done[256];
+  static int n_done = 0;
+  static std::mutex mu;
+  int dev = 0;
+  VITK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  for (int i = 0; i < n_done; ++i)
+    if (done[i].fn == fn && done[i].dev == dev) return VITK_OK;
+  VITK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (n_done < 256) done[n_done++] = Done{fn, dev};
+  return VITK_OK;
+}
+#ifdef VITK_DEV
+// device-side tracer: one setter per translation unit (each has its own copy of the device pointer)
+static void (*g_trace_setters[32])(unsigned long long*);
+static int g_n_trace_setters = 0;
+void trace_register(void (*setter)(unsigned long long*)) {
+  if (g_n_trace_setters < 32) g_trace_setters[g_n_trace_setters++] = setter;
+}
+static void trace_set_all(unsigned long long* p) {
+  for (int i = 0; i < g_n_trace_setters; ++i) g_trace_setters[i](p);
+}
+#endif
 // ---- tensor-map cache: open addressing over FNV-1a of the key bytes
 struct TmapEntry { TmapKey key; unsigned char map[128]; bool used; };
 static constexpr int TMAP_SLOTS = 8192;
@@ -77,6 +105,38 @@ void set_pdl(int on) { g_pdl.store(on); }
 extern "C" {
 int vitk_version(void) { return VITK_VERSION; }
 int vitk_set_sm_budget(int n) { return vitk::set_sm_budget(n); }
+int vitk_is_dev_build(void) {
+#ifdef VITK_DEV
+  return 1;
+#else
+  return 0;
+#endif
+}
+// Device-side tracer (development build only): `buf` = device buffer of `bytes` bytes, cleared here; every CTA of every
+// libvitk kernel appends three 64-bit words per mark (see common.cuh) until vitk_trace_stop().  Both calls synchronise the device.
+int vitk_trace_start(void* buf, size_t bytes) {
+#ifdef VITK_DEV
+  VITK_CHECK_ARG(buf && bytes >= 64);
+  VITK_CUDA(cudaDeviceSynchronize());
+  const unsigned long long hdr[2] = {0ull, (unsigned long long)((bytes - 16) / 24)};
+  VITK_CUDA(cudaMemcpy(buf, hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+  vitk::trace_set_all(reinterpret_cast<unsigned long long*>(buf));
+  VITK_CUDA(cudaDeviceSynchronize());
+  return VITK_OK;
+#else
+  (void)buf; (void)bytes;
+  vitk::set_error("vitk_trace_start: the tracer exists only in the development build (libvitk_dev.so)");
+  return VITK_ERR_UNSUPPORTED;
+#endif
+}
+int vitk_trace_stop(void) {
+#ifdef VITK_DEV
+  VITK_CUDA(cudaDeviceSynchronize());
+  vitk::trace_set_all(nullptr);
+  VITK_CUDA(cudaDeviceSynchronize());
+#endif
+  return VITK_OK;
+}
 long long vitk_launch_count(void) { return vitk::launches(); }
 const char* vitk_last_error_string(void) { return vitk::g_err; }
 int vitk_device_info(int* sm_count, int* cc_major, int* cc_minor) {

@@ -1,19 +1,20 @@
-// C-ABI of the attention core + engine dispatch (fp32 -> FFMA kernel, bf16 -> tensor-core kernel).
+// C-ABI of the attention core + engine dispatch (fp32 -> FFMA kernel, bf16 -> tcgen05 kernel).
 #include "common.cuh"
 
 namespace vitk {
 int attn_fwd_simt(const void* qkv, void* out, float* lse, int batch, int dtype, cudaStream_t st);
 int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
                   int dtype, cudaStream_t st);
-int attn_fwd_mma(const void* qkv, void* out, float* lse, int batch, cudaStream_t st);
-int attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum,
-                 int batch, cudaStream_t st, int cs_sections);
-int attn_debug_variant();
-int debug_knob(int key);
+int attn_fwd_tc(const void* qkv, void* out, float* lse, int batch, cudaStream_t st);
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum, int batch,
+                cudaStream_t st, int cs_sections);
+int tune_knob(int key);
 int colsum_headmajor(const void* x, int dtype, int M, int C, float* db, cudaStream_t st);
 
-int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dtype, cudaStream_t st) {
-  if (dtype == VITK_BF16 && default_engine() != VITK_ENGINE_SIMT) return attn_fwd_mma(qkv, out, lse, batch, st);
+static bool use_tc(int dtype, int engine) { return dtype == VITK_BF16 && engine != VITK_ENGINE_SIMT; }
+
+int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dtype, int engine, cudaStream_t st) {
+  if (use_tc(dtype, engine)) return attn_fwd_tc(qkv, out, lse, batch, st);
   return attn_fwd_simt(qkv, out, lse, batch, dtype, st);
 }
 // dqkv_colsum (optional): fp32 [2304] += column sums of dqkv = the qkv bias gradient; fused into the tensor-core
@@ -27,13 +28,12 @@ int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dty
 //     sum_keys dK[key, :] = sum_q (sum_key dS[q, key]) Q[q, :] * scale = 0           -> the k section stays zero
 // (softmax is invariant to a shift of all keys: the k bias has no gradient).  The attention kernel's epilogue warps,
 // which gate the recycling of its dV / dK / dQ accumulators, then sum 4 instead of 12 slabs per item.
-bool attn_bias_split_supported(int dtype) {
-  return dtype == VITK_BF16 && default_engine() != VITK_ENGINE_SIMT && attn_debug_variant() == 0 && debug_knob(12) != 1;
+bool attn_bias_split_supported(int dtype, int engine) {
+  return use_tc(dtype, engine) && tune_knob(12) != 1;   // knob 12 (development build only): all three sections in the kernel
 }
 int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                      float* dqkv_colsum, int batch, int dtype, cudaStream_t st, int cs_sections) {
-  if (dtype == VITK_BF16 && default_engine() != VITK_ENGINE_SIMT)
-    return attn_bwd_mma(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, st, cs_sections);
+                      float* dqkv_colsum, int batch, int dtype, int engine, cudaStream_t st, int cs_sections) {
+  if (use_tc(dtype, engine)) return attn_bwd_tc(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, st, cs_sections);
   VITK_TRY(attn_bwd_simt(qkv, out, dout, lse, dqkv, batch, dtype, st));
   if (dqkv_colsum) VITK_TRY(colsum_headmajor(dqkv, dtype, batch * VITK_NTOK, 3 * VITK_DIM, dqkv_colsum, st));
   return VITK_OK;
@@ -44,10 +44,10 @@ using namespace vitk;
 
 extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int batch, int dtype, void* stream) {
   VITK_CHECK_ARG(qkv && out && batch > 0 && (dtype == VITK_F32 || dtype == VITK_BF16));
-  return attn_fwd_dispatch(qkv, out, lse, batch, dtype, (cudaStream_t)stream);
+  return attn_fwd_dispatch(qkv, out, lse, batch, dtype, VITK_ENGINE_AUTO, (cudaStream_t)stream);
 }
 extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                              float* dqkv_colsum, int batch, int dtype, void* stream) {
   VITK_CHECK_ARG(qkv && out && dout && lse && dqkv && batch > 0 && (dtype == VITK_F32 || dtype == VITK_BF16));
-  return attn_bwd_dispatch(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, dtype, (cudaStream_t)stream, 7);
+  return attn_bwd_dispatch(qkv, out, dout, lse, dqkv, dqkv_colsum, batch, dtype, VITK_ENGINE_AUTO, (cudaStream_t)stream, 7);
 }

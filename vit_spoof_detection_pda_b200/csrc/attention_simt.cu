@@ -24,7 +24,7 @@ __device__ __forceinline__ void at_load_matrix(const T* __restrict__ src, float*
 template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32)
 attn_fwd_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ lse, int batch) {
-  pdl_sync();
+  pdl_sync_traced(TK_ATTN_SIMT);
   extern __shared__ float smem[];
   float* Ks = smem;
   float* Vs = Ks + AT_N * AT_P;
@@ -84,13 +84,14 @@ attn_fwd_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __re
     if (lane == 0 && lse) lse[(int64_t)h * M + (int64_t)b * AT_N + i] = mx + logf(sum);
     __syncwarp();
   }
+  trace_end(TK_ATTN_SIMT);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32)
 attn_bwd_simt_kernel(const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
                      const float* __restrict__ lse, T* __restrict__ dqkv, int batch) {
-  pdl_sync();
+  pdl_sync_traced(TK_ATTN_SIMT);
   extern __shared__ float smem[];
   float* Qs = smem;
   float* Ks = Qs + AT_N * AT_P;
@@ -197,6 +198,7 @@ attn_bwd_simt_kernel(const T* __restrict__ qkv, const T* __restrict__ out, const
     dv[lane + 32] = from_f32<T>(v1);
     __syncwarp();
   }
+  trace_end(TK_ATTN_SIMT);
 }
 
 constexpr size_t AT_FWD_SMEM = (size_t)(2 * AT_N * AT_P + AT_WARPS * (64 + 224)) * sizeof(float);
@@ -204,22 +206,14 @@ constexpr size_t AT_BWD_SMEM = (size_t)(4 * AT_N * AT_P + 400 + AT_WARPS * 448) 
 
 template <typename T>
 static int attn_fwd_simt_t(const void* qkv, void* out, float* lse, int batch, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(attn_fwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_FWD_SMEM));
-    configured = true;
-  }
+  VITK_TRY(set_max_dyn_smem_once((const void*)attn_fwd_simt_kernel<T>, (int)AT_FWD_SMEM));
   VITK_LAUNCH((attn_fwd_simt_kernel<T>), batch * VITK_HEADS, AT_WARPS * 32, AT_FWD_SMEM, st, (const T*)qkv, (T*)out, lse, batch);
   return VITK_OK;
 }
 template <typename T>
 static int attn_bwd_simt_t(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
                            cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_BWD_SMEM));
-    configured = true;
-  }
+  VITK_TRY(set_max_dyn_smem_once((const void*)attn_bwd_simt_kernel<T>, (int)AT_BWD_SMEM));
   VITK_LAUNCH((attn_bwd_simt_kernel<T>), batch * VITK_HEADS, AT_WARPS * 32, AT_BWD_SMEM, st, (const T*)qkv, (const T*)out, (const T*)dout, lse, (T*)dqkv, batch);
   return VITK_OK;
 }

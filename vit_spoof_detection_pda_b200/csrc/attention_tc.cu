@@ -22,8 +22,7 @@
 
 namespace vitk {
 
-int attn_debug_variant();  // gemm_tc.cu: vitk_debug_set(3, v)
-int debug_knob(int key);     // gemm_tc.cu: vitk_debug_set(key, v); key 7 = timing experiments (bit 0 no MMAs, bit 1 no softmax math)
+int tune_knob(int key);     // gemm_tc.cu: vitk_debug_set(key, v); key 7 (development build) = timing experiments, results invalid
 
 namespace atc {
 
@@ -223,6 +222,7 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 
 __global__ void __launch_bounds__(THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                    bf16* __restrict__ out, float* __restrict__ lse, int batch, int n_items) {
+  trace_mark(TK_ATTN_FWD, 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -259,6 +259,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_sync();
+  trace_mark(TK_ATTN_FWD, 1);
 
   const int64_t M = (int64_t)batch * N_TOK;
   const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA
@@ -430,6 +431,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  trace_mark(TK_ATTN_FWD, 2);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -504,7 +506,14 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t lbo) { r
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
                    const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ out, const float* __restrict__ lse,
-                   bf16* __restrict__ dqkv, float* __restrict__ dqkv_colsum, int cs_sections, int batch, int n_items, int dbg) {
+                   bf16* __restrict__ dqkv, float* __restrict__ dqkv_colsum, int cs_sections, int batch, int n_items, int dbg_in) {
+#ifdef VITK_DEV
+  const int dbg = dbg_in;      // timing experiments (bit 0 no MMAs, 1 no softmax math, 2 no draining, 3 no delta, 4 no loads)
+#else
+  constexpr int dbg = 0;       // the release build has no result-invalidating path
+  (void)dbg_in;
+#endif
+  trace_mark(TK_ATTN_BWD, 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -543,6 +552,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_sync();
+  trace_mark(TK_ATTN_BWD, 1);
 
   const int64_t M = (int64_t)batch * N_TOK;
   const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -849,6 +859,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  trace_mark(TK_ATTN_BWD, 2);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -880,11 +891,7 @@ static int make_dout_map(const void* base, int64_t M, CUtensorMap* map) {
 }  // namespace atc
 
 int attn_fwd_tc(const void* qkv, void* out, float* lse, int batch, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(atc::attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atc::FWD_SMEM));
-    configured = true;
-  }
+  VITK_TRY(set_max_dyn_smem_once((const void*)atc::attn_fwd_tc_kernel, (int)atc::FWD_SMEM));
   const int64_t M = (int64_t)batch * VITK_NTOK;
   CUtensorMap map_q, map_kv;
   VITK_TRY(atc::make_hm_map(qkv, M, 3 * VITK_HEADS, 256, &map_q));
@@ -896,11 +903,7 @@ int attn_fwd_tc(const void* qkv, void* out, float* lse, int batch, cudaStream_t 
 
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dqkv_colsum, int batch,
                 cudaStream_t st, int cs_sections) {
-  static bool configured = false;
-  if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(atc::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atc::BWD_SMEM));
-    configured = true;
-  }
+  VITK_TRY(set_max_dyn_smem_once((const void*)atc::attn_bwd_tc_kernel, (int)atc::BWD_SMEM));
   const int64_t M = (int64_t)batch * VITK_NTOK;
   CUtensorMap map_kv, map_q, map_do;
   VITK_TRY(atc::make_hm_map(qkv, M, 3 * VITK_HEADS, 128, &map_kv));
@@ -908,7 +911,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   VITK_TRY(atc::make_dout_map(dout, M, &map_do));
   const int items = batch * VITK_HEADS, sms = sm_count();
   VITK_LAUNCH((atc::attn_bwd_tc_kernel), (items < sms ? items : sms), atc::BWD_THREADS, atc::BWD_SMEM, st, map_kv, map_q, map_do,
-              (const bf16*)out, lse, (bf16*)dqkv, dqkv_colsum, cs_sections, batch, items, debug_knob(7));
+              (const bf16*)out, lse, (bf16*)dqkv, dqkv_colsum, cs_sections, batch, items, tune_knob(7));
   return VITK_OK;
 }
 

@@ -18,7 +18,8 @@ typedef __nv_bfloat16 bf16;
 void set_error(const char* fmt, ...);
 void count_launch();
 int sm_count();
-int default_engine();  // process-wide GEMM/attention engine (VITK_ENGINE_*)
+int set_sm_budget(int n);   // thread-local; returns the previous value
+int set_max_dyn_smem_once(const void* fn, int bytes);
 
 #define VITK_CHECK_ARG(cond)                                                         \
   do {                                                                               \
@@ -65,9 +66,65 @@ void tmap_cache_put(const TmapKey& key, const void* map128);
 // TMEM allocation, tensor-map prefetch -- overlap the tail of the previous kernel; no kernel touches global memory
 // before its pdl_sync().  vitk_debug_set(6, 1) turns the attribute off (plain stream order) for A/B timing.
 bool pdl_enabled();
+
+// Device-side tracer -- exists only in the development build (libvitk_dev.so, -DVITK_DEV; see build.py).  Thread 0 of
+// every CTA appends (globaltimer, kernel id | phase | SM id | block index, aux) records to a caller-provided device
+// buffer: phase 0 = CTA started, 1 = its stream dependencies are satisfied (griddepcontrol.wait returned), 2 = CTA
+// finished.  That is a per-SM timeline of a real training step with programmatic dependent launch and the
+// weight-gradient side stream left ON (tools/step_timeline.py) -- what CUDA-event bracketing cannot give without
+// serialising the launches.  In the release build trace_mark() compiles to nothing.
+enum TraceKernel {
+  TK_GEMM_TC = 1, TK_ATTN_FWD = 2, TK_ATTN_BWD = 3, TK_LN_FWD = 4, TK_LN_BWD = 5, TK_ADAM = 6, TK_SUMSQ = 7, TK_CAST = 8,
+  TK_HEAD = 9, TK_FOCAL = 10, TK_COLSUM = 11, TK_PATCH_EMBED = 12, TK_EMBED_GRADS = 13, TK_SCATTER_CLS = 14,
+  TK_GEMM_SIMT = 15, TK_ATTN_SIMT = 16, TK_EVAL = 17, TK_PATCH_WGRAD = 18
+};
+#ifdef VITK_DEV
+void trace_register(void (*setter)(unsigned long long*));   // api.cu: one setter per translation unit
+#endif
 #ifdef __CUDACC__
+#ifdef VITK_DEV
+static __device__ unsigned long long* g_trace_buf = nullptr;   // [0] record count, [1] capacity, records of 3 words from [2]
+namespace {
+struct TraceTU {
+  static void set(unsigned long long* p) { cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)); }
+  TraceTU() { trace_register(&set); }
+};
+static TraceTU s_trace_tu;
+}  // namespace
+__device__ __forceinline__ void trace_mark(uint32_t kid, uint32_t phase, unsigned long long aux = 0) {
+  if (threadIdx.x != 0) return;
+  unsigned long long* b = g_trace_buf;
+  if (!b) return;
+  const unsigned long long idx = atomicAdd(b, 1ull);
+  if (idx >= b[1]) return;
+  unsigned long long t;
+  uint32_t smid;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  unsigned long long* r = b + 2 + 3 * idx;
+  r[0] = t;
+  r[1] = ((unsigned long long)kid << 48) | ((unsigned long long)phase << 40) | ((unsigned long long)(smid & 0xffffu) << 24) |
+         (unsigned long long)(blockIdx.x & 0xffffffu);
+  r[2] = aux;
+}
+// end-of-CTA mark for kernels whose threads all reach the end of the kernel body
+__device__ __forceinline__ void trace_end(uint32_t kid, unsigned long long aux = 0) {
+  __syncthreads();
+  trace_mark(kid, 2, aux);
+}
+#else
+__device__ __forceinline__ void trace_mark(uint32_t, uint32_t, unsigned long long = 0) {}
+__device__ __forceinline__ void trace_end(uint32_t, unsigned long long = 0) {}
+#endif
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// pdl_sync() for kernels that start with it: CTA-start and dependencies-satisfied marks around the wait
+__device__ __forceinline__ void pdl_sync_traced(uint32_t kid, unsigned long long aux = 0) {
+  trace_mark(kid, 0, aux);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  trace_mark(kid, 1, aux);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 template <typename... KA, typename... A>

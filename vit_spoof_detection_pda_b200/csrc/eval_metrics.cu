@@ -18,7 +18,7 @@ constexpr int TS_MAX_STEPS = 255;
 __global__ void __launch_bounds__(256)
 threshold_hist_kernel(const float* __restrict__ probs, const int64_t* __restrict__ labels, const double* __restrict__ thresholds,
                       int n, int steps, unsigned long long* __restrict__ hist) {
-  pdl_sync();
+  pdl_sync_traced(TK_EVAL);
   __shared__ unsigned int sh[2 * (TS_MAX_STEPS + 1)];
   __shared__ double th[TS_MAX_STEPS];
   for (int i = threadIdx.x; i < 2 * (steps + 1); i += blockDim.x) sh[i] = 0u;
@@ -37,12 +37,13 @@ threshold_hist_kernel(const float* __restrict__ probs, const int64_t* __restrict
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * (steps + 1); i += blockDim.x)
     if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+  trace_end(TK_EVAL);
 }
 
 // counts[s] = (tp, fp, tn, fn) at thresholds[s]:  predicted live <=> k > s
 __global__ void __launch_bounds__(256)
 threshold_counts_kernel(const unsigned long long* __restrict__ hist, int steps, long long* __restrict__ counts) {
-  pdl_sync();
+  pdl_sync_traced(TK_EVAL);
   const unsigned long long* h0 = hist;               // label spoof (0)
   const unsigned long long* h1 = hist + steps + 1;   // label live (1)
   for (int s = threadIdx.x; s < steps; s += blockDim.x) {
@@ -53,6 +54,7 @@ threshold_counts_kernel(const unsigned long long* __restrict__ hist, int steps, 
     counts[4 * s + 0] = (long long)tp; counts[4 * s + 1] = (long long)fp;
     counts[4 * s + 2] = (long long)tn; counts[4 * s + 3] = (long long)fn;
   }
+  trace_end(TK_EVAL);
 }
 
 }  // namespace vitk

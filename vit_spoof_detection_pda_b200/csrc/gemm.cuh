@@ -106,6 +106,5 @@ __device__ __forceinline__ void epilogue_scalar(const EpiParams& ep, int i, int 
 int gemm_simt(const GemmProblem& p, int splits, cudaStream_t st);
 // tcgen05/TMEM engine (bf16 operands only). Returns VITK_ERR_UNSUPPORTED for shapes it does not take.
 int gemm_tc(const GemmProblem& p, cudaStream_t st);
-int default_engine();
 
 }  // namespace vitk

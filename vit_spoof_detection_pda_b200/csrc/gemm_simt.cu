@@ -26,7 +26,7 @@ __device__ __forceinline__ void simt_load_tile(const T* __restrict__ base, const
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(ST_THREADS)
 gemm_simt_kernel(GemmProblem p, int r_per_split) {
-  pdl_sync();
+  pdl_sync_traced(TK_GEMM_SIMT);
   __shared__ float As[ST_BK][ST_BM + ST_PAD];
   __shared__ float Bs[ST_BK][ST_BN + ST_PAD];
   const int i0 = blockIdx.y * ST_BM, j0 = blockIdx.x * ST_BN;
@@ -69,6 +69,7 @@ gemm_simt_kernel(GemmProblem p, int r_per_split) {
       if (j < p.J) epilogue_scalar<TO>(p.ep, i, j, acc[x][y]);
     }
   }
+  trace_end(TK_GEMM_SIMT);
 }
 
 int gemm_simt(const GemmProblem& p, int splits, cudaStream_t st) {

@@ -55,7 +55,10 @@ struct OpCoord {
 };
 
 struct TcParams {
-  int32_t dbg;              // timing experiments only (vitk_debug_set(7, v)): bit 0 skip the epilogue body, bit 1 no operand loads
+#ifdef VITK_DEV
+  int32_t dbg;              // development build, timing experiments only (vitk_debug_set(7, v)): bit 0 skip the epilogue
+                            // body, bit 1 no operand loads -- results invalid; the release build has no such path
+#endif
   int32_t I, J, R;
   int32_t a_mode, b_mode;
   OpCoord ca, cb;
@@ -68,6 +71,12 @@ struct TcParams {
   uint32_t a_kstep, b_kstep;            // bytes advanced per UMMA_K=16 step
   EpiParams ep;
 };
+
+#ifdef VITK_DEV
+#define TC_DBG(p) ((p).dbg)
+#else
+#define TC_DBG(p) 0
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -194,11 +203,6 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 // TMA store / load of epilogue tiles (2-D row-major, 3-D head-major) and bulk-group bookkeeping
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
-// fp32 reduce-add of a staged tile into global memory (the tensor map's element type selects the add)
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
@@ -360,11 +364,10 @@ __device__ __forceinline__ void epilogue_rows8(const EpiParams& ep, int i, int j
 // (rows past the end of the matrix are clipped by the tensor map).  Second operands (fp32 residual, saved gelu')
 // arrive the same way: a TMA load into the staging tile issued BEFORE the accumulator is ready, combined in place.
 // No per-thread global loads/stores and no global-memory latency remain on the epilogue warps' critical path.
-enum { EK_LEGACY = 0, EK_STORE_BF16 = 1, EK_STORE_F32 = 2, EK_GELU = 3, EK_RESIDUAL = 4, EK_SCATTER = 5, EK_GELU_BWD = 6,
-       EK_ACCUM = 7 };   // EK_ACCUM: fp32 tile -> TMA reduce-add into the gradient buffer (weight-gradient partial tiles)
+enum { EK_LEGACY = 0, EK_STORE_BF16 = 1, EK_STORE_F32 = 2, EK_GELU = 3, EK_RESIDUAL = 4, EK_SCATTER = 5, EK_GELU_BWD = 6 };
 // staging per epilogue warp: two 4 KB slots for fp32 tiles, two 2 KB slots for bf16 tiles (EK_GELU: one slot pair g | u).
 // Every KB not spent here is operand-ring depth: the mainloop needs ~1.5 us of loads in flight to ride out DRAM latency.
-__host__ __device__ constexpr uint32_t tc_epi_warp_bytes(int ek) { return (ek == EK_STORE_F32 || ek == EK_RESIDUAL || ek == EK_ACCUM) ? 8192u : 4096u; }
+__host__ __device__ constexpr uint32_t tc_epi_warp_bytes(int ek) { return (ek == EK_STORE_F32 || ek == EK_RESIDUAL) ? 8192u : 4096u; }
 
 template <int BN, int CG, int EK> struct TcCfg {
   static constexpr int B_ROWS = BN / CG;                                   // rows of the B tile this CTA stages
@@ -493,6 +496,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Cfg::BAR_OFF + 8 * (2 * Cfg::STAGES + 4 + 2 * TC_EPI_WARPS));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dbg = TC_DBG(p);   // 0 (compile time) in the release build
+  const unsigned long long tr_aux = ((unsigned long long)p.I << 40) | ((unsigned long long)p.J << 20) | (unsigned long long)p.R;
+  trace_mark(TK_GEMM_TC, 0, tr_aux);
   // CTA pair: rank 0 (leader) owns the barriers the pair shares -- `full` (TMA bytes of both CTAs) and `tmem_empty`
   // (epilogue warps of both CTAs); `empty` and `tmem_full` exist in both CTAs and are signalled by multicast commits.
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -531,6 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
+  trace_mark(TK_GEMM_TC, 1, tr_aux);
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of the B rows) ==========
@@ -550,7 +557,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int a0 = i0 * p.ca.fr0 + kb0 * p.ca.d0, a1 = i0 * p.ca.fr1 + kb0 * p.ca.d1, a2 = (i0 >> 6) * p.ca.fr2 + kb0 * p.ca.d2;
         int b0 = j0 * p.cb.fr0 + kb0 * p.cb.d0, b1 = j0 * p.cb.fr1 + kb0 * p.cb.d1, b2 = (j0 >> 6) * p.cb.fr2 + kb0 * p.cb.d2;
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (p.dbg & 2) continue;
+          if (dbg & 2) continue;
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (leader) {
             if (rank == 0) mbar_expect_tx(full_bar(stage), CG * Cfg::STAGE_BYTES);
@@ -569,7 +576,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (CG == 2 && !(p.dbg & 2)) {
+      if (CG == 2 && !(dbg & 2)) {
         // tail: the leader's last multicast commits must have landed in this CTA's `empty` barriers before it may exit
         for (int s = 0; s < Cfg::STAGES; ++s) {
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -603,7 +610,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < nkb; ++kb) {
-          if (!(p.dbg & 2)) mbar_wait(full_bar(stage), phase);
+          if (!(dbg & 2)) mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           if (leader) {
             const uint32_t so = (uint32_t)stage * (Cfg::STAGE_BYTES >> 4);
@@ -613,7 +620,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_mma_desc(d_tmem, al + 2 * a_ks, a_hi, bl + 2 * b_ks, b_hi, p.idesc, 1u, CG == 2);
             tc_mma_desc(d_tmem, al + 3 * a_ks, a_hi, bl + 3 * b_ks, b_hi, p.idesc, 1u, CG == 2);
             // smem slot free (in both CTAs) once these MMAs retire
-            if (!(p.dbg & 2)) { if constexpr (CG == 2) tc_commit_2cta(empty_bar(stage)); else tc_commit(empty_bar(stage)); }
+            if (!(dbg & 2)) { if constexpr (CG == 2) tc_commit_2cta(empty_bar(stage)); else tc_commit(empty_bar(stage)); }
             if (kb + 1 == nkb) {   // accumulator complete (both CTAs' epilogues)
               if constexpr (CG == 2) tc_commit_2cta(tfull_bar(acc)); else tc_commit(tfull_bar(acc));
             }
@@ -651,7 +658,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
         const uint32_t tb = smem_base + Cfg::EPI_OFF + (uint32_t)we * Cfg::EPI_WARP_BYTES;   // 4 KB transpose buffer
         const int sub_row = lane >> 3, c4 = lane & 7;
-        if (i0 + q * 32 < p.I && !(p.dbg & 1)) {   // warps whose 32 rows are all past the end of the matrix have nothing to write
+        if (i0 + q * 32 < p.I && !(dbg & 1)) {   // warps whose 32 rows are all past the end of the matrix have nothing to write
 #pragma unroll 1
           for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
             uint32_t raw[32];
@@ -679,7 +686,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
       // ---------------- TMA epilogue ----------------
       constexpr bool kLoads = (EK == EK_RESIDUAL || EK == EK_GELU_BWD);       // second operand TMA-loaded into the staging tile
-      constexpr bool kF32 = (EK == EK_STORE_F32 || EK == EK_RESIDUAL || EK == EK_ACCUM);   // fp32 tiles: 4 KB, 128-byte rows
+      constexpr bool kF32 = (EK == EK_STORE_F32 || EK == EK_RESIDUAL);   // fp32 tiles: 4 KB, 128-byte rows
       constexpr uint32_t kTileBytes = kF32 ? 4096u : 2048u;
       constexpr int NCH = BN / 64;                                             // 32-column chunks per warp and tile
       constexpr uint32_t kSlotBytes = kF32 ? 4096u : 2048u;
@@ -708,7 +715,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-        if (!active || (p.dbg & 1)) {
+        if (!active || (dbg & 1)) {
           release_tmem();
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           continue;
@@ -765,7 +772,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               // optional column sums of the bf16 output (no bias in this mode: rows past the end of the matrix are zero)
               if (p.ep.colsum) { __syncwarp(); tile_colsum_bf16(t0, lane, p.ep.colsum + col); }
             }
-          } else if constexpr (EK == EK_STORE_F32 || EK == EK_ACCUM) {
+          } else if constexpr (EK == EK_STORE_F32) {
             slot_ready();
 #pragma unroll
             for (int k8 = 0; k8 < 8; ++k8)
@@ -818,8 +825,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (lane == 0) {
             if constexpr (EK == EK_SCATTER) {
               tma_store_3d(&map_c, t0, col & 63, row0, col >> 6);
-            } else if constexpr (EK == EK_ACCUM) {
-              tma_reduce_add_2d(&map_c, t0, col, row0);
             } else {
               tma_store_2d(&map_c, t0, col, row0);
               if constexpr (EK == EK_GELU) {
@@ -837,6 +842,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody exits while its peer may still touch it
+  trace_mark(TK_GEMM_TC, 2, tr_aux);
   if (warp == 1) {
     tc_fence_after();
     if constexpr (CG == 2)
@@ -919,9 +925,20 @@ static int make_operand_map(const void* base, const MatLayout& l, int rows, int 
 }
 
 
+// Tuning overrides (vitk_debug_set): process-wide, for tests and A/B timing; every one of them yields valid results.
+//   1 whole-K tiles for accumulate GEMMs, 2 forced BLOCK_N, 4 CTA group, 5 per-thread epilogue IO, 6 no programmatic
+//   dependent launch, 13 stream-K instead of sliced split-K (> 1: fill threshold in percent).
+// Development build only (libvitk_dev.so): 0 swap LBO/SBO of MN-major operands, 7 timing-only bit mask (results INVALID),
+//   12 whole qkv bias gradient from the attention kernel.
 static int g_tc_debug[16] = {0};
-int attn_debug_variant() { return g_tc_debug[3]; }
-int debug_knob(int key) { return (key >= 0 && key < 16) ? g_tc_debug[key] : 0; }
+static bool knob_allowed(int key) {
+#ifdef VITK_DEV
+  return key >= 0 && key < 16;
+#else
+  return key == 1 || key == 2 || key == 4 || key == 5 || key == 6 || key == 13;
+#endif
+}
+int tune_knob(int key) { return knob_allowed(key) ? g_tc_debug[key] : 0; }
 
 // 32 x 32 element tile maps of the epilogue operands: row-major [rows][ld] (2-D) or head-major [C/64][rows][64] (3-D).
 // 4-byte elements -> 128-byte tile rows (SWIZZLE_128B), 2-byte -> 64-byte rows (SWIZZLE_64B).
@@ -964,9 +981,9 @@ static int epilogue_kind(const EpiParams& ep) {
     case E_BIAS_GELU: return (ok16 && ep.out_dtype == VITK_BF16 && (((uintptr_t)ep.aux & 15) == 0)) ? EK_GELU : EK_LEGACY;
     case E_BIAS_RESIDUAL: return (ok16 && (((uintptr_t)ep.residual & 15) == 0)) ? EK_RESIDUAL : EK_LEGACY;
     case E_QKV_SCATTER: return (ok16 && ep.out_dtype == VITK_BF16) ? EK_SCATTER : EK_LEGACY;
-    // TMA reduce-add of the partial tiles is opt-in (knob 14 = 1): measured 2-3 % slower than the transposing
-    // red.global.add.v4 path on all four weight-gradient shapes (gpurun_out/ac_cublas.log)
-    case E_ACCUM: return (g_tc_debug[14] == 1 && ok16 && ep.out_dtype == VITK_F32 && !ep.colsum && !ep.bias) ? EK_ACCUM : EK_LEGACY;
+    // weight-gradient partial tiles: the transposing red.global.add.v4 path (a TMA reduce-add epilogue measured 2-3 %
+    // slower on all four shapes in round 1 and was removed)
+    case E_ACCUM: return EK_LEGACY;
     case E_GELU_BWD: return (ok16 && ep.out_dtype == VITK_BF16 && ep.aux && (((uintptr_t)ep.aux & 15) == 0)) ? EK_GELU_BWD : EK_LEGACY;
     default: return EK_LEGACY;
   }
@@ -985,9 +1002,6 @@ static int tc_decompose(TcParams& p, bool accumulate, int BN, int CG) {
   if (accumulate && g_tc_debug[1] != 1) {
     const int64_t total = (int64_t)tiles * p.kb_total;
     grid = total < slots ? (int)total : slots;
-    // knob 11 (A/B): at most this many partial sums per output tile -- fewer, longer-lived CTAs and less atomic traffic
-    // for the small weight-gradient GEMMs that run next to the dgrad chain
-    if (g_tc_debug[11] > 0 && grid > tiles * g_tc_debug[11]) grid = tiles * g_tc_debug[11];
     p.streamk = 1;
     p.units_per_cta = (total + grid - 1) / grid;
     grid = (int)((total + p.units_per_cta - 1) / p.units_per_cta);
@@ -1046,15 +1060,13 @@ static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* b
 template <int BN, int CG, int EK>
 static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
   using Cfg = TcCfg<BN, CG, EK>;
-  static bool configured = false;
-  if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  VITK_TRY(set_max_dyn_smem_once((const void*)gemm_tc_kernel<BN, CG, EK>, (int)Cfg::SMEM_BYTES));
   CUtensorMap map_a, map_b, map_c, map_d;
   TcParams p{};
   p.I = pr.I; p.J = pr.J; p.R = pr.R;
+#ifdef VITK_DEV
   p.dbg = g_tc_debug[7];
+#endif
   VITK_TRY(make_operand_map(pr.A, pr.la, pr.I, pr.R, TC_BM, &map_a, &p.a_mode));
   VITK_TRY(make_operand_map(pr.B, pr.lb, pr.J, pr.R, Cfg::B_ROWS, &map_b, &p.b_mode));
   const EpiParams& ep = pr.ep;
@@ -1064,7 +1076,7 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
     VITK_TRY(make_tile_map(ep.out, VITK_BF16, pr.J, pr.I, 0, ep.hm_rows, &map_c));
     map_d = map_c;
   } else {
-    const int odt = (EK == EK_STORE_F32 || EK == EK_RESIDUAL || EK == EK_ACCUM) ? VITK_F32 : VITK_BF16;
+    const int odt = (EK == EK_STORE_F32 || EK == EK_RESIDUAL) ? VITK_F32 : VITK_BF16;
     VITK_TRY(make_tile_map(ep.out, odt, pr.J, pr.I, ep.ldc, 0, &map_c));
     if constexpr (EK == EK_RESIDUAL) VITK_TRY(make_tile_map(ep.residual, VITK_F32, pr.J, pr.I, ep.ldc, 0, &map_d));
     else if constexpr (EK == EK_GELU_BWD) VITK_TRY(make_tile_map(ep.aux, VITK_BF16, pr.J, pr.I, ep.ldc, 0, &map_d));
@@ -1088,10 +1100,12 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
   // MN-major: 8-r groups 1024 B apart (SBO), 64-wide MN atoms TC_BK*128 B apart (LBO)
   p.a_sbo = 1024; p.a_lbo = a_mn ? TC_BK * 128 : 16; p.a_kstep = a_mn ? 16 * 128 : 32;
   p.b_sbo = 1024; p.b_lbo = b_mn ? TC_BK * 128 : 16; p.b_kstep = b_mn ? 16 * 128 : 32;
+#ifdef VITK_DEV
   if (g_tc_debug[0] == 1) {  // debug variant: swap LBO/SBO roles of MN-major operands
     if (a_mn) { p.a_sbo = TC_BK * 128; p.a_lbo = 1024; }
     if (b_mn) { p.b_sbo = TC_BK * 128; p.b_lbo = 1024; }
   }
+#endif
   const int grid = tc_decompose(p, pr.ep.mode == E_ACCUM, BN, CG);
   p.ep = pr.ep;
   cudaLaunchConfig_t cfg{};
@@ -1127,7 +1141,6 @@ static int launch_tc_kind(const GemmProblem& pr, int ek, cudaStream_t st) {
     case EK_RESIDUAL: return launch_tc<BN, CG, EK_RESIDUAL>(pr, st);
     case EK_SCATTER: return launch_tc<BN, CG, EK_SCATTER>(pr, st);
     case EK_GELU_BWD: return launch_tc<BN, CG, EK_GELU_BWD>(pr, st);
-    case EK_ACCUM: return launch_tc<BN, CG, EK_ACCUM>(pr, st);
     default: return launch_tc<BN, CG, EK_LEGACY>(pr, st);
   }
 }
@@ -1204,7 +1217,10 @@ extern "C" int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_m
   return n;
 }
 extern "C" int vitk_debug_set(int key, int value) {
-  if (key < 0 || key >= 16) return VITK_ERR_ARG;
+  if (!vitk::knob_allowed(key)) {
+    vitk::set_error("vitk_debug_set: key %d is not available in this build (development-only keys need libvitk_dev.so)", key);
+    return VITK_ERR_ARG;
+  }
   vitk::g_tc_debug[key] = value;
   if (key == 6) vitk::set_pdl(value ? 0 : 1);   // key 6: 1 = plain stream order (no programmatic dependent launch)
   return VITK_OK;

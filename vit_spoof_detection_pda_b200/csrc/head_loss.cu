@@ -33,7 +33,7 @@ head_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ ln_w, 
                 const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                 const float* __restrict__ b2, const float* __restrict__ mask1, const float* __restrict__ mask2,
                 float* __restrict__ logits, float* __restrict__ save, int num_classes) {
-  pdl_sync();
+  pdl_sync_traced(TK_HEAD);
   __shared__ __align__(16) float ys[HD_IN];
   __shared__ float as[HD_HID];
   __shared__ float red[HD_THREADS / 32];
@@ -95,6 +95,7 @@ head_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ ln_w, 
     a = warp_sum(a);
     if (lane == 0) logits[(int64_t)b * num_classes + c] = a + b2[c];
   }
+  trace_end(TK_HEAD);
 }
 
 // per-sample backward to the feature; leaves dz1 and dym in the save area for the parameter-grad kernel.
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(HD_THREADS)
 head_bwd_data_kernel(const float* __restrict__ dlogits, float* save, const float* __restrict__ ln_w,
                      const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ mask1,
                      const float* __restrict__ mask2, float* __restrict__ dfeat, int num_classes) {
-  pdl_sync();
+  pdl_sync_traced(TK_HEAD);
   __shared__ float dz[HB_T];
   __shared__ float red[HD_THREADS / 32];
   __shared__ int is_last;
@@ -139,7 +140,7 @@ head_bwd_data_kernel(const float* __restrict__ dlogits, float* save, const float
   __syncthreads();
   if (tid == 0) is_last = (atomicAdd(reinterpret_cast<int*>(sv + HS_RSTD + 1), 1) == HB_SPLIT - 1);
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) { trace_mark(TK_HEAD, 2); return; }
   __threadfence();
   if (tid == 0) sv[HS_RSTD + 1] = 0.f;        // ticket back to zero
   float dxh[2], xh[2];
@@ -167,6 +168,7 @@ head_bwd_data_kernel(const float* __restrict__ dlogits, float* save, const float
     const int k = tid + e * HD_THREADS;
     if (k < HD_IN) dfeat[(int64_t)b * HD_IN + k] = rstd * (dxh[e] - c1 - xh[e] * c2);
   }
+  trace_end(TK_HEAD);
 }
 
 // parameter gradients: blockIdx.x in [0,64) -> 8 rows t of dw1 (+ db1) per CTA, so the saved activations of the batch
@@ -179,7 +181,7 @@ head_bwd_param_kernel(const float* __restrict__ dlogits, const float* __restrict
                       float* __restrict__ dln_w, float* __restrict__ dln_b, float* __restrict__ dw1,
                       float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2, int batch,
                       int num_classes) {
-  pdl_sync();
+  pdl_sync_traced(TK_HEAD);
   const int blk = blockIdx.x, tid = threadIdx.x;
   if (blk < HP_BLOCKS) {
     const int t0 = blk * HP_ROWS;
@@ -239,6 +241,7 @@ head_bwd_param_kernel(const float* __restrict__ dlogits, const float* __restrict
       db2[c] += sb;
     }
   }
+  trace_end(TK_HEAD);
 }
 
 constexpr int FOCAL_MAX_C = 8;
@@ -248,7 +251,7 @@ focal_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targe
              float gamma, int reduction, float grad_scale, float* __restrict__ loss_per_sample,
              float* __restrict__ loss_out, float* __restrict__ dlogits, float* __restrict__ probs1,
              int64_t* __restrict__ preds, int* __restrict__ ncorrect, int batch, int C) {
-  pdl_sync();
+  pdl_sync_traced(TK_FOCAL);
   __shared__ float red[8];
   __shared__ int redi[8];
   const float gscale = grad_scale * (reduction == 0 ? 1.0f / (float)batch : 1.0f);
@@ -269,12 +272,14 @@ focal_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targe
     for (int c = 0; c < FOCAL_MAX_C; ++c)
       if (c < C) se += expf(z[c] - mx);
     const float lse = mx + logf(se);
-    const int y = (int)targets[b];
+    const int64_t yt = targets[b];
+    const bool bad_target = yt < 0 || yt >= (int64_t)C;   // F.cross_entropy device-asserts; here the loss and the gradient
+    const int y = bad_target ? 0 : (int)yt;               // of that sample become NaN (ignore_index is not supported)
     float zy = 0.f;
 #pragma unroll
     for (int c = 0; c < FOCAL_MAX_C; ++c)
       if (c == y) zy = z[c];
-    const float ce = lse - zy;
+    const float ce = bad_target ? __int_as_float(0x7fc00000) : lse - zy;
     const float pt = expf(-ce);
     const float om = 1.0f - pt;
     const float w = alpha[y];
@@ -307,6 +312,7 @@ focal_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targe
     if (loss_out) loss_out[0] = (reduction == 0) ? s / (float)batch : s;
     if (ncorrect) ncorrect[0] = n;
   }
+  trace_end(TK_FOCAL);
 }
 
 }  // namespace vitk

@@ -8,8 +8,6 @@
 
 namespace vitk {
 
-int debug_knob(int key);
-
 constexpr int LN_COLS = VITK_DIM;        // 768
 constexpr int LN_VEC = LN_COLS / 128;    // 6 float4 per lane
 constexpr int LN_WARPS = 8;
@@ -80,7 +78,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ gamma,
               const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int rows, float eps) {
-  pdl_sync();
+  pdl_sync_traced(TK_LN_FWD);
   const int lane = threadIdx.x & 31;
   const int nw = gridDim.x * LN_WARPS;
   for (int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < rows; row += 2 * nw) {
@@ -97,6 +95,7 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __rest
     ln_row<T>(a, lane, gamma, beta, y + (int64_t)row * LN_COLS, mean_out, rstd_out, row, eps);
     if (row2 < rows) ln_row<T>(b, lane, gamma, beta, y + (int64_t)row2 * LN_COLS, mean_out, rstd_out, row2, eps);
   }
+  trace_end(TK_LN_FWD);
 }
 
 // Persistent over rows.  dgamma/dbeta partials live in per-warp shared-memory accumulators (only the owning
@@ -111,7 +110,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_s
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* dres, float* dx, bf16* __restrict__ dx16,  // dres may alias dx (in-place residual-grad update)
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx_colsum, int rows) {
-  pdl_sync();
+  pdl_sync_traced(TK_LN_BWD);
   extern __shared__ float ln_acc[];  // [warp][3][768]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* acc_g = ln_acc + (size_t)warp * 3 * LN_COLS;
@@ -179,6 +178,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_s
     for (int w = 0; w < LN_WARPS; ++w) s += ln_acc[(size_t)w * 3 * LN_COLS + c];
     atomicAdd(dst + (c % LN_COLS), s);
   }
+  trace_end(TK_LN_BWD);
 }
 
 }  // namespace vitk
@@ -195,7 +195,7 @@ extern "C" int vitk_layernorm_fwd(const float* x, int64_t x_stride, const float*
   if (rows == 0) return VITK_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  const int cap = sm_count() * (debug_knob(9) > 0 ? debug_knob(9) : 8);   // CTAs per SM (knob 9 for A/B: 8 measured best in-step)
+  const int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
   if (y_dtype == VITK_F32)
     VITK_LAUNCH((ln_fwd_kernel<float>), grid, LN_WARPS * 32, 0, st, x, x_stride, gamma, beta, (float*)y, mean, rstd, rows, eps);
@@ -215,12 +215,8 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, 
   VITK_CHECK_ARG(x_stride % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)dx % 16) == 0);
   if (rows == 0) return VITK_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool configured = false;
-  if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_BWD_SMEM));
-    VITK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_BWD_SMEM));
-    configured = true;
-  }
+  VITK_TRY(set_max_dyn_smem_once((const void*)ln_bwd_kernel<float>, LN_BWD_SMEM));
+  VITK_TRY(set_max_dyn_smem_once((const void*)ln_bwd_kernel<bf16>, LN_BWD_SMEM));
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   const int cap = sm_count() * 2;  // 2 CTAs per SM are co-resident (launch bounds): one persistent wave
   if (grid > cap) grid = cap;

@@ -10,9 +10,6 @@
 
 namespace vitk {
 
-static std::atomic<int> g_engine{VITK_ENGINE_AUTO};
-int default_engine() { return g_engine.load(); }
-
 // ---- optional per-launch GEMM timing (bench.py's live roofline measurement) ----------------------
 // When enabled, every GEMM launch is bracketed by CUDA events on the launching stream; the list of
 // (I, J, R, epilogue, engine, ms) is read back after a synchronize.  Off by default (no events recorded).
@@ -27,7 +24,6 @@ static int run_gemm_impl(const GemmProblem& p, int engine, int simt_splits, cuda
 }
 
 static int run_gemm(const GemmProblem& p, int engine, int simt_splits, cudaStream_t st) {
-  if (engine == VITK_ENGINE_AUTO) engine = default_engine();
   if (p.in_dtype == VITK_F32) engine = VITK_ENGINE_SIMT;  // fp32 products only exist on the FFMA pipe
   if (engine == VITK_ENGINE_AUTO) engine = VITK_ENGINE_TCGEN05;
   if (!g_prof_on.load()) return run_gemm_impl(p, engine, simt_splits, st);
@@ -47,7 +43,7 @@ static int run_gemm(const GemmProblem& p, int engine, int simt_splits, cudaStrea
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ dy, MatLayout l, int M, int C, int rows_per_block, float* __restrict__ db) {
-  pdl_sync();
+  pdl_sync_traced(TK_COLSUM);
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -62,6 +58,7 @@ colsum_kernel(const T* __restrict__ dy, MatLayout l, int M, int C, int rows_per_
     for (int w = 1; w < 8; ++w) s += red[w][tx];
     atomicAdd(db + c, s);
   }
+  trace_end(TK_COLSUM);
 }
 
 // bf16 fast path: every thread owns 8 consecutive columns (one 16-byte load per row), CHUNKS threads cover a
@@ -72,7 +69,7 @@ template <int CHUNKS>
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ dy, int64_t ld, int64_t blk_stride, int M, int rows_per_block,
                    float* __restrict__ db, int db_blk_stride) {
-  pdl_sync();
+  pdl_sync_traced(TK_COLSUM);
   constexpr int RL = 256 / CHUNKS;
   __shared__ float red[RL][CHUNKS * 8 + 1];
   const int ch = threadIdx.x % CHUNKS, rl = threadIdx.x / CHUNKS;
@@ -93,6 +90,7 @@ colsum_bf16_kernel(const bf16* __restrict__ dy, int64_t ld, int64_t blk_stride, 
     for (int r = 0; r < RL; ++r) s += red[r][c];
     atomicAdd(db + blockIdx.z * db_blk_stride + blockIdx.x * (8 * CHUNKS) + c, s);
   }
+  trace_end(TK_COLSUM);
 }
 
 static int colsum(const void* dy, int dtype, MatLayout l, int M, int C, float* db, cudaStream_t st) {
@@ -159,7 +157,7 @@ im2col_kernel(const float* __restrict__ img, T* __restrict__ patches, int batch)
 __global__ void __launch_bounds__(256)
 embed_param_grads_kernel(const float* __restrict__ dx0, int batch, float* __restrict__ dpos,
                          float* __restrict__ dcls, float* __restrict__ dbpe) {
-  pdl_sync();
+  pdl_sync_traced(TK_EMBED_GRADS);
   const int t = blockIdx.x;
   for (int j = threadIdx.x; j < VITK_DIM; j += blockDim.x) {
     float s = 0.f;
@@ -168,13 +166,12 @@ embed_param_grads_kernel(const float* __restrict__ dx0, int batch, float* __rest
     if (t == 0) dcls[j] += s;
     else atomicAdd(dbpe + j, s);
   }
+  trace_end(TK_EMBED_GRADS);
 }
 
 }  // namespace vitk
 
 using namespace vitk;
-
-extern "C" int vitk_set_gemm_engine(int engine) { return g_engine.exchange(engine); }
 
 extern "C" int vitk_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -238,7 +235,7 @@ extern "C" int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, v
   // column sums of dX (with gelu_grad: the bias gradient of the Linear in front of the GELU; without: e.g. the v section
   // of the qkv bias gradient from the proj dgrad, attention.cu): fused into the tcgen05 epilogue; the SIMT engine
   // (fp32-validate) runs the reduction kernel on the finished output instead
-  int eng = engine == VITK_ENGINE_AUTO ? default_engine() : engine;
+  int eng = engine;
   if (dtype == VITK_F32) eng = VITK_ENGINE_SIMT;
   if (eng == VITK_ENGINE_AUTO) eng = VITK_ENGINE_TCGEN05;
   p.ep.colsum = (eng == VITK_ENGINE_TCGEN05) ? dx_colsum : nullptr;

@@ -5,12 +5,18 @@
 
 namespace vitk {
 
-int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dtype, cudaStream_t st);
+int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dtype, int engine, cudaStream_t st);
 int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                      float* dqkv_colsum, int batch, int dtype, cudaStream_t st, int cs_sections);
-bool attn_bias_split_supported(int dtype);
+                      float* dqkv_colsum, int batch, int dtype, int engine, cudaStream_t st, int cs_sections);
+bool attn_bias_split_supported(int dtype, int engine);
 
-int debug_knob(int key);   // gemm_tc.cu: vitk_debug_set(8, 1) keeps the weight-gradient GEMMs on the main stream
+// vitk_model.sm_budget applies to the kernels THIS call enqueues (thread-local, restored on return)
+struct SmBudgetScope {
+  int prev;
+  bool on;
+  explicit SmBudgetScope(int n) : prev(0), on(n > 0) { if (on) prev = set_sm_budget(n); }
+  ~SmBudgetScope() { if (on) set_sm_budget(prev); }
+};
 
 constexpr int D = VITK_DIM, NT = VITK_NTOK, MLP = VITK_MLP, HID = VITK_HEAD_HIDDEN;
 
@@ -29,10 +35,7 @@ static SideStream* side_stream() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
   SideStream& ss = per_dev[dev];
   if (!ss.s) {
-    // knob 10 (A/B): 1 = lowest priority for the weight-gradient stream (the dgrad chain is the critical path)
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&ss.s, cudaStreamNonBlocking, debug_knob(10) == 1 ? lo : 0) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     for (auto& e : ss.ev)
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
@@ -138,7 +141,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 scatter_cls_grad_kernel(const float* __restrict__ dxc, float* __restrict__ dx, T* __restrict__ dx16, int64_t M,
                         float* __restrict__ colsum) {
-  pdl_sync();
+  pdl_sync_traced(TK_SCATTER_CLS);
   const int64_t total = M * (D / 4);
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = idx / (D / 4);
@@ -159,6 +162,7 @@ scatter_cls_grad_kernel(const float* __restrict__ dxc, float* __restrict__ dx, T
       *reinterpret_cast<uint2*>(dx16 + m * D + c4 * 4) = u;
     }
   }
+  trace_end(TK_SCATTER_CLS);
 }
 
 struct Ctx {
@@ -222,6 +226,7 @@ extern "C" int vitk_model_fwd(const vitk_model* m, void* stream) {
   Ctx c;
   VITK_TRY(make_ctx(m, stream, &c));
   VITK_CHECK_ARG((m->images || m->images_u8) && m->logits);
+  SmBudgetScope budget(m->sm_budget);
   const ParamOffsets& po = c.po;
   const Plan& pl = c.pl;
   const int M = c.M, dt = c.dt, eng = m->engine;
@@ -255,7 +260,7 @@ extern "C" int vitk_model_fwd(const vitk_model* m, void* stream) {
     VITK_TRY(vitk_layernorm_fwd(x, D, c.P(b.n1w), c.P(b.n1b), ln1, dt, mean1, rstd1, M, 1e-6f, st));
     VITK_TRY(vitk_linear_fwd(ln1, VITK_LAYOUT_ROWMAJOR, c.W(b.qkvw), c.P(b.qkvb), qkv, nullptr, M, 3 * D, D,
                              VITK_EPI_QKV_SCATTER, dt, eng, st));
-    VITK_TRY(attn_fwd_dispatch(qkv, ao, lse, m->batch, dt, c.st));
+    VITK_TRY(attn_fwd_dispatch(qkv, ao, lse, m->batch, dt, eng, c.st));
     VITK_TRY(vitk_linear_fwd(ao, VITK_LAYOUT_ROWMAJOR, c.W(b.projw), c.P(b.projb), xmid, x, M, D, D,
                              VITK_EPI_BIAS_RESIDUAL, dt, eng, st));
     VITK_TRY(vitk_layernorm_fwd(xmid, D, c.P(b.n2w), c.P(b.n2b), ln2, dt, mean2, rstd2, M, 1e-6f, st));
@@ -281,6 +286,7 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   VITK_TRY(make_ctx(m, stream, &c));
   VITK_CHECK_ARG(m->training && m->grads && m->dlogits);
   VITK_CHECK_ARG(stage >= 0 && stage < m->depth + 2);
+  SmBudgetScope budget(m->sm_budget);
   const ParamOffsets& po = c.po;
   const Plan& pl = c.pl;
   const int M = c.M, dt = c.dt, eng = m->engine;
@@ -325,7 +331,7 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   void* dh = ws + pl.dh;
   void* dqkv = ws + pl.dqkv;
 
-  SideStream* ss = (dt == VITK_BF16 && debug_knob(8) != 1) ? side_stream() : nullptr;
+  SideStream* ss = (dt == VITK_BF16 && !(m->flags & VITK_FLAG_WGRAD_INLINE)) ? side_stream() : nullptr;
   cudaStream_t ms = c.st;
   void* wst = ss ? (void*)ss->s : st;     // stream of the weight-gradient GEMMs
   auto after = [&](int e, cudaStream_t from, cudaStream_t to) -> int {   // `to` continues after everything enqueued on `from`
@@ -356,10 +362,10 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   // column sum of dh (softmax rows sum to one), taken in the epilogue of the GEMM that produces dh; the k section is zero
   // (rows of dS sum to zero); only the q section is summed by the attention backward's epilogue warps.  fp32 path: a
   // column-sum pass over dqkv.
-  const bool split_bias = attn_bias_split_supported(dt) && eng != VITK_ENGINE_SIMT;
+  const bool split_bias = attn_bias_split_supported(dt, eng);
   VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.projw), dh, nullptr, split_bias ? c.G(b.qkvb) + 2 * D : nullptr,
                              M, D, D, dt, eng, st));
-  VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, c.G(b.qkvb), m->batch, dt, c.st,
+  VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, c.G(b.qkvb), m->batch, dt, eng, c.st,
                              split_bias ? 1 : 7));
   VITK_TRY(after(5, ms, ss ? ss->s : ms));   // dqkv ready
   VITK_TRY(vitk_linear_wgrad(dqkv, VITK_LAYOUT_HEADMAJOR, ln1, c.G(b.qkvw), nullptr, M, 3 * D, D, dt, eng, wst));

@@ -103,9 +103,11 @@ class DataParallel(nn.Module):
         if broadcast:
             flat = module.flat_params()
             dist.broadcast(flat, src=0, group=process_group)
+            module.invalidate_shadow()   # the bf16 shadow (if a forward already built one) no longer matches the masters
         module._bucket_hook = self._on_stage
         module._finish_hook = self._on_finish
         self._first = True
+        self._n_sms = None
 
     def _on_stage(self, stage: int, lo: int, hi: int, flat_grad: torch.Tensor):
         if stage == 0:
@@ -113,18 +115,20 @@ class DataParallel(nn.Module):
         self.bucketer.add(flat_grad, lo, hi)
         if self.comm_sms and self.bucketer._works:
             # a collective is (or may still be) in flight: later stages size their persistent grids for the SMs left
-            from . import _lib as L
-            lib = L.load()
+            self.module._sm_budget = max(1, self._hw_sms() - self.comm_sms)
+
+    def _hw_sms(self) -> int:
+        if self._n_sms is None:
             import ctypes as C
+            from . import _lib as L
             n = C.c_int(0)
-            lib.vitk_device_info(C.byref(n), None, None)
-            lib.vitk_set_sm_budget(max(1, n.value - self.comm_sms))
+            L.load().vitk_device_info(C.byref(n), None, None)
+            self._n_sms = n.value
+        return self._n_sms
 
     def _on_finish(self, flat_grad: torch.Tensor):
         self.bucketer.finish(flat_grad)
-        if self.comm_sms:
-            from . import _lib as L
-            L.load().vitk_set_sm_budget(0)
+        self.module._sm_budget = 0
 
     def forward(self, x):
         return self.module(x)
@@ -143,10 +147,15 @@ class DevicePrefetcher:
     64-image fp32 batch, ~1.5 ms over PCIe 5) leaves the critical path.  Iterate it like the loader::
 
         for images, labels in DevicePrefetcher(loader, device): ...
+
+    Buffer-reuse contract: the yielded tensors are two preallocated device slots; a slot is overwritten two iterations
+    later.  Consumers that keep a batch's tensors beyond the next iteration (the reference's eval loops collect
+    ``labels`` in lists before ``.cpu()``) must copy them, or construct the prefetcher with ``clone=True``.
     """
 
-    def __init__(self, loader, device):
+    def __init__(self, loader, device, clone: bool = False):
         self.loader = loader
+        self.clone = bool(clone)
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
         self._bufs = [None, None]          # two preallocated device slots (no allocator traffic in steady state)
@@ -158,6 +167,9 @@ class DevicePrefetcher:
                               for s, d in zip(batch, dst)) or len(dst) != len(batch):
             dst = [torch.empty(s.shape, dtype=s.dtype, device=self.device) if torch.is_tensor(s) else None for s in batch]
             self._bufs[slot] = dst
+            # fresh memory from the caching allocator may be a block whose last user is still queued on the compute
+            # stream: the copy stream must not write it before that work has drained
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
         if self._free[slot] is not None:
             self.stream.wait_event(self._free[slot])   # the step that last read this slot has finished on the GPU
         with torch.cuda.stream(self.stream):
@@ -186,7 +198,7 @@ class DevicePrefetcher:
                 nxt = None
             compute = torch.cuda.current_stream(self.device)
             compute.wait_event(ev)
-            yield cur
+            yield tuple(t.clone() if torch.is_tensor(t) else t for t in cur) if self.clone else cur
             # everything the consumer enqueued for this batch is now in the compute stream: mark the slot reusable
             done = torch.cuda.Event()
             done.record(compute)

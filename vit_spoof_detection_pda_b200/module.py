@@ -147,6 +147,8 @@ class ViTFaceAntiSpoofing(nn.Module):
         self._bucket_hook = None   # set by DataParallel: fn(stage, lo, hi) after each backward stage
         self._finish_hook = None   # set by DataParallel: fn() before gradients are handed to autograd
         self._pending_clip = None  # (sumsq tensor, max_norm) left by clip_grad_norm_ for FusedAdam
+        self._sm_budget = 0        # set by DataParallel while a collective is in flight (vitk_model.sm_budget)
+        self._flags = 0            # vitk_model.flags (L.FLAG_*)
         self.last_masks = None
         for p in self.parameters():
             p._vitk_owner = weakref.ref(self)
@@ -223,7 +225,14 @@ class ViTFaceAntiSpoofing(nn.Module):
         return plist
 
     def _params_version(self, plist) -> int:
-        return sum(p._version for p in plist)
+        # version counters of the Parameters plus the flat buffer's own (writes through flat_params(), dist.broadcast)
+        return sum(p._version for p in plist) + (self._flat._version if self._flat is not None else 0)
+
+    def invalidate_shadow(self):
+        """Force the bf16 weight shadow to be rebuilt before the next forward.  Call after writing the fp32 masters in a
+        way that bypasses the Parameters' version counters (``p.data.copy_()``, raw writes through ``flat_params()`` on
+        another stream, external collectives)."""
+        self._shadow_version = -1
 
     def _ensure_shadow(self, plist):
         if self.precision != "bf16":
@@ -313,6 +322,8 @@ class ViTFaceAntiSpoofing(nn.Module):
         m.mask1 = L.ptr(masks[0]) if masks else None
         m.mask2 = L.ptr(masks[1]) if masks else None
         m.frozen_backbone = 1 if frozen else 0
+        m.sm_budget = int(self._sm_budget)
+        m.flags = int(self._flags)
         return m
 
     # ImageNet statistics of the reference's transforms.Normalize (train_advanced.py:175, 181; test.py:162)
@@ -403,9 +414,14 @@ class ViTFaceAntiSpoofing(nn.Module):
         n_stages = 1 if frozen else self.depth + 2
         for s in range(n_stages):
             L.call("vitk_model_bwd_stage", C.byref(m), s, st)
-            if self._bucket_hook is not None and not aliased:
+            # data parallel: every backward reduces the gradient IT produced -- also the micro-step gradients of a
+            # gradient-accumulation loop and the backward after zero_grad(set_to_none=False), which land in the second
+            # buffer (`aliased`) before autograd adds them to .grad.  The all-reduce is linear, so reducing each micro-step
+            # and accumulating equals torch DDP's result.
+            if self._bucket_hook is not None:
                 self._bucket_hook(s, ranges[s][0], ranges[s][1], g)
-        if self._finish_hook is not None and not aliased:
+                m.sm_budget = int(self._sm_budget)   # a collective now in flight owns some SMs (dp.py)
+        if self._finish_hook is not None:
             self._finish_hook(g)
         outs = []
         for p, off, n in zip(plist, self._offsets, self._sizes):

@@ -7,6 +7,8 @@ weight_decay 1e-4 (L2), which is ``adamw=False`` here.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -42,6 +44,7 @@ def _gather_flat_grads(owner, params):
         return g
     owner._gathered_serial = serial
     base = g.data_ptr()
+    foreign = []
     for p, off, n in zip(owner._param_list(), owner._offsets, owner._sizes):
         if p.grad is None:
             if p.requires_grad:
@@ -49,26 +52,50 @@ def _gather_flat_grads(owner, params):
             continue
         if p.grad.data_ptr() != base + 4 * off:
             g[off:off + n].copy_(p.grad.reshape(-1))   # foreign gradient tensor (cloned / accumulated elsewhere)
+            foreign.append((p, off, n))
+    owner._foreign_grads = foreign
     return g
 
 
-def clip_grad_norm_(parameters, max_norm: float):
-    """Drop-in for ``torch.nn.utils.clip_grad_norm_`` on a vitk model: one deterministic sum-of-squares
-    reduction over the flat gradient buffer; the scaling itself is folded into the next FusedAdam.step().
-    Returns the total norm (0-dim tensor)."""
-    if isinstance(parameters, torch.Tensor):
-        parameters = [parameters]
-    owner, params = _owner_of(parameters, materialize=False)
-    g = _gather_flat_grads(owner, params)
+def _scale_grads_now(owner, g, mult: float, sumsq, max_norm: float):
+    """Eager in-place g *= mult * clipcoef over the flat buffer (and back into any gradient tensor that is not a view of
+    it), for callers that pair ONE fused piece with stock torch ones -- e.g. FusedGradScaler.unscale_ followed by
+    torch.nn.utils.clip_grad_norm_, or this module's clip_grad_norm_ in front of a stock torch optimizer."""
+    L.call("vitk_grad_scale", L.ptr(g), g.numel(), float(mult), L.ptr(sumsq), float(max_norm), L.stream_ptr())
+    for p, off, n in getattr(owner, "_foreign_grads", []) or []:
+        p.grad.copy_(g[off:off + n].view(p.grad.shape))
+
+
+def _sumsq(owner, g):
     lib = L.load()
     if getattr(owner, "_sumsq_scratch", None) is None:
         owner._sumsq_scratch = torch.empty(lib.vitk_grad_sumsq_scratch_floats(), dtype=torch.float32, device=g.device)
         owner._sumsq = torch.zeros(1, dtype=torch.float32, device=g.device)
     L.call("vitk_grad_sumsq", L.ptr(g), g.numel(), L.ptr(owner._sumsq_scratch), L.ptr(owner._sumsq), L.stream_ptr())
-    owner._pending_clip = (owner._sumsq, float(max_norm))
-    mult = getattr(owner, "_grad_mult", 1.0)     # 1/scale after FusedGradScaler.unscale_ (folded into the Adam pass)
-    norm = owner._sumsq.sqrt().reshape(())
-    return norm * mult if mult != 1.0 else norm
+    return owner._sumsq
+
+
+def clip_grad_norm_(parameters, max_norm: float):
+    """Drop-in for ``torch.nn.utils.clip_grad_norm_`` on a vitk model: one deterministic sum-of-squares
+    reduction over the flat gradient buffer.  When a FusedAdam drives the model the scaling itself is folded into
+    its next step() (no extra pass over the gradients); with any other optimizer the gradients are scaled in place
+    right here, like torch's.  Returns the total norm (0-dim tensor)."""
+    if isinstance(parameters, torch.Tensor):
+        parameters = [parameters]
+    owner, params = _owner_of(parameters, materialize=False)
+    g = _gather_flat_grads(owner, params)
+    sumsq = _sumsq(owner, g)
+    mult = getattr(owner, "_grad_mult", 1.0)     # 1/scale after a LAZY FusedGradScaler.unscale_ (folded into the Adam pass)
+    norm = sumsq.sqrt().reshape(())
+    norm = norm * mult if mult != 1.0 else norm
+    fused_ref = getattr(owner, "_fused_opt", None)
+    if fused_ref is not None and fused_ref() is not None:
+        owner._pending_clip = (sumsq, float(max_norm))
+    else:
+        _scale_grads_now(owner, g, mult, sumsq, float(max_norm))
+        owner._grad_mult = 1.0
+        owner._pending_clip = None
+    return norm
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -82,6 +109,7 @@ class FusedAdam(torch.optim.Optimizer):
         if len(self.param_groups) != 1:
             raise ValueError("FusedAdam supports a single param group (the reference uses one)")
         self._owner, _ = _owner_of(self.param_groups[0]["params"])
+        self._owner._fused_opt = weakref.ref(self)   # clip_grad_norm_ may leave its scaling to this optimizer's pass
         self.max_grad_norm = max_grad_norm
         self.grad_mult = grad_mult
         self._step = 0
@@ -175,13 +203,18 @@ class FusedGradScaler:
     """``torch.cuda.amp.GradScaler`` for the fused path (the reference builds one at train_advanced.py:609 and drives it at
     :330-336: ``scaler.scale(loss).backward(); scaler.unscale_(optimizer); clip_grad_norm_(...); scaler.step(optimizer);
     scaler.update()``).  Same API and state machine -- skip the step when a gradient is non-finite, halve the scale, double
-    it after ``growth_interval`` clean steps -- but the unscale never touches memory: 1/scale is folded into the single
-    sum-of-squares + Adam pass (``grad_mult``), and the finiteness test is the finiteness of that one sum of squares.
-    Like torch's, ``step`` reads one scalar back (one host sync per step; the reference loop has two more at :345-346).
-    bf16 needs no loss scaling; this exists so the reference's loop runs unmodified."""
+    it after ``growth_interval`` clean steps.
+
+    ``unscale_`` divides the gradients in place (one pass over the flat buffer), so whatever follows it -- the stock
+    ``torch.nn.utils.clip_grad_norm_`` of the reference loop or this package's -- sees true gradients.
+    ``lazy_unscale=True`` is the fully fused variant: ``unscale_`` touches no memory, 1/scale is folded into the single
+    sum-of-squares + Adam pass; it is only correct with THIS package's ``clip_grad_norm_`` and ``FusedAdam`` and raises
+    otherwise.  The finiteness test is the finiteness of one sum of squares; like torch's, ``step`` reads one scalar back
+    (one host sync per step; the reference loop has two more at :345-346).  bf16 needs no loss scaling; this exists so the
+    reference's loop runs unmodified."""
 
     def __init__(self, init_scale: float = 2.0 ** 16, growth_factor: float = 2.0, backoff_factor: float = 0.5,
-                 growth_interval: int = 2000, enabled: bool = True):
+                 growth_interval: int = 2000, enabled: bool = True, lazy_unscale: bool = False):
         self._enabled = bool(enabled)
         self._scale = float(init_scale)
         self._growth_factor, self._backoff_factor = float(growth_factor), float(backoff_factor)
@@ -189,6 +222,7 @@ class FusedGradScaler:
         self._growth_tracker = 0
         self._found_inf = False
         self._unscaled = False
+        self._lazy = bool(lazy_unscale)
 
     def is_enabled(self):
         return self._enabled
@@ -199,25 +233,41 @@ class FusedGradScaler:
     def scale(self, outputs):
         return outputs * self._scale if self._enabled else outputs
 
+    @staticmethod
+    def _owner(optimizer):
+        owner = getattr(optimizer, "_owner", None)
+        if owner is None:
+            owner, _ = _owner_of(optimizer.param_groups[0]["params"][:1])
+        return owner
+
     def unscale_(self, optimizer):
         if not self._enabled:
             return
         if self._unscaled:
             raise RuntimeError("unscale_() has already been called on this optimizer since the last update().")
-        optimizer._owner._grad_mult = 1.0 / self._scale
+        owner = self._owner(optimizer)
+        if self._lazy:
+            if not isinstance(optimizer, FusedAdam):
+                raise TypeError("FusedGradScaler(lazy_unscale=True) needs FusedAdam: the factor is applied inside its pass")
+            owner._grad_mult = 1.0 / self._scale
+        else:
+            g = _gather_flat_grads(owner, None)
+            _scale_grads_now(owner, g, 1.0 / self._scale, None, 0.0)
         self._unscaled = True
 
     def step(self, optimizer, *args, **kwargs):
         if not self._enabled:
             return optimizer.step(*args, **kwargs)
-        if not isinstance(optimizer, FusedAdam):
-            raise TypeError("FusedGradScaler drives FusedAdam; use torch.amp.GradScaler with stock torch optimizers")
-        owner = optimizer._owner
+        owner = self._owner(optimizer)
         if not self._unscaled:
             self.unscale_(optimizer)
-        if owner._pending_clip is None:          # no clip_grad_norm_ this step: still need the sum of squares
-            clip_grad_norm_(optimizer.param_groups[0]["params"][:1], 0.0)
-        sumsq = owner._pending_clip[0]
+        if owner._pending_clip is not None:
+            sumsq = owner._pending_clip[0]           # this package's clip_grad_norm_ ran after unscale_: reuse its reduction
+        else:
+            # none, or the stock torch clip (which rescales in place: non-finite values stay non-finite)
+            sumsq = _sumsq(owner, _gather_flat_grads(owner, None))
+            if self._lazy:
+                owner._pending_clip = (sumsq, 0.0)
         self._found_inf = not bool(torch.isfinite(sumsq).item())
         if self._found_inf:
             owner._pending_clip = None
