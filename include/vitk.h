@@ -109,26 +109,30 @@ int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, float* dw, f
                       int M, int N, int K, int dtype, int engine, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Patch embedding (timm PatchEmbed.proj = Conv2d(3,768,k16,s16) + _pos_embed; K1,K2).
- *   fwd  : x0[b,1+p,:] = patch(b,p) . Wpe^T + bpe + pos[1+p] ; x0[b,0,:] = cls + pos[0]   (fp32 out)
- *          `patches` is caller scratch [B*197][768] of `dtype`: the cast image regrouped per token
- *          (row b*197+t, k = c*256+i*16+j), CLS rows (t = 0) zero, so fwd and wgrad are plain
- *          token-row GEMMs and the CLS/pos handling lives in the GEMM epilogue.
+ * Patch embedding (timm PatchEmbed.proj = Conv2d(3,768,k16,s16) + _pos_embed; K1,K2) as an im2col-free GEMM: the patch
+ * matrix is never materialised in global memory.  VITK_PREC_BF16 (tcgen05 engine): TMA boxes of a 5-D tensor map over the
+ * NCHW fp32 image -- or over the uint8 HWC image -- land in shared memory, converter warps write the bf16 operand tile
+ * (ToTensor + Normalize first on the uint8 edge), tcgen05.mma consumes it against the bf16 weight shadow.
+ * VITK_PREC_FP32_VALIDATE / VITK_ENGINE_SIMT: the FFMA GEMM reads the image in place.
+ *   fwd  : x0[b,1+p,:] = patch(b,p) . Wpe^T + bpe + pos[1+p] ; x0[b,0,:] = cls + pos[0]   (fp32 out, [B*197][768])
+ *          wpe = fp32 [768][3*16*16] (vit.patch_embed.proj.weight); wpe16 = its bf16 shadow (tcgen05 path; NULL otherwise)
  *   wgrad: dWpe += dx0^T patches ; dbpe += colsum(dx0[:,1:]) ; dpos += sum_b dx0 ; dcls += sum_b dx0[b,0]
- *          `dx0_act` = dx0 in `dtype` (row-major [B*197][768]); images need no gradient.
+ *          dx0 = fp32 gradient of x0 ([B*197][768]); dx0_bf16 = the same in bf16 (tcgen05 path; NULL otherwise);
+ *          images = the fp32 NCHW input; images need no gradient.
  * ------------------------------------------------------------------------------------------- */
-int vitk_patch_embed_fwd(const float* images, const void* wpe, const float* bpe, const float* cls,
-                         const float* pos, void* patches, float* x0, int batch, int dtype, int engine,
-                         void* stream);
+int vitk_patch_embed_fwd(const float* images, const float* wpe, const void* wpe16, const float* bpe, const float* cls,
+                         const float* pos, float* x0, int batch, int precision, int engine, void* stream);
 /* same forward from uint8 HWC pixels [B][224][224][3]: ToTensor (x / 255) + Normalize ((x - mean[c]) / std[c]) of the
  * reference's transforms (train_advanced.py:174-175, 180-181; test.py get_test_transforms) fused into the patch loader:
- * 150 KB instead of 602 KB read per image, no fp32 NCHW tensor materialised */
-int vitk_patch_embed_fwd_u8(const uint8_t* images_hwc, const float* mean3, const float* std3, const void* wpe,
-                            const float* bpe, const float* cls, const float* pos, void* patches, float* x0, int batch,
-                            int dtype, int engine, void* stream);
-int vitk_patch_embed_wgrad(const float* dx0, const void* dx0_act, const void* patches, float* dwpe,
-                           float* dbpe, float* dcls, float* dpos, int batch, int dtype, int engine,
-                           void* stream);
+ * 150 KB instead of 602 KB read per image, no fp32 NCHW tensor materialised on the bf16 path.  nchw_scratch (fp32
+ * [B][3][224][224], may be NULL on the bf16 / tcgen05 path) is only written by the fp32-validate / SIMT path. */
+int vitk_patch_embed_fwd_u8(const uint8_t* images_hwc, const float* mean3, const float* std3, const float* wpe,
+                            const void* wpe16, const float* bpe, const float* cls, const float* pos, float* x0,
+                            float* nchw_scratch, int batch, int precision, int engine, void* stream);
+/* ToTensor + Normalize alone: uint8 HWC -> fp32 NCHW (the weight gradient of a uint8-fed training step reads this) */
+int vitk_u8_to_nchw(const uint8_t* images_hwc, const float* mean3, const float* std3, float* out, int batch, void* stream);
+int vitk_patch_embed_wgrad(const float* dx0, const void* dx0_bf16, const float* images, float* dwpe, float* dbpe,
+                           float* dcls, float* dpos, int batch, int precision, int engine, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-head self-attention core, N=197, d=64, 12 heads, scale 1/8, no mask, no dropout

@@ -25,9 +25,12 @@ KID = {1: "gemm_tc", 2: "attn_fwd", 3: "attn_bwd", 4: "ln_fwd", 5: "ln_bwd", 6: 
        17: "eval", 18: "patch_wgrad"}
 
 
+DETAIL_PHASES, DETAIL_SLOTS = 24, 64
+
+
 def parse(buf):
     n = min(int(buf[0]), int(buf[1]))
-    rec = buf[2:2 + 3 * n].reshape(n, 3)
+    rec = buf[4:4 + 3 * n].reshape(n, 3)
     t = rec[:, 0]
     tag = rec[:, 1]
     aux = rec[:, 2]
@@ -54,6 +57,15 @@ def parse(buf):
     return launches, n
 
 
+def detail_of(buf, kid):
+    """Kernel-internal marks of CTA 0 of the LAST launch of kernel `kid`: {phase: [time ns per slot]} (0 = not written)."""
+    off = int(buf[2])
+    if off == 0:
+        return {}
+    area = buf[off + kid * DETAIL_PHASES * DETAIL_SLOTS: off + (kid + 1) * DETAIL_PHASES * DETAIL_SLOTS].reshape(DETAIL_PHASES, DETAIL_SLOTS)
+    return {8 + p: area[p].tolist() for p in range(DETAIL_PHASES) if int(area[p].max()) > 0}
+
+
 def name_of(ln):
     nm = KID.get(ln["kid"], str(ln["kid"]))
     if ln["kid"] == 1:
@@ -66,6 +78,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--out", default="gpurun_out/timeline")
+    ap.add_argument("--detail", action="store_true", help="also write the kernel-internal marks of CTA 0 (<out>_detail.md)")
     a = ap.parse_args()
     lib = L.load()
     assert lib.vitk_is_dev_build() == 1, "run with VITK_LIB=dev (libvitk_dev.so)"
@@ -94,7 +107,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms_untraced = e0.elapsed_time(e1) / 10
-    buf = torch.zeros(3 * 400_000 + 2, dtype=torch.int64, device=dev)
+    buf = torch.zeros(3 * 400_000 + 4 + 32 * DETAIL_PHASES * DETAIL_SLOTS, dtype=torch.int64, device=dev)
     L.check(lib.vitk_trace_start(buf.data_ptr(), buf.numel() * 8), "trace_start")
     e0.record()
     for i in range(2):       # the second traced step is the one reported (host run-ahead has refilled the queue)
@@ -149,6 +162,20 @@ def main():
                 "up to more than 100 %)\n\n## launches in order\n\n| # | kernel | ready (us) | dur (us) | CTAs | CTA-start lead (us) |\n|---:|---|---:|---:|---:|---:|\n")
         for i, r in enumerate(rows):
             f.write(f"| {i} | `{r['kernel']}` | {r['ready_us']:.1f} | {r['dur_us']:.1f} | {r['ctas']} | {r['ready_us'] - r['start_us']:.1f} |\n")
+    if a.detail:
+        hb = buf.cpu()
+        with open(a.out + "_detail.md", "w") as f:
+            for kid in (3, 12):
+                d = detail_of(hb, kid)
+                if not d:
+                    continue
+                ev = sorted((tt, ph, slot) for ph, arr in d.items() for slot, tt in enumerate(arr) if tt > 0)
+                t0 = ev[0][0]
+                f.write(f"## {KID.get(kid, kid)}: kernel-internal marks of CTA 0, last launch ({len(ev)} marks; t in us from the first)\n\n"
+                        "| t (us) | phase | slot (aux & 63) |\n|---:|---:|---:|\n")
+                for tt, ph, slot in ev:
+                    f.write(f"| {(tt - t0) / 1e3:.2f} | {ph} | {slot} |\n")
+                f.write("\n")
     print(f"step {ms_untraced:.3f} ms (dev build, untraced) / {ms_traced:.3f} ms traced; {len(rows)} launches; span {span / 1e3:.3f} ms; "
           f"busy {busy / 1e3:.3f} ms; wrote {a.out}.md/.json")
 

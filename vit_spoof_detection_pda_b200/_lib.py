@@ -48,7 +48,8 @@ PROTOTYPES = {
     "vitk_linear_dgrad": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "vitk_linear_wgrad": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "vitk_patch_embed_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
-    "vitk_patch_embed_fwd_u8": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "vitk_patch_embed_fwd_u8": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "vitk_u8_to_nchw": (i32, [vp, vp, vp, vp, i32, vp]),
     "vitk_patch_embed_wgrad": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "vitk_attn_fwd": (i32, [vp, vp, vp, i32, i32, vp]),
     "vitk_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp]),

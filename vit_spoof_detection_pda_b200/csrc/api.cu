@@ -116,10 +116,16 @@ int vitk_is_dev_build(void) {
 // libvitk kernel appends three 64-bit words per mark (see common.cuh) until vitk_trace_stop().  Both calls synchronise the device.
 int vitk_trace_start(void* buf, size_t bytes) {
 #ifdef VITK_DEV
-  VITK_CHECK_ARG(buf && bytes >= 64);
+  // layout (64-bit words): [0] marks written, [1] mark capacity, [2] word offset of the detail area, [3] unused,
+  // [4 ..] marks of 3 words, then the detail area: 32 kernels x 24 phases x 64 slots
+  const size_t detail_words = 32 * 24 * 64;
+  VITK_CHECK_ARG(buf && bytes >= (detail_words + 64) * 8);
   VITK_CUDA(cudaDeviceSynchronize());
-  const unsigned long long hdr[2] = {0ull, (unsigned long long)((bytes - 16) / 24)};
+  const size_t words = bytes / 8;
+  const unsigned long long cap = (words - 4 - detail_words) / 3;
+  const unsigned long long hdr[4] = {0ull, cap, 4 + 3 * cap, 0ull};
   VITK_CUDA(cudaMemcpy(buf, hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+  VITK_CUDA(cudaMemset(reinterpret_cast<unsigned long long*>(buf) + hdr[2], 0, detail_words * 8));
   vitk::trace_set_all(reinterpret_cast<unsigned long long*>(buf));
   VITK_CUDA(cudaDeviceSynchronize());
   return VITK_OK;

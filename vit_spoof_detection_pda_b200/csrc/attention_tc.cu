@@ -17,6 +17,7 @@
 // Algorithmic FLOPs per item: 4 * 197^2 * 64; exps: 197 * 208 (MUFU-bound: 16/clk/SM).
 #include <cuda.h>
 #include <string.h>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -150,25 +151,23 @@ __device__ __forceinline__ float ex2(float x) {
 //   nullptr when row r must not be written.
 //   colsum (optional, 32 floats, 32-byte aligned): += column sums of the bf16 values of the rows that are written (the qkv
 //   bias gradient), read back from the staged tile.
+__device__ __forceinline__ void pack_slab32(const uint32_t (&o)[32], float scale, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(__uint_as_float(o[2 * e]) * scale, __uint_as_float(o[2 * e + 1]) * scale);
+}
 template <typename RowPtr>
-__device__ __forceinline__ void store_slab32(uint32_t stg, int lane, const uint32_t (&o)[32], float scale, RowPtr row_ptr,
-                                             float* colsum = nullptr) {
+__device__ __forceinline__ void store_slab_packed(uint32_t stg, int lane, const uint32_t (&pk)[16], RowPtr row_ptr, float* colsum = nullptr) {
 #pragma unroll
   for (int k4 = 0; k4 < 4; ++k4) {
     const uint32_t a = stg + (uint32_t)(lane * 64 + ((k4 ^ ((lane >> 1) & 3)) << 4));
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
-                 "r"(pack_bf16x2(__uint_as_float(o[8 * k4 + 0]) * scale, __uint_as_float(o[8 * k4 + 1]) * scale)),
-                 "r"(pack_bf16x2(__uint_as_float(o[8 * k4 + 2]) * scale, __uint_as_float(o[8 * k4 + 3]) * scale)),
-                 "r"(pack_bf16x2(__uint_as_float(o[8 * k4 + 4]) * scale, __uint_as_float(o[8 * k4 + 5]) * scale)),
-                 "r"(pack_bf16x2(__uint_as_float(o[8 * k4 + 6]) * scale, __uint_as_float(o[8 * k4 + 7]) * scale)) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * k4]), "r"(pk[4 * k4 + 1]), "r"(pk[4 * k4 + 2]),
+                 "r"(pk[4 * k4 + 3]) : "memory");
   }
   __syncwarp();
   if (colsum) {
     // lane reads the 16-byte chunk (lane & 3) -- 8 columns -- of rows (lane >> 2) + 8 j: four conflict-free 128-bit loads
     // cover the tile; the 8 lanes that share a chunk are then summed with three shuffle stages and lanes 0..3 add their
-    // 8 columns to global memory with two vector reductions.  (These warps gate the recycling of the dV/dK/dQ
-    // accumulators, so every cycle here is on the kernel's critical path: the first version, 32 two-byte loads per lane
-    // and one atomic per lane, cost 27 us of a 104 us launch.)
+    // 8 columns to global memory with two vector reductions.
     float cs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) cs[i] = 0.f;
@@ -208,6 +207,13 @@ __device__ __forceinline__ void store_slab32(uint32_t stg, int lane, const uint3
     if (dst) *reinterpret_cast<uint4*>(dst + k4 * 8) = u;
   }
   __syncwarp();
+}
+template <typename RowPtr>
+__device__ __forceinline__ void store_slab32(uint32_t stg, int lane, const uint32_t (&o)[32], float scale, RowPtr row_ptr,
+                                             float* colsum = nullptr) {
+  uint32_t pk[16];
+  pack_slab32(o, scale, pk);
+  store_slab_packed(stg, lane, pk, row_ptr, colsum);
 }
 
 // instruction descriptor: D = f32, A = B = bf16, majors, N >> 3, M = 128
@@ -291,6 +297,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const uint32_t par = it & 1;
       const uint32_t sq = sbase + s * STAGE_BYTES, sk = sq + Q_BYTES, sv = sk + KV_BYTES;
       mbar_wait(ld_full(s), (it >> 1) & 1);
+#pragma unroll
       for (int t = 0; t < 2; ++t) {
         mbar_wait(t_free(t), par ^ 1);     // the previous item's O_t has been read out of tensor memory
         tc_fence_after();
@@ -302,6 +309,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         __syncwarp();
       }
+#pragma unroll
       for (int t = 0; t < 2; ++t) {
         mbar_wait(p_full(t), par);         // P_t (bf16) is in tensor memory columns [208t, 208t + 104)
         tc_fence_after();
@@ -492,7 +500,7 @@ static int make_hm_map(const void* base, int64_t M, int n_blk, int box_rows, CUt
 // ================================================================================================
 constexpr uint32_t B_SK = 0, B_SV = 32768, B_SQ = 65536, B_SDO = 98304, B_SDS = 131072;   // byte offsets
 constexpr uint32_t B_SL = B_SDS + 65536, B_SD = B_SL + 2048, B_STG = B_SD + 2048, B_BAR = B_STG + 4 * 2048;
-constexpr int BWD_THREADS = 64 + 8 * 32 + 4 * 32;   // producer, MMA issuer, 8 softmax warps, 4 epilogue / delta warps
+constexpr int BWD_THREADS = 64 + 8 * 32 + 4 * 32 + 2 * 32;   // producer, MMA issuer, 8 softmax warps, 4 epilogue warps, 2 delta warps
 constexpr size_t BWD_SMEM = 1024 + B_BAR + 512;
 constexpr uint32_t T_DV = 256, T_DK = 320, T_DQ = 384;
 
@@ -503,9 +511,62 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
 
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+// lean MMA issue: 64-bit descriptors = (running low word, constant high word); accumulate flag known at compile time
+template <bool ACC>
+__device__ __forceinline__ void mma_ss_c(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void mma_ts_c(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(hi), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
+// The MMAs of one backward step, step index S = 4 t + c known at compile time (key tile t, query chunk c, buffer S & 1).
+struct BwdMma {
+  uint32_t tmem, hi, kK, kV, kQ, kdO, kDS;     // descriptor low words of the operand bases (byte offsets add as (off >> 4))
+  template <int S, int K = 0>
+  __device__ __forceinline__ void front() {    // S^T = K_t Q_c^T, dP^T = V_t dO_c^T (two interleaved accumulation chains)
+    constexpr int t = S >> 2, c = S & 3, buf = S & 1;
+    constexpr uint32_t idesc = c < 3 ? make_idesc(64, 0, 0) : make_idesc(16, 0, 0);
+    mma_ss_c<(K > 0)>(tmem + buf * 128, kK + ((t * 16384 + K * 32) >> 4), kQ + ((c * 8192 + K * 32) >> 4), hi, idesc);
+    mma_ss_c<(K > 0)>(tmem + buf * 128 + 64, kV + ((t * 16384 + K * 32) >> 4), kdO + ((c * 8192 + K * 32) >> 4), hi, idesc);
+    if constexpr (K < 3) front<S, K + 1>();
+  }
+  template <int S, int KS = 0>
+  __device__ __forceinline__ void back_vk() {  // dV_t += P^T dO_c, dK_t += dS^T Q_c (A from tensor memory)
+    constexpr int c = S & 3, buf = S & 1, nks = c < 3 ? 4 : 1;
+    constexpr uint32_t idesc = make_idesc(64, 0, 1);
+    mma_ts_c<(c > 0 || KS > 0)>(tmem + T_DV, tmem + buf * 128 + KS * 8, kdO + ((c * 8192 + KS * 2048) >> 4), hi, idesc);
+    mma_ts_c<(c > 0 || KS > 0)>(tmem + T_DK, tmem + buf * 128 + 64 + KS * 8, kQ + ((c * 8192 + KS * 2048) >> 4), hi, idesc);
+    if constexpr (KS + 1 < nks) back_vk<S, KS + 1>();
+  }
+  template <int S, int KS = 0>
+  __device__ __forceinline__ void back_q() {   // dQ_m += dS_(m,t) K_t (A = dS^T in shared memory, read MN-major)
+    constexpr int t = S >> 2, m = (S & 3) >> 1;
+    constexpr uint32_t idesc = make_idesc(64, 1, 1);
+    mma_ss_c<(t > 0 || KS > 0)>(tmem + T_DQ + m * 64, kDS + ((m * 32768 + KS * 2048) >> 4), kK + ((t * 16384 + KS * 2048) >> 4), hi, idesc);
+    if constexpr (KS < 7) back_q<S, KS + 1>();
+  }
+};
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)   // 512 threads x 128 registers = the whole register file
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
-                   const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ out, const float* __restrict__ lse,
+                   const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ out, const bf16* __restrict__ dout_g,
+                   const float* __restrict__ lse,
                    bf16* __restrict__ dqkv, float* __restrict__ dqkv_colsum, int cs_sections, int batch, int n_items, int dbg_in) {
 #ifdef VITK_DEV
   const int dbg = dbg_in;      // timing experiments (bit 0 no MMAs, 1 no softmax math, 2 no draining, 3 no delta, 4 no loads)
@@ -527,8 +588,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
   auto p_full = [&](int b) { return bars + 8u * (14 + b); };    // 14,15
   auto ds_free = [&](int m) { return bars + 8u * (16 + m); };   // 16,17
   const uint32_t dvk_full = bars + 8u * 18, dvk_free = bars + 8u * 19, dq_full = bars + 8u * 20, dq_free = bars + 8u * 21;
-  auto delta_ready = [&](int c) { return bars + 8u * (22 + c); };   // 22..25
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + B_BAR + 8 * 26);
+  auto delta_ready = [&](int par, int c) { return bars + 8u * (22 + par * 4 + c); };   // 22..29: item parity x chunk
+  auto ld_free = [&](int par) { return bars + 8u * (30 + par); };   // 30,31: the L / delta buffer of that item parity has been consumed
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + B_BAR + 8 * 32);
   // L_q = lse_q * log2(e) and delta_q = dO_q . O_q, double-buffered by item parity: [2][256] floats each
   float* sL = reinterpret_cast<float*>(smem + B_SL);
   float* sD = reinterpret_cast<float*>(smem + B_SD);
@@ -538,9 +600,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_kv)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_do)) : "memory");
-    for (int i = 0; i < 2; ++i) { mbar_init(kv_full(i), 1); mbar_init(kv_free(i), 1); mbar_init(st_full(i), 1); mbar_init(p_full(i), 8); mbar_init(ds_free(i), 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(qd_full(i), 1); mbar_init(qd_free(i), 1); mbar_init(delta_ready(i), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(kv_full(i), 1); mbar_init(kv_free(i), 1); mbar_init(st_full(i), 1); mbar_init(p_full(i), 4); mbar_init(ds_free(i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(qd_full(i), 1); mbar_init(qd_free(i), 1); mbar_init(delta_ready(0, i), 2); mbar_init(delta_ready(1, i), 2); }
     mbar_init(dvk_full, 1); mbar_init(dvk_free, 4); mbar_init(dq_full, 1); mbar_init(dq_free, 4);
+    mbar_init(ld_free(0), 8); mbar_init(ld_free(1), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -593,62 +656,54 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // One elected lane issues ~20 MMAs per step; what it costs per MMA in instructions IS the step time (measured with the
+    // kernel-internal trace marks of the development build: with run-time step indices -- multiplies, shifts and branches per
+    // descriptor -- the issue thread needed ~4,000 clocks per step while the softmax warps needed ~2,300 and the tensor
+    // pipe ~650).  The eight steps of an item are therefore UNROLLED AT COMPILE TIME (template step index): every
+    // descriptor low word is a base register plus an immediate, the accumulate predicates are constants.
     const bool leader = elect_one();
     const bool do_mma = !(dbg & 1);
-    constexpr uint32_t ID_S64 = make_idesc(64, 0, 0), ID_S16 = make_idesc(16, 0, 0);   // S^T / dP^T chunks
-    constexpr uint32_t ID_TS = make_idesc(64, 0, 1);                                    // dV, dK: A in TMEM, B MN-major
-    constexpr uint32_t ID_DQ = make_idesc(64, 1, 1);                                    // dQ: A, B MN-major
-    const uint32_t sK = sbase + B_SK, sV = sbase + B_SV, sQ = sbase + B_SQ, sdO = sbase + B_SDO, sDS = sbase + B_SDS;
+    unsigned long long* trd = lane == 0 ? trace_detail_base(TK_ATTN_BWD) : nullptr;
+    BwdMma mm;
+    mm.tmem = tmem_base;
+    mm.hi = DESC_HI;
+    mm.kK = desc_lo(sbase + B_SK); mm.kV = desc_lo(sbase + B_SV); mm.kQ = desc_lo(sbase + B_SQ); mm.kdO = desc_lo(sbase + B_SDO);
+    mm.kDS = desc_lo_mn(sbase + B_SDS, 16384);
     for (int it = 0; it < n_my; ++it) {
       const uint32_t ipar = it & 1;
-      // front(s): MMA1, MMA2 of step s;  back(s): MMA3, MMA4 (and MMA5 after odd chunks) of step s
-      auto front = [&](int s) {
-        const int t = s >> 2, c = s & 3, buf = s & 1;
+      // front<S>: MMA1, MMA2 of step S;  back<S>: MMA3, MMA4 (and MMA5 after odd chunks) of step S
+      auto front = [&](auto S) {
+        constexpr int s = decltype(S)::value, t = s >> 2, c = s & 3, buf = s & 1;
         if (c == 0) mbar_wait(kv_full(t), ipar);
         if (t == 0) mbar_wait(qd_full(c), ipar);
         tc_fence_after();
+        trace_detail(trd, 8, it * 8 + s);      // front(s): operands landed, MMA1/2 issued now
         if (leader) {
-          const uint32_t idesc = c < 3 ? ID_S64 : ID_S16;
-          const uint32_t d_st = tmem_base + buf * 128, d_dp = d_st + 64;
-          if (do_mma) {
-            // the two accumulation chains are interleaved: consecutive MMAs on one accumulator are dependent
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              mma_ss(d_st, desc_lo(sK + t * 16384 + k * 32), DESC_HI, desc_lo(sQ + c * 8192 + k * 32), DESC_HI, idesc, k > 0 ? 1u : 0u);
-              mma_ss(d_dp, desc_lo(sV + t * 16384 + k * 32), DESC_HI, desc_lo(sdO + c * 8192 + k * 32), DESC_HI, idesc, k > 0 ? 1u : 0u);
-            }
-          }
+          if (do_mma) mm.front<s>();
           tc_commit(st_full(buf));
         }
         __syncwarp();
       };
-      auto back = [&](int s) {
-        const int t = s >> 2, c = s & 3, buf = s & 1;
+      auto back = [&](auto S) {
+        constexpr int s = decltype(S)::value, t = s >> 2, c = s & 3, buf = s & 1;
         const int n_b = it * 4 + (s >> 1);                 // completions of this buffer's barriers so far
         mbar_wait(p_full(buf), n_b & 1);
+        trace_detail(trd, 9, it * 8 + s);      // back(s): P^T / dS^T ready
         if (c == 0) mbar_wait(dvk_free, ((it * 2 + t) & 1) ^ 1);   // the previous dV / dK tile has been read out
         tc_fence_after();
+        trace_detail(trd, 10, it * 8 + s);     // back(s): accumulators free, MMA3/4(/5) issued now
         if (leader) {
-          const uint32_t a_p = tmem_base + buf * 128, a_ds = a_p + 64;
-          const int nks = c < 3 ? 4 : 1;
-          for (int ks = 0; ks < nks && do_mma; ++ks) {
-            const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
-            mma_ts(tmem_base + T_DV, a_p + ks * 8, desc_lo(sdO + c * 8192 + ks * 2048), DESC_HI, ID_TS, acc);
-            mma_ts(tmem_base + T_DK, a_ds + ks * 8, desc_lo(sQ + c * 8192 + ks * 2048), DESC_HI, ID_TS, acc);
-          }
+          if (do_mma) mm.back_vk<s>();
           if (t == 1) tc_commit(qd_free(c));       // Q_c / dO_c no longer needed by this item
           if (c == 3) tc_commit(dvk_full);         // dV_t, dK_t complete
         }
         __syncwarp();
         if (c & 1) {
-          const int m = c >> 1;
+          constexpr int m = c >> 1;
           if (t == 0) mbar_wait(dq_free, ipar ^ 1);          // the previous item's dQ has been read out
           tc_fence_after();
           if (leader) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              if (do_mma) mma_ss(tmem_base + T_DQ + m * 64, desc_lo_mn(sDS + m * 32768 + ks * 2048, 16384), DESC_HI,
-                     desc_lo(sK + t * 16384 + ks * 2048), DESC_HI, ID_DQ, (t > 0 || ks > 0) ? 1u : 0u);
+            if (do_mma) mm.back_q<s>();
             tc_commit(ds_free(m));
             if (m == 1) tc_commit(kv_free(t));     // K_t / V_t no longer needed
             if (t == 1 && m == 1) tc_commit(dq_full);
@@ -656,74 +711,89 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
           __syncwarp();
         }
       };
-      front(0);
-      for (int s = 1; s < 8; ++s) {
-        front(s);
-        back(s - 1);
-      }
-      back(7);
+      using std::integral_constant;
+      front(integral_constant<int, 0>{});
+      front(integral_constant<int, 1>{}); back(integral_constant<int, 0>{});
+      front(integral_constant<int, 2>{}); back(integral_constant<int, 1>{});
+      front(integral_constant<int, 3>{}); back(integral_constant<int, 2>{});
+      front(integral_constant<int, 4>{}); back(integral_constant<int, 3>{});
+      front(integral_constant<int, 5>{}); back(integral_constant<int, 4>{});
+      front(integral_constant<int, 6>{}); back(integral_constant<int, 5>{});
+      front(integral_constant<int, 7>{}); back(integral_constant<int, 6>{});
+      back(integral_constant<int, 7>{});
     }
   } else if (warp < 10) {
-    // ===================== softmax warps: never leave the step loop =====================
+    // ===================== softmax warps: two groups of four, ping-pong over the steps =====================
+    // Group g = (warp - 2) / 4 owns the steps with s & 1 == g, i.e. tensor-memory buffer g: while one group is between its
+    // tcgen05.ld and its arrive, the other group's MMAs (back of the previous step, front of the next) and its own
+    // softmax run -- the step pipeline is two deep in the softmax stage as well, not only in tensor memory.  (With all
+    // eight warps on ONE step the warps sat in the ld -> exp -> st -> fence chain of that step while the tensor pipe and
+    // the other buffer idled: 4,000 clocks per step measured, for ~600 issue slots of work.)  A lane owns one key row
+    // and walks the 64 query columns of the chunk in two halves, half 0 first: the bf16 P^T / dS^T it writes in place
+    // (16 packed columns per half) then only ever cover fp32 columns it has already read.
     const int we = warp - 2;
     const int qr = warp & 3;             // TMEM lane quarter
-    const int ch = we >> 2;              // column half (32 of the 64 chunk columns)
+    const int grp = we >> 2;             // step parity / tensor-memory buffer of this group
     const int row = qr * 32 + lane;      // TMEM lane = key inside the 128-key tile
     const float sl2 = SCALE * LOG2E;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qr * 32) << 16);
     const uint32_t sDS = sbase + B_SDS;
+    const int buf = grp;
+    unsigned long long* trd = (qr == 0 && lane == 0) ? trace_detail_base(TK_ATTN_BWD) : nullptr;
     for (int it = 0; it < n_my; ++it) {
       const uint32_t ipar = it & 1;
       const uint32_t sLb = sbase + B_SL + ipar * 1024, sDb = sbase + B_SD + ipar * 1024;   // this item's L / delta
 #pragma unroll 1
-      for (int s = 0; s < 8; ++s) {
-        const int t = s >> 2, c = s & 3, buf = s & 1, m = c >> 1;
+      for (int s = grp; s < 8; s += 2) {
+        const int t = s >> 2, c = s & 3, m = c >> 1;
         const int n_b = it * 4 + (s >> 1);
         const int key = t * 128 + row;
+        trace_detail(trd, 11 + grp, it * 8 + s);   // softmax group: waiting for step s
         mbar_wait(st_full(buf), n_b & 1);      // MMA1/2 of this step retired
-        if ((c & 1) == 0) mbar_wait(ds_free(m), ((it * 2 + t) & 1) ^ 1);   // MMA5 of the previous key tile has read dS^T buffer m
-        if (t == 0) mbar_wait(delta_ready(c), ipar);                       // L / delta of this chunk's queries (epilogue warps)
+        trace_detail(trd, 13 + grp, it * 8 + s);   // S^T / dP^T of step s complete
+        mbar_wait(ds_free(m), ((it * 2 + t) & 1) ^ 1);                     // MMA5 of the previous key tile has read dS^T buffer m
+        if (t == 0) mbar_wait(delta_ready(ipar, c), (it >> 1) & 1);        // L / delta of this chunk's queries (delta warps)
         tc_fence_after();
-        const uint32_t a_st = lane_addr + buf * 128 + ch * 32, a_dp = a_st + 64;
+        trace_detail(trd, 15 + grp, it * 8 + s);   // all inputs of step s ready: math starts
         const uint32_t ds_row = sDS + m * 32768 + (c & 1) * 16384 + row * 128;
         if (dbg & 2) {
         } else if (c < 3) {
-          uint32_t vs[32], vd[32];
-          tm_ld32(a_st, vs);
-          tm_ld32(a_dp, vd);
-          const int q0 = c * 64 + ch * 32;
-          float4 Lr[8], Dr[8];      // per-query constants of this warp's 32 columns (broadcast reads)
+#pragma unroll 1
+          for (int ch = 0; ch < 2; ++ch) {
+            const uint32_t a_st = lane_addr + buf * 128 + ch * 32, a_dp = a_st + 64;
+            uint32_t vs[32], vd[32];
+            tm_ld32(a_st, vs);
+            tm_ld32(a_dp, vd);
+            const int q0 = c * 64 + ch * 32;
+            tm_ld_wait();
+            uint32_t pp[16], pd[16];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Lr[j4].x), "=f"(Lr[j4].y), "=f"(Lr[j4].z), "=f"(Lr[j4].w)
-                         : "r"(sLb + (q0 + j4 * 4) * 4));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Dr[j4].x), "=f"(Dr[j4].y), "=f"(Dr[j4].z), "=f"(Dr[j4].w)
-                         : "r"(sDb + (q0 + j4 * 4) * 4));
-          }
-          tm_ld_wait();
-          // the partner warp (other column half, same lanes) must have read its scores before either overwrites them
-          asm volatile("bar.sync %0, 64;" ::"r"(2 + qr) : "memory");
-          uint32_t pp[16], pd[16];
+            for (int j4 = 0; j4 < 8; ++j4) {
+              // per-query constants of 4 columns (broadcast shared-memory reads, fetched as they are needed: holding all
+              // 64 of them next to the 64 accumulator words spills at 128 registers per thread)
+              float Lv[4], Dv[4];
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Lv[0]), "=f"(Lv[1]), "=f"(Lv[2]), "=f"(Lv[3])
+                           : "r"(sLb + (q0 + j4 * 4) * 4));
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(Dv[0]), "=f"(Dv[1]), "=f"(Dv[2]), "=f"(Dv[3])
+                           : "r"(sDb + (q0 + j4 * 4) * 4));
+              float p[4], d[4];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float Lv[4] = {Lr[j4].x, Lr[j4].y, Lr[j4].z, Lr[j4].w}, Dv[4] = {Dr[j4].x, Dr[j4].y, Dr[j4].z, Dr[j4].w};
-            float p[4], d[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              p[e] = key < N_TOK ? ex2(fmaf(__uint_as_float(vs[j4 * 4 + e]), sl2, -Lv[e])) : 0.f;
-              d[e] = p[e] * (__uint_as_float(vd[j4 * 4 + e]) - Dv[e]);
+              for (int e = 0; e < 4; ++e) {
+                p[e] = key < N_TOK ? ex2(fmaf(__uint_as_float(vs[j4 * 4 + e]), sl2, -Lv[e])) : 0.f;
+                d[e] = p[e] * (__uint_as_float(vd[j4 * 4 + e]) - Dv[e]);
+              }
+              pp[j4 * 2] = pack_bf16x2(p[0], p[1]); pp[j4 * 2 + 1] = pack_bf16x2(p[2], p[3]);
+              pd[j4 * 2] = pack_bf16x2(d[0], d[1]); pd[j4 * 2 + 1] = pack_bf16x2(d[2], d[3]);
             }
-            pp[j4 * 2] = pack_bf16x2(p[0], p[1]); pp[j4 * 2 + 1] = pack_bf16x2(p[2], p[3]);
-            pd[j4 * 2] = pack_bf16x2(d[0], d[1]); pd[j4 * 2 + 1] = pack_bf16x2(d[2], d[3]);
-          }
-          tm_st16(lane_addr + buf * 128 + ch * 16, pp);
-          tm_st16(lane_addr + buf * 128 + 64 + ch * 16, pd);
+            tm_st16(lane_addr + buf * 128 + ch * 16, pp);
+            tm_st16(lane_addr + buf * 128 + 64 + ch * 16, pd);
 #pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + (((ch * 4 + g4) ^ (row & 7)) << 4)),
-                         "r"(pd[g4 * 4]), "r"(pd[g4 * 4 + 1]), "r"(pd[g4 * 4 + 2]), "r"(pd[g4 * 4 + 3]) : "memory");
+            for (int g4 = 0; g4 < 4; ++g4)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + (((ch * 4 + g4) ^ (row & 7)) << 4)),
+                           "r"(pd[g4 * 4]), "r"(pd[g4 * 4 + 1]), "r"(pd[g4 * 4 + 2]), "r"(pd[g4 * 4 + 3]) : "memory");
+          }
           tm_st_wait();
-        } else if (ch == 0) {
+        } else {
           // last chunk: queries 192..207 (16 columns), valid up to 196
           uint32_t vs[16], vd[16];
           tm_ld16(lane_addr + buf * 128, vs);
@@ -762,98 +832,170 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(buf));
+        trace_detail(trd, 17 + grp, it * 8 + s);   // step s handed to the MMA issuer
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ld_free(ipar));   // this warp is done with the item's L / delta values
     }
-  } else {
-    // ===================== epilogue / delta warps (10..13): everything that is not on the step critical path ==========
-    //   delta_q = dO_q . O_q and L_q for the NEXT item's queries as its dO chunks land; dV / dK after each key tile and dQ
-    //   after the item: tensor memory -> staging tile -> coalesced global rows.
+  } else if (warp < 14) {
+    // ===================== epilogue warps (10..13): dV / dK after each key tile, dQ after the item =====================
+    // The accumulators are single-buffered in tensor memory and gate the next key tile / item (dvk_free, dq_free), so each
+    // drain first pulls its accumulator into registers (packed to bf16), hands the tensor memory back, and only then sends
+    // the rows through the staging tile to global memory.  (Measured with the kernel-internal marks: when these warps also
+    // computed delta for the next item -- three global-memory round trips per item -- the next item's first back() and its
+    // first dQ MMA stalled 3 + 9 us per item behind them.)
     const int ew = warp - 10;            // 0..3
     const int qr = warp & 3;             // TMEM lane quarter this warp may touch
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qr * 32) << 16);
-    const uint32_t sdO = sbase + B_SDO, stg = sbase + B_STG + (uint32_t)ew * 2048;
+    const uint32_t stg = sbase + B_STG + (uint32_t)ew * 2048;
     const int64_t hstride = (int64_t)VITK_HEADS * M * 64;
-    // chunk c of item `it_` (its dO_c must have landed): every warp takes 16 of the 64 queries, 8 lanes per query
-    auto delta_chunk = [&](int it_, int c) {
-      if (dbg & 8) { __syncwarp(); if (lane == 0) mbar_arrive(delta_ready(c)); return; }
-      const int item = blockIdx.x + it_ * gridDim.x;
-      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
-      const bf16* obase = out + ((int64_t)b * N_TOK) * VITK_DIM + h * VITK_HEAD_DIM + (lane & 7) * 8;
-      float* dD = sD + (it_ & 1) * 256;
-      float* dL = sL + (it_ & 1) * 256;
-      uint4 ov[4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int q = c * 64 + ew * 16 + g * 4 + (lane >> 3);
-        ov[g] = q < N_TOK ? __ldg(reinterpret_cast<const uint4*>(obase + (int64_t)q * VITK_DIM)) : make_uint4(0u, 0u, 0u, 0u);
-      }
-      const int ql = c * 64 + ew * 16 + (lane & 15);     // lanes 0..15: the log-sum-exp of this warp's 16 queries
-      const float lv = (lane < 16 && ql < N_TOK) ? __ldg(lse + (int64_t)h * M + (int64_t)b * N_TOK + ql) : 0.f;
-      mbar_wait(qd_full(c), it_ & 1);     // dO_c of that item has landed
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int q = c * 64 + ew * 16 + g * 4 + (lane >> 3), r = q & 63;
-        uint4 av;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(av.x), "=r"(av.y), "=r"(av.z), "=r"(av.w)
-                     : "r"(sdO + c * 8192 + r * 128 + (((lane & 7) ^ (r & 7)) << 4)));
-        const float2 a0 = unpack_bf16x2(av.x), a1 = unpack_bf16x2(av.y), a2 = unpack_bf16x2(av.z), a3 = unpack_bf16x2(av.w);
-        const float2 o0 = unpack_bf16x2(ov[g].x), o1 = unpack_bf16x2(ov[g].y), o2 = unpack_bf16x2(ov[g].z), o3 = unpack_bf16x2(ov[g].w);
-        float dl = a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
-        dl += __shfl_xor_sync(0xffffffffu, dl, 1);
-        dl += __shfl_xor_sync(0xffffffffu, dl, 2);
-        dl += __shfl_xor_sync(0xffffffffu, dl, 4);
-        if ((lane & 7) == 0) dD[q] = q < N_TOK ? dl : 0.f;
-      }
-      if (lane < 16) dL[ql] = lv * LOG2E;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(delta_ready(c));     // release: the stores above are visible to the waiting softmax warps
-    };
-    // one 128-row x 64-column fp32 accumulator tile (TMEM column `col`) -> bf16 rows of `dst` (row stride 64), rows < n_valid
-    // cs: this (section, head)'s 64 entries of the qkv bias gradient, or nullptr
-    auto drain_tile = [&](uint32_t col, bf16* dst, int row0, float scale, float* cs) {
-      if (row0 + qr * 32 >= N_TOK) return;      // none of this warp's rows exists
-#pragma unroll
-      for (int half = 0; half < 2 && !(dbg & 4); ++half) {
-        uint32_t o[32];
-        tm_ld32(lane_addr + col + half * 32, o);
-        tm_ld_wait();
-        store_slab32(stg, lane, o, scale,
-                     [&](int r) -> bf16* { return (row0 + qr * 32 + r < N_TOK) ? dst + (int64_t)(row0 + qr * 32 + r) * 64 + half * 32 : nullptr; },
-                     cs ? cs + half * 32 : nullptr);
-      }
-    };
-    if (n_my > 0)
-      for (int c = 0; c < 4; ++c) delta_chunk(0, c);
+    unsigned long long* trd = (ew == 0 && lane == 0) ? trace_detail_base(TK_ATTN_BWD) : nullptr;
     for (int it = 0; it < n_my; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int b = item / VITK_HEADS, h = item % VITK_HEADS;
       const uint32_t ipar = it & 1;
       const int64_t hm = ((int64_t)h * M + (int64_t)b * N_TOK) * 64;
-      const bool has_next = it + 1 < n_my;
+      float* csb = dqkv_colsum ? dqkv_colsum + h * 64 : nullptr;      // [3][12][64]: q | k | v sections (cs_sections: bits 0 | 1 | 2)
       for (int t = 0; t < 2; ++t) {
         // ---- dV_t, dK_t (lane = key)
         mbar_wait(dvk_full, (it * 2 + t) & 1);
         tc_fence_after();
-        float* csb = dqkv_colsum ? dqkv_colsum + h * 64 : nullptr;      // [3][12][64]: q | k | v sections (cs_sections: bits 0 | 1 | 2)
-        drain_tile(T_DV, dqkv + hm + 2 * hstride, t * 128, 1.0f, (csb && (cs_sections & 4)) ? csb + 2 * VITK_DIM : nullptr);
-        drain_tile(T_DK, dqkv + hm + hstride, t * 128, SCALE, (csb && (cs_sections & 2)) ? csb + VITK_DIM : nullptr);
+        trace_detail(trd, 19, it * 2 + t);        // dV / dK of key tile t complete
+        const bool rows_exist = t * 128 + qr * 32 < N_TOK;
+        uint32_t pv[2][16], pkk[2][16];
+        if (rows_exist && !(dbg & 4)) {
+          uint32_t o[32];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            tm_ld32(lane_addr + T_DV + half * 32, o);
+            tm_ld_wait();
+            pack_slab32(o, 1.0f, pv[half]);
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            tm_ld32(lane_addr + T_DK + half * 32, o);
+            tm_ld_wait();
+            pack_slab32(o, SCALE, pkk[half]);
+          }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dvk_free);
-        // the next item's dO chunks 0..2 land while this item's second key tile runs
-        if (t == 0 && has_next)
-          for (int c = 0; c < 3; ++c) delta_chunk(it + 1, c);
+        trace_detail(trd, 20, it * 2 + t);        // dV / dK pulled out of tensor memory
+        if (rows_exist && !(dbg & 4)) {
+          const int r0 = t * 128 + qr * 32;
+          bf16* dv = dqkv + hm + 2 * hstride;
+          bf16* dk = dqkv + hm + hstride;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            store_slab_packed(stg, lane, pv[half],
+                              [&](int r) -> bf16* { return (r0 + r < N_TOK) ? dv + (int64_t)(r0 + r) * 64 + half * 32 : nullptr; },
+                              (csb && (cs_sections & 4)) ? csb + 2 * VITK_DIM + half * 32 : nullptr);
+            store_slab_packed(stg, lane, pkk[half],
+                              [&](int r) -> bf16* { return (r0 + r < N_TOK) ? dk + (int64_t)(r0 + r) * 64 + half * 32 : nullptr; },
+                              (csb && (cs_sections & 2)) ? csb + VITK_DIM + half * 32 : nullptr);
+          }
+        }
       }
-      // ---- dQ (lane = query), two 128-query tiles
+      // ---- dQ (lane = query), two 128-query tiles: same order -- registers first, tensor memory released, then the stores
+      trace_detail(trd, 21, it);                  // dV / dK rows stored; waiting for dQ
       mbar_wait(dq_full, ipar);
       tc_fence_after();
-      float* csq = (dqkv_colsum && (cs_sections & 1)) ? dqkv_colsum + h * 64 : nullptr;
-      drain_tile(T_DQ, dqkv + hm, 0, SCALE, csq);
-      drain_tile(T_DQ + 64, dqkv + hm, 128, SCALE, csq);
+      trace_detail(trd, 22, it);
+      uint32_t pq[2][2][16];
+      const bool q_exist[2] = {true, 128 + qr * 32 < N_TOK};
+      if (!(dbg & 4)) {
+        uint32_t o[32];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (!q_exist[mt]) continue;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            tm_ld32(lane_addr + T_DQ + mt * 64 + half * 32, o);
+            tm_ld_wait();
+            pack_slab32(o, SCALE, pq[mt][half]);
+          }
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
-      if (has_next) delta_chunk(it + 1, 3);
+      trace_detail(trd, 23, it);
+      if (!(dbg & 4)) {
+        float* csq = (csb && (cs_sections & 1)) ? csb : nullptr;
+        bf16* dq = dqkv + hm;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (!q_exist[mt]) continue;
+          const int r0 = mt * 128 + qr * 32;
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+            store_slab_packed(stg, lane, pq[mt][half],
+                              [&](int r) -> bf16* { return (r0 + r < N_TOK) ? dq + (int64_t)(r0 + r) * 64 + half * 32 : nullptr; },
+                              csq ? csq + half * 32 : nullptr);
+        }
+      }
+      trace_detail(trd, 24, it);                  // dQ rows stored
+    }
+  } else {
+    // ===================== delta warps (14, 15): delta_q = dO_q . O_q and L_q = lse_q log2(e), ONE ITEM AHEAD =====================
+    // Both operands are read from global memory (L2: dO was just written by the proj dgrad), not from the dO boxes in shared
+    // memory -- those are recycled per chunk only when the previous item's second key tile retires, so anything that waits for
+    // them is late for the next item's first key tile (measured: 1.5 - 2.7 us per step on three of its four steps).
+    // Every warp takes 32 of the 64 queries of a chunk, 8 lanes per query.  L / delta are double-buffered by item parity
+    // ([2][256] floats, one ready barrier per parity and chunk, one free barrier per parity on which every softmax warp
+    // arrives when it has finished an item): these warps run up to two items ahead and never a barrier phase too far.
+    const int dw = warp - 14;            // 0..1
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / VITK_HEADS, h = item % VITK_HEADS;
+      const int64_t rowbase = ((int64_t)b * N_TOK) * VITK_DIM + h * VITK_HEAD_DIM + (lane & 7) * 8;
+      float* dD = sD + (it & 1) * 256;
+      float* dL = sL + (it & 1) * 256;
+      if (it >= 2) mbar_wait(ld_free(it & 1), ((it >> 1) - 1) & 1);      // item it - 2 no longer reads this buffer
+      if (dbg & 8) {
+        for (int c = 0; c < 4; ++c) { __syncwarp(); if (lane == 0) mbar_arrive(delta_ready(it & 1, c)); }
+        continue;
+      }
+      // 7 half-chunks of 16 queries per warp (chunk 3 holds 16 queries: one half).  The 8 row fetches of half-chunk k + 1 are
+      // in flight while half-chunk k is reduced: these warps are bound by the latency of their global loads (O comes from
+      // HBM), and only when they outrun the item rate do they get -- and stay -- ahead of the softmax warps.
+      uint4 ov[2][4], av[2][4];
+      auto fetch = [&](int hc, int slot) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int q = (hc >> 1) * 64 + dw * 32 + ((hc & 1) * 4 + g) * 4 + (lane >> 3);
+          const int64_t off = rowbase + (int64_t)(q < N_TOK ? q : 0) * VITK_DIM;
+          ov[slot][g] = __ldg(reinterpret_cast<const uint4*>(out + off));
+          av[slot][g] = __ldg(reinterpret_cast<const uint4*>(dout_g + off));
+        }
+      };
+      fetch(0, 0);
+#pragma unroll
+      for (int hc = 0; hc < 7; ++hc) {
+        const int c = hc >> 1, slot = hc & 1;
+        if (hc + 1 < 7) fetch(hc + 1, slot ^ 1);
+        const int ql = c * 64 + dw * 32 + lane;     // the log-sum-exp of this warp's 32 queries of the chunk
+        float lv = 0.f;
+        if ((hc & 1) == 0 && ql < N_TOK) lv = __ldg(lse + (int64_t)h * M + (int64_t)b * N_TOK + ql);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int q = c * 64 + dw * 32 + ((hc & 1) * 4 + g) * 4 + (lane >> 3);
+          const uint4 a = av[slot][g], o = ov[slot][g];
+          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+          const float2 o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y), o2 = unpack_bf16x2(o.z), o3 = unpack_bf16x2(o.w);
+          float d = a0.x * o0.x + a0.y * o0.y + a1.x * o1.x + a1.y * o1.y + a2.x * o2.x + a2.y * o2.y + a3.x * o3.x + a3.y * o3.y;
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if ((lane & 7) == 0) dD[q] = q < N_TOK ? d : 0.f;
+        }
+        if ((hc & 1) == 0) dL[ql] = lv * LOG2E;
+        if ((hc & 1) == 1 || hc == 6) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(delta_ready(it & 1, c));     // release: the stores above are visible to the waiting softmax warps
+        }
+      }
     }
   }
 
@@ -911,7 +1053,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   VITK_TRY(atc::make_dout_map(dout, M, &map_do));
   const int items = batch * VITK_HEADS, sms = sm_count();
   VITK_LAUNCH((atc::attn_bwd_tc_kernel), (items < sms ? items : sms), atc::BWD_THREADS, atc::BWD_SMEM, st, map_kv, map_q, map_do,
-              (const bf16*)out, lse, (bf16*)dqkv, dqkv_colsum, cs_sections, batch, items, tune_knob(7));
+              (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, dqkv_colsum, cs_sections, batch, items, tune_knob(7));
   return VITK_OK;
 }
 

@@ -83,7 +83,7 @@ void trace_register(void (*setter)(unsigned long long*));   // api.cu: one sette
 #endif
 #ifdef __CUDACC__
 #ifdef VITK_DEV
-static __device__ unsigned long long* g_trace_buf = nullptr;   // [0] record count, [1] capacity, records of 3 words from [2]
+static __device__ unsigned long long* g_trace_buf = nullptr;   // [0] record count, [1] capacity, [2] detail offset, [3] pad, records of 3 words from [4]
 namespace {
 struct TraceTU {
   static void set(unsigned long long* p) { cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)); }
@@ -101,11 +101,30 @@ __device__ __forceinline__ void trace_mark(uint32_t kid, uint32_t phase, unsigne
   uint32_t smid;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  unsigned long long* r = b + 2 + 3 * idx;
+  unsigned long long* r = b + 4 + 3 * idx;
   r[0] = t;
   r[1] = ((unsigned long long)kid << 48) | ((unsigned long long)phase << 40) | ((unsigned long long)(smid & 0xffffu) << 24) |
          (unsigned long long)(blockIdx.x & 0xffffffu);
   r[2] = aux;
+}
+// Kernel-internal marks (CTA 0 only, any single thread the caller elects): timestamps go to STATIC slots of a detail region
+// behind the launch marks -- slot = (phase - 8) * 64 + (aux & 63), overwritten by every launch -- so that a mark is one
+// special-register read and one fire-and-forget store (an atomically allocated record would stall the marking thread for
+// an L2 round trip and distort exactly the fine-grained timing it is meant to show).  trace_detail_base() is called once
+// per warp role (one dependent load), trace_detail() per event.
+constexpr int TRACE_DETAIL_PHASES = 24, TRACE_DETAIL_SLOTS = 64;
+__device__ __forceinline__ unsigned long long* trace_detail_base(uint32_t kid) {
+  if (blockIdx.x != 0) return nullptr;
+  unsigned long long* b = g_trace_buf;
+  if (!b) return nullptr;
+  const unsigned long long off = b[2];          // word offset of the detail area (0 = off)
+  return off ? b + off + (unsigned long long)kid * (TRACE_DETAIL_PHASES * TRACE_DETAIL_SLOTS) : nullptr;
+}
+__device__ __forceinline__ void trace_detail(unsigned long long* dbase, uint32_t phase, uint32_t aux = 0) {
+  if (!dbase) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  dbase[(phase - 8) * TRACE_DETAIL_SLOTS + (aux & (TRACE_DETAIL_SLOTS - 1))] = t;
 }
 // end-of-CTA mark for kernels whose threads all reach the end of the kernel body
 __device__ __forceinline__ void trace_end(uint32_t kid, unsigned long long aux = 0) {
@@ -114,6 +133,8 @@ __device__ __forceinline__ void trace_end(uint32_t kid, unsigned long long aux =
 }
 #else
 __device__ __forceinline__ void trace_mark(uint32_t, uint32_t, unsigned long long = 0) {}
+__device__ __forceinline__ unsigned long long* trace_detail_base(uint32_t) { return nullptr; }
+__device__ __forceinline__ void trace_detail(unsigned long long*, uint32_t, uint32_t = 0) {}
 __device__ __forceinline__ void trace_end(uint32_t, unsigned long long = 0) {}
 #endif
 __device__ __forceinline__ void pdl_sync() {

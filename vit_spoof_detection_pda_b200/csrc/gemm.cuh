@@ -11,9 +11,18 @@ namespace vitk {
 struct MatLayout {
   int64_t s_row;  // element stride of the row index (i or j)
   int64_t s_col;  // element stride of the reduction index r
-  int32_t split;  // 0: none; 1: row index is split (row>>6)*s_blk + (row&63)*s_row; 2: same for r
+  int32_t split;  // 0: none; 1: row index is split (row>>6)*s_blk + (row&63)*s_row; 2: same for r;
+                  // 3 / 4: the patch matrix of an NCHW image read in place (no im2col copy): 3 = (row = token b*197+t,
+                  // col = k = c*256+i*16+j), 4 = (row = k, col = token); CLS tokens (t = 0) have no patch: at() < 0 = zero
   int64_t s_blk;
   __host__ __device__ __forceinline__ int64_t at(int row, int col) const {
+    if (split >= 3) {
+      const int tok = split == 3 ? row : col, k = split == 3 ? col : row;
+      const int b = tok / VITK_NTOK, t = tok % VITK_NTOK;
+      if (t == 0) return -1;
+      const int py = (t - 1) / 14, px = (t - 1) % 14, c = k >> 8, i = (k >> 4) & 15, j = k & 15;
+      return (((int64_t)b * 3 + c) * VITK_IMG + py * 16 + i) * VITK_IMG + px * 16 + j;
+    }
     int64_t a = (split == 1) ? (int64_t)(row >> 6) * s_blk + (int64_t)(row & 63) * s_row : (int64_t)row * s_row;
     a += (split == 2) ? (int64_t)(col >> 6) * s_blk + (int64_t)(col & 63) * s_col : (int64_t)col * s_col;
     return a;
@@ -25,6 +34,9 @@ static inline MatLayout layout_transposed(int64_t ld) { return MatLayout{1, ld, 
 // head-major X_hm(m, c) = (c>>6)*M*64 + m*64 + (c&63)
 static inline MatLayout layout_headmajor_rows_m(int64_t M) { return MatLayout{64, 1, 2, M * 64}; }   // row = m, r = c
 static inline MatLayout layout_headmajor_rows_c(int64_t M) { return MatLayout{1, 64, 1, M * 64}; }   // row = c, r = m
+// the patch matrix read straight from the NCHW fp32 image (SIMT engine only; the tcgen05 path has its own TMA kernel)
+static inline MatLayout layout_patches_rows_tok() { return MatLayout{0, 1, 3, 0}; }   // row = token, r = k   (k contiguous)
+static inline MatLayout layout_patches_rows_k() { return MatLayout{1, 0, 4, 0}; }     // row = k, r = token
 
 enum EpiMode {
   E_STORE = 0,          // out[i][j] = acc (+ bias[j])                       out_dtype, row-major ldc

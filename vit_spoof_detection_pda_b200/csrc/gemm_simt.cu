@@ -18,7 +18,10 @@ __device__ __forceinline__ void simt_load_tile(const T* __restrict__ base, const
     if (k_contig) { rr = idx % ST_BK; ii = idx / ST_BK; } else { ii = idx % ST_BM; rr = idx / ST_BM; }
     const int row = row0 + ii, r = r0 + rr;
     float v = 0.f;
-    if (row < nrows && r < r_end) v = to_f32(base[l.at(row, r)]);
+    if (row < nrows && r < r_end) {
+      const int64_t o = l.at(row, r);
+      if (o >= 0) v = to_f32(base[o]);     // o < 0: structurally zero element (CLS rows of the in-place patch matrix)
+    }
     dst[rr][ii] = v;
   }
 }

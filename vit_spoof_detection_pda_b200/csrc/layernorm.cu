@@ -31,69 +31,111 @@ template <> struct Vec4IO<bf16> {
   }
 };
 
-// One warp normalises one row held in registers (6 float4 per lane).  Persistent: the grid is a fixed number of CTAs per
-// SM (8 = full occupancy) and every warp walks rows with a stride of the total warp count, TWO rows per iteration: 12,608
-// rows on 148 x 64 resident warps are 1.33 rows per warp, so every warp finishes in one iteration with 6 or 12 independent
-// 16-byte loads per lane in flight, instead of a half-empty second wave of CTAs.
-template <typename T>
-__device__ __forceinline__ void ln_row(const float4 (&v_in)[LN_VEC], int lane, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, T* __restrict__ yr, float* __restrict__ mean_out,
-                                       float* __restrict__ rstd_out, int row, float eps) {
-  float4 v[LN_VEC];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < LN_VEC; ++i) {
-    v[i] = v_in[i];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float mean = warp_sum(s) * (1.0f / LN_COLS);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < LN_VEC; ++i) {
-    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-  }
-  const float var = warp_sum(q) * (1.0f / LN_COLS);
-  const float rstd = 1.0f / sqrtf(var + eps);
-#pragma unroll
-  for (int i = 0; i < LN_VEC; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-    float4 o;
-    o.x = v[i].x * rstd * g.x + b.x;
-    o.y = v[i].y * rstd * g.y + b.y;
-    o.z = v[i].z * rstd * g.z + b.z;
-    o.w = v[i].w * rstd * g.w + b.w;
-    Vec4IO<T>::store(yr + c, o);
-  }
-  if (lane == 0 && mean_out) {
-    mean_out[row] = mean;
-    rstd_out[row] = rstd;
-  }
+// Forward: one warp normalises one row.  The kernel is a pure stream (58 MB at batch 64) whose first version -- row in
+// registers, loads issued by the threads -- ran at 2.8 TB/s inside the step (tools/step_timeline.py: 21 us per launch): too
+// few bytes in flight per SM and four waves of short-lived CTAs.  Now the rows are STAGED THROUGH SHARED MEMORY BY THE
+// BULK-COPY ENGINE: every warp owns a ring of LN_RING 3 KB row buffers, lane 0 keeps cp.async.bulk copies (one per row,
+// completion on an mbarrier) in flight for the next LN_RING rows of the warp, and the lanes only ever read shared memory.
+// One persistent wave of 2 CTAs per SM: 16 warps x 4 rows x 3 KB = 192 KB in flight per SM, no registers tied up by
+// outstanding loads.
+constexpr int LN_RING = 4;
+constexpr int LN_ROW_BYTES = LN_COLS * 4;                         // 3072
+constexpr int LN_FWD_SMEM = LN_WARPS * LN_RING * LN_ROW_BYTES + LN_WARPS * LN_RING * 8;   // 98,560 B
+
+__device__ __forceinline__ uint32_t ln_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ln_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// lane 0: arm the barrier and start the bulk copy of one row (3072 B, 16-byte aligned source)
+__device__ __forceinline__ void ln_fetch_row(uint32_t dst, const float* src, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(LN_ROW_BYTES) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(LN_ROW_BYTES), "r"(bar) : "memory");
 }
 
 template <typename T>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ gamma,
               const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int rows, float eps) {
-  pdl_sync_traced(TK_LN_FWD);
-  const int lane = threadIdx.x & 31;
+  trace_mark(TK_LN_FWD, 0);
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ring = ln_smem_u32(ln_smem) + (uint32_t)warp * (LN_RING * LN_ROW_BYTES);
+  const uint32_t bars = ln_smem_u32(ln_smem) + LN_WARPS * LN_RING * LN_ROW_BYTES + (uint32_t)warp * (LN_RING * 8);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < LN_RING; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  pdl_sync();
+  trace_mark(TK_LN_FWD, 1);
   const int nw = gridDim.x * LN_WARPS;
-  for (int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < rows; row += 2 * nw) {
-    const int row2 = row + nw;
-    const float* xr = x + (int64_t)row * x_stride;
-    const float* xr2 = x + (int64_t)row2 * x_stride;
-    float4 a[LN_VEC], b[LN_VEC];
+  const int row0 = blockIdx.x * LN_WARPS + warp;
+  if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < LN_VEC; ++i) a[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
-    if (row2 < rows) {
-#pragma unroll
-      for (int i = 0; i < LN_VEC; ++i) b[i] = *reinterpret_cast<const float4*>(xr2 + (i * 32 + lane) * 4);
+    for (int s = 0; s < LN_RING; ++s) {
+      const int r = row0 + s * nw;
+      if (r < rows) ln_fetch_row(ring + s * LN_ROW_BYTES, x + (int64_t)r * x_stride, bars + 8u * s);
     }
-    ln_row<T>(a, lane, gamma, beta, y + (int64_t)row * LN_COLS, mean_out, rstd_out, row, eps);
-    if (row2 < rows) ln_row<T>(b, lane, gamma, beta, y + (int64_t)row2 * LN_COLS, mean_out, rstd_out, row2, eps);
+  }
+  // gamma / beta of this lane's columns stay in registers for all rows of the warp (fetched under the first row copies)
+  float4 g[LN_VEC], b[LN_VEC];
+#pragma unroll
+  for (int i = 0; i < LN_VEC; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
+    b[i] = __ldg(reinterpret_cast<const float4*>(beta + (i * 32 + lane) * 4));
+  }
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int row = row0; row < rows; row += nw) {
+    ln_mbar_wait(bars + 8u * slot, phase);
+    float4 v[LN_VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_VEC; ++i) {
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                   : "r"(ring + slot * LN_ROW_BYTES + (i * 32 + lane) * 16));
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    __syncwarp();                                   // every lane has read the slot: it may be refilled
+    if (lane == 0) {
+      const int rn = row + LN_RING * nw;
+      if (rn < rows) ln_fetch_row(ring + slot * LN_ROW_BYTES, x + (int64_t)rn * x_stride, bars + 8u * slot);
+    }
+    const float mean = warp_sum(s) * (1.0f / LN_COLS);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_VEC; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float var = warp_sum(q) * (1.0f / LN_COLS);
+    const float rstd = 1.0f / sqrtf(var + eps);
+    T* yr = y + (int64_t)row * LN_COLS;
+#pragma unroll
+    for (int i = 0; i < LN_VEC; ++i) {
+      float4 o;
+      o.x = v[i].x * rstd * g[i].x + b[i].x;
+      o.y = v[i].y * rstd * g[i].y + b[i].y;
+      o.z = v[i].z * rstd * g[i].z + b[i].z;
+      o.w = v[i].w * rstd * g[i].w + b[i].w;
+      Vec4IO<T>::store(yr + (i * 32 + lane) * 4, o);
+    }
+    if (lane == 0 && mean_out) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+    if (++slot == LN_RING) { slot = 0; phase ^= 1; }
   }
   trace_end(TK_LN_FWD);
 }
@@ -194,16 +236,18 @@ extern "C" int vitk_layernorm_fwd(const float* x, int64_t x_stride, const float*
   VITK_CHECK_ARG(x_stride % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0);
   if (rows == 0) return VITK_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  VITK_CHECK_ARG(((x_stride * 4) % 16) == 0);
+  VITK_TRY(set_max_dyn_smem_once((const void*)ln_fwd_kernel<float>, LN_FWD_SMEM));
+  VITK_TRY(set_max_dyn_smem_once((const void*)ln_fwd_kernel<bf16>, LN_FWD_SMEM));
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  const int cap = sm_count() * 8;
+  const int cap = sm_count() * 2;   // one persistent wave: 2 CTAs per SM (96 KB of row ring each)
   if (grid > cap) grid = cap;
   if (y_dtype == VITK_F32)
-    VITK_LAUNCH((ln_fwd_kernel<float>), grid, LN_WARPS * 32, 0, st, x, x_stride, gamma, beta, (float*)y, mean, rstd, rows, eps);
+    VITK_LAUNCH((ln_fwd_kernel<float>), grid, LN_WARPS * 32, LN_FWD_SMEM, st, x, x_stride, gamma, beta, (float*)y, mean, rstd, rows, eps);
   else if (y_dtype == VITK_BF16)
-    VITK_LAUNCH((ln_fwd_kernel<bf16>), grid, LN_WARPS * 32, 0, st, x, x_stride, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
+    VITK_LAUNCH((ln_fwd_kernel<bf16>), grid, LN_WARPS * 32, LN_FWD_SMEM, st, x, x_stride, gamma, beta, (bf16*)y, mean, rstd, rows, eps);
   else
     VITK_CHECK_ARG(!"bad dtype");
-  VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
 
@@ -226,6 +270,5 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, 
     VITK_LAUNCH((ln_bwd_kernel<bf16>), grid, LN_WARPS * 32, LN_BWD_SMEM, st, (const bf16*)dy, x, x_stride, gamma, mean, rstd, dres, dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
   else
     VITK_CHECK_ARG(!"bad dtype");
-  VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

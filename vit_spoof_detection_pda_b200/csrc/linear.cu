@@ -1,6 +1,6 @@
-// nn.Linear forward / dgrad / wgrad and the patch-embedding GEMM: builds GemmProblems and
-// dispatches them to the tcgen05 engine (bf16) or the SIMT engine (fp32-validate / cross-check).
-// Reference call sites: timm Attention.qkv / .proj, Mlp.fc1 / .fc2 and PatchEmbed.proj reached from
+// nn.Linear forward / dgrad / wgrad: builds GemmProblems and dispatches them to the tcgen05 engine (bf16) or
+// the SIMT engine (fp32-validate / cross-check).  (The patch-embedding GEMM has its own TMA-fed kernel: patch_embed.cu.)
+// Reference call sites: timm Attention.qkv / .proj, Mlp.fc1 / .fc2 reached from
 // /root/reference/train_advanced.py:203 (self.vit(x)); backward from loss.backward() at :330.
 #include <atomic>
 #include <mutex>
@@ -125,50 +125,6 @@ int colsum_headmajor(const void* x, int dtype, int M, int C, float* db, cudaStre
   return colsum(x, dtype, layout_headmajor_rows_m(M), M, C, db, st);
 }
 
-// patches[(b*197 + t)][c*256 + i*16 + j] = image[b][c][py*16+i][px*16+j], t = 1 + py*14 + px; row t=0 zero.
-template <typename T>
-__global__ void __launch_bounds__(256)
-im2col_kernel(const float* __restrict__ img, T* __restrict__ patches, int batch) {
-  pdl_sync();
-  const int64_t total = (int64_t)batch * VITK_NTOK * (VITK_DIM / 4);
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int k4 = (int)(idx % (VITK_DIM / 4));
-    const int64_t row = idx / (VITK_DIM / 4);
-    const int t = (int)(row % VITK_NTOK), b = (int)(row / VITK_NTOK);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t > 0) {
-      const int p = t - 1, py = p / 14, px = p % 14;
-      const int k = k4 * 4, c = k >> 8, i = (k >> 4) & 15, j = k & 15;
-      v = *reinterpret_cast<const float4*>(img + (((int64_t)b * 3 + c) * VITK_IMG + py * 16 + i) * VITK_IMG + px * 16 + j);
-    }
-    T* dst = patches + row * VITK_DIM + k4 * 4;
-    if constexpr (sizeof(T) == 4) {
-      *reinterpret_cast<float4*>(dst) = v;
-    } else {
-      uint2 u;
-      u.x = pack_bf16x2(v.x, v.y);
-      u.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(dst) = u;
-    }
-  }
-}
-
-// dpos[t][j] += sum_b dx0[b][t][j]; dcls[j] += that at t = 0; dbpe[j] += sum over t >= 1
-__global__ void __launch_bounds__(256)
-embed_param_grads_kernel(const float* __restrict__ dx0, int batch, float* __restrict__ dpos,
-                         float* __restrict__ dcls, float* __restrict__ dbpe) {
-  pdl_sync_traced(TK_EMBED_GRADS);
-  const int t = blockIdx.x;
-  for (int j = threadIdx.x; j < VITK_DIM; j += blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < batch; ++b) s += dx0[((int64_t)b * VITK_NTOK + t) * VITK_DIM + j];
-    dpos[(int64_t)t * VITK_DIM + j] += s;
-    if (t == 0) dcls[j] += s;
-    else atomicAdd(dbpe + j, s);
-  }
-  trace_end(TK_EMBED_GRADS);
-}
-
 }  // namespace vitk
 
 using namespace vitk;
@@ -266,94 +222,5 @@ extern "C" int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, f
     const MatLayout l = dy_layout == VITK_LAYOUT_HEADMAJOR ? layout_headmajor_rows_m(M) : layout_rowmajor(N);
     VITK_TRY(colsum(dy, dtype, l, M, N, db, st));
   }
-  return VITK_OK;
-}
-
-// same regrouping from uint8 HWC pixels with ToTensor + Normalize fused (fp32 arithmetic in torchvision's order:
-// (float(u) / 255 - mean[c]) / std[c]); one thread = 4 consecutive pixels j..j+3 of one (patch row i, channel c)
-template <typename T>
-__global__ void __launch_bounds__(256)
-im2col_u8_kernel(const uint8_t* __restrict__ img, float m0, float m1, float m2, float s0, float s1, float s2,
-                 T* __restrict__ patches, int batch) {
-  pdl_sync();
-  const int64_t total = (int64_t)batch * VITK_NTOK * (VITK_DIM / 4);
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int k4 = (int)(idx % (VITK_DIM / 4));
-    const int64_t row = idx / (VITK_DIM / 4);
-    const int t = (int)(row % VITK_NTOK), b = (int)(row / VITK_NTOK);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t > 0) {
-      const int p = t - 1, py = p / 14, px = p % 14;
-      const int k = k4 * 4, c = k >> 8, i = (k >> 4) & 15, j = k & 15;
-      const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
-      const uint8_t* src = img + (((int64_t)b * VITK_IMG + py * 16 + i) * VITK_IMG + px * 16 + j) * 3 + c;
-      v.x = ((float)src[0] / 255.0f - mean) / sd;
-      v.y = ((float)src[3] / 255.0f - mean) / sd;
-      v.z = ((float)src[6] / 255.0f - mean) / sd;
-      v.w = ((float)src[9] / 255.0f - mean) / sd;
-    }
-    T* dst = patches + row * VITK_DIM + k4 * 4;
-    if constexpr (sizeof(T) == 4) {
-      *reinterpret_cast<float4*>(dst) = v;
-    } else {
-      uint2 u;
-      u.x = pack_bf16x2(v.x, v.y);
-      u.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(dst) = u;
-    }
-  }
-}
-
-static int patch_gemm(const void* wpe, const float* bpe, const float* cls, const float* pos, void* patches, float* x0, int batch,
-                      int dtype, int engine, cudaStream_t st);
-
-extern "C" int vitk_patch_embed_fwd_u8(const uint8_t* images_hwc, const float* mean3, const float* std3, const void* wpe,
-                                       const float* bpe, const float* cls, const float* pos, void* patches, float* x0,
-                                       int batch, int dtype, int engine, void* stream) {
-  VITK_CHECK_ARG(images_hwc && mean3 && std3 && wpe && bpe && cls && pos && patches && x0 && batch > 0);
-  VITK_CHECK_ARG(dtype == VITK_F32 || dtype == VITK_BF16);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t total = (int64_t)batch * VITK_NTOK * (VITK_DIM / 4);
-  const int grid = (int)((total + 255) / 256 < (int64_t)sm_count() * 16 ? (total + 255) / 256 : (int64_t)sm_count() * 16);
-  if (dtype == VITK_BF16)
-    VITK_LAUNCH((im2col_u8_kernel<bf16>), grid, 256, 0, st, images_hwc, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], (bf16*)patches, batch);
-  else
-    VITK_LAUNCH((im2col_u8_kernel<float>), grid, 256, 0, st, images_hwc, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], (float*)patches, batch);
-  return patch_gemm(wpe, bpe, cls, pos, patches, x0, batch, dtype, engine, st);
-}
-
-extern "C" int vitk_patch_embed_fwd(const float* images, const void* wpe, const float* bpe, const float* cls,
-                                    const float* pos, void* patches, float* x0, int batch, int dtype, int engine,
-                                    void* stream) {
-  VITK_CHECK_ARG(images && wpe && bpe && cls && pos && patches && x0 && batch > 0);
-  VITK_CHECK_ARG(dtype == VITK_F32 || dtype == VITK_BF16);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t total = (int64_t)batch * VITK_NTOK * (VITK_DIM / 4);
-  const int grid = (int)((total + 255) / 256 < (int64_t)sm_count() * 16 ? (total + 255) / 256 : (int64_t)sm_count() * 16);
-  if (dtype == VITK_BF16) VITK_LAUNCH((im2col_kernel<bf16>), grid, 256, 0, st, images, (bf16*)patches, batch);
-  else VITK_LAUNCH((im2col_kernel<float>), grid, 256, 0, st, images, (float*)patches, batch);
-  return patch_gemm(wpe, bpe, cls, pos, patches, x0, batch, dtype, engine, st);
-}
-
-static int patch_gemm(const void* wpe, const float* bpe, const float* cls, const float* pos, void* patches, float* x0, int batch,
-                      int dtype, int engine, cudaStream_t st) {
-  GemmProblem p{};
-  p.I = batch * VITK_NTOK; p.J = VITK_DIM; p.R = VITK_DIM;
-  p.A = patches; p.B = wpe; p.in_dtype = dtype;
-  p.la = layout_rowmajor(VITK_DIM); p.lb = layout_rowmajor(VITK_DIM);
-  p.ep.mode = E_PATCH; p.ep.out = x0; p.ep.out_dtype = VITK_F32; p.ep.bias = bpe; p.ep.residual = pos;
-  p.ep.aux = const_cast<float*>(cls); p.ep.ldc = VITK_DIM;
-  return run_gemm(p, engine, 1, st);
-}
-
-extern "C" int vitk_patch_embed_wgrad(const float* dx0, const void* dx0_act, const void* patches, float* dwpe,
-                                      float* dbpe, float* dcls, float* dpos, int batch, int dtype, int engine,
-                                      void* stream) {
-  VITK_CHECK_ARG(dx0 && dx0_act && patches && dwpe && dbpe && dcls && dpos && batch > 0);
-  cudaStream_t st = (cudaStream_t)stream;
-  // CLS rows of `patches` are zero, so the plain token-row wgrad is exact (no row remap needed)
-  VITK_TRY(vitk_linear_wgrad(dx0_act, VITK_LAYOUT_ROWMAJOR, patches, dwpe, nullptr, batch * VITK_NTOK, VITK_DIM,
-                             VITK_DIM, dtype, engine, stream));
-  VITK_LAUNCH((embed_param_grads_kernel), VITK_NTOK, 256, 0, st, dx0, batch, dpos, dcls, dbpe);
   return VITK_OK;
 }

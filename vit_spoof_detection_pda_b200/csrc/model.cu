@@ -9,6 +9,7 @@ int attn_fwd_dispatch(const void* qkv, void* out, float* lse, int batch, int dty
 int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                       float* dqkv_colsum, int batch, int dtype, int engine, cudaStream_t st, int cs_sections);
 bool attn_bias_split_supported(int dtype, int engine);
+int colsum_headmajor(const void* x, int dtype, int M, int C, float* db, cudaStream_t st);   // linear.cu
 
 // vitk_model.sm_budget applies to the kernels THIS call enqueues (thread-local, restored on return)
 struct SmBudgetScope {
@@ -87,7 +88,7 @@ static int build_param_offsets(int depth, int num_classes, ParamOffsets* po, int
 struct Plan {
   size_t total;
   // forward (per-layer stride applies only when activations are saved)
-  size_t patches, x_in, x_mid, ln1, ln2, qkv, ao, u, g, mean1, rstd1, mean2, rstd2, lse;
+  size_t nchw, x_in, x_mid, ln1, ln2, qkv, ao, u, g, mean1, rstd1, mean2, rstd2, lse;
   size_t x_stride, act768_stride, qkv_stride, act3072_stride, stat_stride, lse_stride;
   size_t meanf, rstdf, feat, head_save;
   // backward transients
@@ -101,7 +102,7 @@ static void make_plan(int B, int depth, int precision, int training, int frozen,
   size_t cur = 0;
   auto take = [&](size_t bytes) { const size_t o = cur; cur += align_up(bytes, 256); return o; };
   const size_t L = save ? (size_t)depth : 1;
-  p->patches = take(M * D * T);
+  p->nchw = take((size_t)B * 3 * VITK_IMG * VITK_IMG * 4);   // fp32 NCHW image of a uint8-fed step (fp32-validate forward, weight gradient)
   p->x_stride = align_up(M * D * 4, 256);
   p->x_in = take(p->x_stride * (save ? depth + 1 : 2));   // eval: ping-pong
   p->x_mid = take(p->x_stride * L);
@@ -233,13 +234,14 @@ extern "C" int vitk_model_fwd(const vitk_model* m, void* stream) {
   void* st = stream;
   char* ws = c.ws;
   auto xin = [&](int l) { return (float*)(ws + pl.x_in + pl.x_stride * (size_t)(c.save ? l : (l & 1))); };
+  auto w16 = [&](int64_t off) -> const void* { return dt == VITK_BF16 ? (const void*)((const bf16*)m->params16 + off) : nullptr; };
 
   if (m->images_u8)   // uint8 HWC pixels: ToTensor + Normalize fused into the patch loader
-    VITK_TRY(vitk_patch_embed_fwd_u8(m->images_u8, m->norm_mean, m->norm_std, c.W(po.pew), c.P(po.peb), c.P(po.cls), c.P(po.pos),
-                                     ws + pl.patches, xin(0), m->batch, dt, eng, st));
+    VITK_TRY(vitk_patch_embed_fwd_u8(m->images_u8, m->norm_mean, m->norm_std, c.P(po.pew), w16(po.pew), c.P(po.peb), c.P(po.cls),
+                                     c.P(po.pos), xin(0), (float*)(ws + pl.nchw), m->batch, m->precision, eng, st));
   else
-    VITK_TRY(vitk_patch_embed_fwd(m->images, c.W(po.pew), c.P(po.peb), c.P(po.cls), c.P(po.pos), ws + pl.patches, xin(0),
-                                  m->batch, dt, eng, st));
+    VITK_TRY(vitk_patch_embed_fwd(m->images, c.P(po.pew), w16(po.pew), c.P(po.peb), c.P(po.cls), c.P(po.pos), xin(0), m->batch,
+                                  m->precision, eng, st));
   for (int l = 0; l < m->depth; ++l) {
     const BlockOffsets& b = po.blk[l];
     float* x = xin(l);
@@ -314,8 +316,13 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   }
   if (m->frozen_backbone) return VITK_OK;
   if (stage == m->depth + 1) {
-    return vitk_patch_embed_wgrad(dx, dxa, ws + pl.patches, c.G(po.pew), c.G(po.peb), c.G(po.cls), c.G(po.pos), m->batch,
-                                  dt, eng, st);
+    const float* img = m->images;
+    if (m->images_u8) {     // uint8-fed step: the weight gradient reads the normalised fp32 image
+      VITK_TRY(vitk_u8_to_nchw(m->images_u8, m->norm_mean, m->norm_std, (float*)(ws + pl.nchw), m->batch, st));
+      img = (const float*)(ws + pl.nchw);
+    }
+    VITK_CHECK_ARG(img);
+    return vitk_patch_embed_wgrad(dx, dx16, img, c.G(po.pew), c.G(po.peb), c.G(po.cls), c.G(po.pos), m->batch, m->precision, eng, st);
   }
   const int l = m->depth - stage;  // stage 1 -> last block
   const BlockOffsets& b = po.blk[l];
@@ -365,9 +372,13 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   const bool split_bias = attn_bias_split_supported(dt, eng);
   VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.projw), dh, nullptr, split_bias ? c.G(b.qkvb) + 2 * D : nullptr,
                              M, D, D, dt, eng, st));
-  VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, c.G(b.qkvb), m->batch, dt, eng, c.st,
-                             split_bias ? 1 : 7));
+  // (split_bias: the attention kernel sums nothing -- its epilogue warps gate the recycling of the dV / dK / dQ accumulators,
+  //  and the red.global adds of 148 CTAs into the same 64 floats of a head serialise in L2: measured 5.7 us per item on the
+  //  kernel's critical path.  The q section is a coalesced column-sum pass over dQ on the weight-gradient stream instead.)
+  VITK_TRY(attn_bwd_dispatch(qkv, ao, dh, (float*)c.at(pl.lse, pl.lse_stride, l), dqkv, split_bias ? nullptr : c.G(b.qkvb), m->batch,
+                             dt, eng, c.st, split_bias ? 0 : 7));
   VITK_TRY(after(5, ms, ss ? ss->s : ms));   // dqkv ready
+  if (split_bias) VITK_TRY(colsum_headmajor(dqkv, dt, M, D, c.G(b.qkvb), (cudaStream_t)wst));   // q section: heads 0..11 of dqkv
   VITK_TRY(vitk_linear_wgrad(dqkv, VITK_LAYOUT_HEADMAJOR, ln1, c.G(b.qkvw), nullptr, M, 3 * D, D, dt, eng, wst));
   VITK_TRY(vitk_linear_dgrad(dqkv, VITK_LAYOUT_HEADMAJOR, c.W(b.qkvw), dh, nullptr, nullptr, M, 3 * D, D, dt, eng, st));
   if (ss) VITK_CUDA(cudaStreamWaitEvent(ms, ss->ev[4], 0));              // the LayerNorm backward overwrites dx16
