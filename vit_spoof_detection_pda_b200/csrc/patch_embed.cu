@@ -2,20 +2,20 @@
 // reached from /root/reference/train_advanced.py:190/203) as an IM2COL-FREE GEMM FED BY TMA.
 //
 // The patch matrix  P[(b, py, px)][k = c*256 + i*16 + j] = image[b][c][16 py + i][16 px + j]  is never materialised in
-// global memory: a 5-D tensor map over the NCHW fp32 image -- dims (j 16, i 16, px 14, py 14, b*3+c), strides (4, 896,
-// 64, 14336, 200704) bytes -- lets ONE TMA box {16, NI, 14, NPY, 1} deliver NI image rows of 14*NPY patches into shared
-// memory as [patch][NI x 16 floats]: the K-slice (c, i0..i0+NI) of those patches, rows contiguous in k order.  Four
+// global memory: a 4-D tensor map over the NCHW fp32 image -- dims (x 224, i 16, py 14, b*3+c) with image row y = 16 py + i,
+// strides (4, 896, 14336, 200704) bytes -- lets ONE TMA box {224, NI, NPY, 1} deliver NI image rows of each of NPY patch
+// rows into shared memory as [py][i][224 pixels]: the K-slice (c, i0..i0+NI) of 14 * NPY patches.  Four
 // converter warps turn each raw box into a bf16 operand tile in the canonical 128-byte-swizzled layout ([row][64 k] =
 // 128 B rows, 16-byte chunk c at c ^ (row & 7)) -- byte for byte what a TMA load of a materialised bf16 patch matrix
 // would have produced -- and tcgen05.mma.kind::f16 consumes it next to the bf16 weights / gradients that arrive by TMA.
 //   forward   x0[b, 1+p, :] = P[b, p, :] . Wpe^T + bpe + pos[1+p] ;  x0[b, 0, :] = cls + pos[0]
 //             CTA = (image b, half h, 256 output columns): 128 accumulator rows = patches py in [9h, 9h+9) (126 rows; the box
 //             of h = 1 runs past py = 13 and is zero-filled); 12 k-blocks of 64 in (image-row group, channel) order.
-//   uint8 edge: the same kernel, raw boxes {48 B = 16 px x 3 ch, 4 rows, 14, 9, 1} of the HWC uint8 image;
+//   uint8 edge: the same kernel, raw boxes {672 B = 224 px x 3 ch, 4 rows, 9, 1} of the HWC uint8 image;
 //             the converter applies ToTensor + Normalize ((u / 255 - mean[c]) / std[c], fp32, torchvision's order:
 //             train_advanced.py:174-175) before the bf16 cast: the same values, in the same k order, as the fp32 edge.
 //   wgrad     dWpe[n][k] += sum_tokens dx0[token][n] * P[token][k]: both operands MN-major (token = reduction = slow axis
-//             of both arrays).  A = bf16 dx0 by TMA (3-D map [b][t][768], 64-token boxes), B = raw boxes {16, 16, 14, 4, 1}
+//             of both arrays).  A = bf16 dx0 by TMA (3-D map [b][t][768], 64-token boxes), B = raw boxes {224, 16, 4, 1}
 //             (56 patches x the 256 k of one channel) through the converter (rows 56..63 of the tile are zero);
 //             accumulator 128 (n) x 256 (k) in tensor memory, images split over CTAs, partial tiles summed with
 //             red.global.add.v4.f32.
@@ -34,11 +34,12 @@ constexpr int STAGES = 3;
 constexpr uint32_t A_BYTES = 128 * 128;    // bf16 operand tile of the patches: 128 rows x 64 k = 16 KB
 constexpr uint32_t B_BYTES = BN * 128;     // bf16 weights: 256 rows x 64 k = 32 KB
 constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;          // 48 KB
-constexpr uint32_t RAW_BYTES = 32768;      // fp32 box {16, 4, 14, 9, 1}: 126 x 256 B = 32,256; uint8 box {48, 4, 14, 9, 1}: 24,192
+constexpr uint32_t RAW_BYTES = 32768;      // fp32 box {224, 4, 9, 1}: 36 image rows x 896 B = 32,256; uint8 box: 36 x 672 B = 24,192
 constexpr uint32_t RAW_OFF = STAGES * STAGE_BYTES;           // 147,456
 constexpr uint32_t BAR_OFF = RAW_OFF + 2 * RAW_BYTES;        // 212,992
 constexpr size_t FWD_SMEM = 1024 + BAR_OFF + 256;
-constexpr int FWD_THREADS = 192;          // warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 converter + epilogue
+constexpr int NCW = 8;                     // converter / epilogue warps (two per tensor-memory lane quarter)
+constexpr int FWD_THREADS = 64 + 32 * NCW; // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 converter + epilogue
 constexpr int ROWS_H0 = 126, ROWS_H1 = 70;   // patches of the two halves of an image (9 and 5 patch rows)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,10 +71,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -127,45 +128,64 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) 
   return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }
 
-// ---- converter: one raw row segment (64 k values of one patch) -> 128 bytes of bf16 in a SWIZZLE_128B tile --------------
-// Task = (row, chunk ch of 4 values); a warp takes 2 rows x 16 chunks per pass: 512 contiguous raw bytes (fp32), 128-byte
-// tile rows written as 8-byte halves of the swizzled 16-byte chunks -- conflict-free on both sides.
-//   fp32 raw: values ch*4 .. ch*4+3 at raw_row + ch*16
-//   uint8 raw (HWC): row segment = [4 image rows][16 px][3 ch]; value (i_l = ch / 4, px = (ch % 4)*4 + x, channel c) at byte
-//                    i_l*48 + ((ch % 4)*4 + x)*3 + c
+// ---- converter: 64 k values (4 image rows x 16 pixels of one channel) of one patch -> 128 bytes of bf16 in a SWIZZLE_128B tile --
+// The raw box holds WHOLE image rows -- [patch row py][image row i][224 pixels] (fp32: 896 B rows; uint8 HWC: 672 B rows) --
+// because TMA moves a box as one request per contiguous inner row: boxes cut into 16-pixel rows (64 B) arrived at ~12
+// clocks per row and were the kernel's bottleneck (504 rows per k-block), whole image rows are 36.
+// Task = (patch r = py * 14 + px, chunk ch of 4 pixels: image row i = ch / 4, pixels 4 (ch % 4) ..); a warp takes 2 patches x 16
+// chunks per pass.
+//   fp32 raw : 4 floats at ((py * n_i + i0 + i) * 224 + px * 16 + (ch % 4) * 4) * 4
+//   uint8 raw: 12 bytes (4 pixels x 3 channels) at (py * 4 + i) * 672 + px * 48 + (ch % 4) * 12; channel c is picked out
 template <bool U8>
-__device__ __forceinline__ void convert_rows(uint32_t raw, uint32_t raw_row_stride, uint32_t raw_seg_off, uint32_t tile, int n_rows,
-                                             int n_tile_rows, int cw, int lane, int c, float mean, float sd) {
+__device__ __forceinline__ void convert_rows(uint32_t raw, int n_i, int i0, uint32_t tile, int n_rows, int n_tile_rows, int cw,
+                                             int lane, int c, float mean, float sd) {
   const int ch = lane & 15;
-  for (int r = cw * 2 + (lane >> 4); r < n_tile_rows; r += 8) {
-    uint32_t lo = 0u, hi = 0u;              // rows past n_rows: zeros
-    if (r < n_rows) {
+  const int r_first = cw * 2 + (lane >> 4);     // NCW warps x 2 rows per pass
+  // rows r_first + 8 k, four at a time: the four shared-memory fetches are issued before any of them is used (a
+  // one-row-per-iteration loop was bound by the load -> convert -> store latency: 160 clocks per row, 2,500 per k-block)
+#pragma unroll 1
+  for (int rb = r_first; rb < n_tile_rows; rb += 8 * NCW) {
+    uint32_t w[4][3];
+    float4 f[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + 2 * NCW * u;
+      const int rr = r < n_rows ? r : 0;
+      const int py = rr / 14, px = rr - py * 14;
       if (U8) {
-        const uint32_t src = raw + (uint32_t)r * raw_row_stride + raw_seg_off + (uint32_t)(ch >> 2) * 48 + (uint32_t)(ch & 3) * 12;
-        uint32_t w0, w1, w2;
-        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(src));
-        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(src + 4));
-        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w2) : "r"(src + 8));
-        const uint64_t lo64 = (uint64_t)w0 | ((uint64_t)w1 << 32);
+        const uint32_t src = raw + (uint32_t)((py * 4 + (ch >> 2)) * 672 + px * 48 + (ch & 3) * 12);
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[u][0]) : "r"(src));
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[u][1]) : "r"(src + 4));
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[u][2]) : "r"(src + 8));
+      } else {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[u].x), "=f"(f[u].y), "=f"(f[u].z), "=f"(f[u].w)
+                     : "r"(raw + (uint32_t)(((py * n_i + i0 + (ch >> 2)) * 224 + px * 16 + (ch & 3) * 4) * 4)));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + 2 * NCW * u;
+      if (r >= n_tile_rows) break;
+      uint32_t lo, hi;
+      if (U8) {
+        const uint64_t lo64 = (uint64_t)w[u][0] | ((uint64_t)w[u][1] << 32);
         float v[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
           const int byte = x * 3 + c;     // 0..11
-          const uint32_t u = byte < 8 ? (uint32_t)((lo64 >> (8 * byte)) & 0xffu) : ((w2 >> (8 * (byte - 8))) & 0xffu);
-          v[x] = ((float)u / 255.0f - mean) / sd;
+          const uint32_t uu = byte < 8 ? (uint32_t)((lo64 >> (8 * byte)) & 0xffu) : ((w[u][2] >> (8 * (byte - 8))) & 0xffu);
+          v[x] = ((float)uu / 255.0f - mean) / sd;
         }
         lo = pack_bf16x2(v[0], v[1]);
         hi = pack_bf16x2(v[2], v[3]);
       } else {
-        float4 f;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
-                     : "r"(raw + (uint32_t)r * raw_row_stride + raw_seg_off + (uint32_t)ch * 16));
-        lo = pack_bf16x2(f.x, f.y);
-        hi = pack_bf16x2(f.z, f.w);
+        lo = pack_bf16x2(f[u].x, f[u].y);
+        hi = pack_bf16x2(f[u].z, f[u].w);
       }
+      if (r >= n_rows) { lo = 0u; hi = 0u; }     // rows past n_rows: zeros
+      const uint32_t dst = tile + (uint32_t)r * 128 + ((((uint32_t)ch >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)ch & 1u) * 8;
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(lo), "r"(hi) : "memory");
     }
-    const uint32_t dst = tile + (uint32_t)r * 128 + ((((uint32_t)ch >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)ch & 1u) * 8;
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(lo), "r"(hi) : "memory");
   }
 }
 
@@ -199,17 +219,16 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap map_img, const __grid
   // k-block q covers k = c*256 + ig*64 .. +64 with ig = q / 3 (image rows 4 ig .. 4 ig + 3), c = q % 3: the uint8 raw box of
   // an image-row group holds all three channels; the fp32 edge walks the same order (bit-identical accumulators)
   constexpr int RAW_PER_KB = U8 ? 3 : 1;                     // k-blocks fed by one raw box
-  constexpr uint32_t RAW_TX = U8 ? 48u * 4u * 14u * 9u : 16u * 4u * 14u * 9u * 4u;
-  constexpr uint32_t RAW_ROW = U8 ? 192u : 256u;
+  constexpr uint32_t RAW_TX = U8 ? 672u * 4u * 9u : 224u * 4u * 4u * 9u;      // whole image rows: [9 py][4 i][224 px (x 3 ch | x 4 B)]
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_img)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 5);              // producer's expect_tx arrive (weights) + the four converter warps (patches)
+      mbar_init(full_bar(s), 1 + NCW);        // producer's expect_tx arrive (weights) + the converter warps (patches)
       mbar_init(empty_bar(s), 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), NCW); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -227,17 +246,20 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap map_img, const __grid
   if (warp == 0) {
     // ===================== TMA producer: raw image boxes + weight tiles =====================
     const bool leader = elect_one();
+    unsigned long long* trd = lane == 0 ? trace_detail_base(TK_PATCH_EMBED) : nullptr;
     for (int q = 0; q < N_KB; ++q) {
       const int s = q % STAGES, ig = q / 3, c = q % 3;
+      trace_detail(trd, 9, q);                  // producer reaches k-block q
       if (q % RAW_PER_KB == 0) {
         const int rq = q / RAW_PER_KB, rs = rq & 1;
         mbar_wait(raw_empty(rs), ((rq >> 1) & 1) ^ 1);
         if (leader) {
           mbar_expect_tx(raw_full(rs), RAW_TX);
-          tma_load_5d(sbase + RAW_OFF + rs * RAW_BYTES, &map_img, raw_full(rs), 0, ig * 4, 0, py0, U8 ? b : b * 3 + c);
+          tma_load_4d(sbase + RAW_OFF + rs * RAW_BYTES, &map_img, raw_full(rs), 0, ig * 4, py0, U8 ? b : b * 3 + c);
         }
       }
       mbar_wait(empty_bar(s), ((q / STAGES) & 1) ^ 1);
+      trace_detail(trd, 10, q);                 // stage free: weights issued
       if (leader) {
         mbar_expect_tx(full_bar(s), B_BYTES);
         tma_load_2d(sbase + s * STAGE_BYTES + A_BYTES, &map_w, full_bar(s), c * 256 + ig * 64, tn * BN);
@@ -248,10 +270,12 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap map_img, const __grid
     // ===================== MMA issuer =====================
     const bool leader = elect_one();
     constexpr uint32_t IDESC = idesc_bf16(BN, 0, 0);
+    unsigned long long* trd = lane == 0 ? trace_detail_base(TK_PATCH_EMBED) : nullptr;
     for (int q = 0; q < N_KB; ++q) {
       const int s = q % STAGES;
       mbar_wait(full_bar(s), (q / STAGES) & 1);
       tc_fence_after();
+      trace_detail(trd, 11, q);                 // operands of k-block q complete: MMAs issued
       if (leader) {
         const uint32_t sa = sbase + s * STAGE_BYTES;
 #pragma unroll
@@ -266,42 +290,65 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap map_img, const __grid
   } else {
     const int cw = warp - 2;                 // 0..3
     // ===================== converter: raw rows -> bf16 operand tiles =====================
+    unsigned long long* trd = (cw == 0 && lane == 0) ? trace_detail_base(TK_PATCH_EMBED) : nullptr;
     for (int q = 0; q < N_KB; ++q) {
       const int s = q % STAGES, c = q % 3;
       const int rq = q / RAW_PER_KB, rs = rq & 1;
       if (q % RAW_PER_KB == 0) mbar_wait(raw_full(rs), (rq >> 1) & 1);
+      trace_detail(trd, 12, q);                 // raw box of k-block q landed
       mbar_wait(empty_bar(s), ((q / STAGES) & 1) ^ 1);
-      convert_rows<U8>(sbase + RAW_OFF + rs * RAW_BYTES, RAW_ROW, 0u, sbase + s * STAGE_BYTES, ROWS_H0, 128, cw, lane, c,
-                       p.mean[c], p.stdv[c]);
+      trace_detail(trd, 13, q);                 // stage free: conversion starts
+      convert_rows<U8>(sbase + RAW_OFF + rs * RAW_BYTES, 4, 0, sbase + s * STAGE_BYTES, ROWS_H0, 128, cw, lane, c, p.mean[c], p.stdv[c]);
       fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(full_bar(s));
         if (q % RAW_PER_KB == RAW_PER_KB - 1) mbar_arrive(raw_empty(rs));   // the raw box has been consumed
       }
+      trace_detail(trd, 14, q);                 // conversion of k-block q done
     }
     // ===================== epilogue: + bias + pos_embed, token rows of this half; the CLS row =====================
     // tcgen05.ld hands a lane one accumulator ROW; the 32 x 32 chunk goes through a swizzled transpose buffer (the raw ring,
     // idle by now) so that 8 lanes cover 128 contiguous bytes of ONE token row: coalesced pos reads and x0 stores.
     const int q4 = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int chs = cw >> 2;                 // which interleaved half of the eight 32-column chunks
     const int nvalid = half ? ROWS_H1 : ROWS_H0;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    trace_detail((cw == 0 && lane == 0) ? trace_detail_base(TK_PATCH_EMBED) : nullptr, 8);      // main loop done, epilogue starts
     const uint32_t tb = sbase + RAW_OFF + (uint32_t)cw * 4096;
     const int sub_row = lane >> 3, c4 = lane & 7;
     const int t_base = 1 + half * ROWS_H0 + q4 * 32;       // token of this warp's accumulator row 0
+    // pos_embed / bias of the NEXT chunk are fetched while the current one is written (those of the first chunk under the
+    // end of the main loop): fetched inside the chunk they cost one global-memory round trip per chunk.  The loop is kept
+    // rolled: this code runs once per CTA, straight-line copies of it only add instruction-cache misses.
+    float4 pn[8], bn;
+    auto fetch_pos = [&](int ch) {
+      const int col = tn * BN + ch * 32 + c4 * 4;
+      bn = __ldg(reinterpret_cast<const float4*>(p.bpe + col));
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) {
+        const int rr = itr * 4 + sub_row;
+        const int t = (q4 * 32 + rr < nvalid) ? t_base + rr : 0;
+        pn[itr] = __ldg(reinterpret_cast<const float4*>(p.pos + (int64_t)t * VITK_DIM + col));
+      }
+    };
+    fetch_pos(chs);
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    trace_detail(trd, 8);                        // main loop done, epilogue starts
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
+    for (int ch = chs; ch < BN / 32; ch += 2) {
       uint32_t v[32];
       tm_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + ch * 32, v);
+      float4 pc[8];
+      const float4 b4 = bn;
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) pc[itr] = pn[itr];
+      if (ch + 2 < BN / 32) fetch_pos(ch + 2);
 #pragma unroll
       for (int g = 0; g < 8; ++g)
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tb + (uint32_t)(lane * 128 + ((g ^ (lane & 7)) << 4))),
                      "r"(v[g * 4]), "r"(v[g * 4 + 1]), "r"(v[g * 4 + 2]), "r"(v[g * 4 + 3]) : "memory");
       __syncwarp();
       const int col = tn * BN + ch * 32 + c4 * 4;
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bpe + col));
 #pragma unroll
       for (int itr = 0; itr < 8; ++itr) {
         const int rr = itr * 4 + sub_row;
@@ -310,13 +357,13 @@ patch_embed_fwd_kernel(const __grid_constant__ CUtensorMap map_img, const __grid
                      : "r"(tb + (uint32_t)(rr * 128 + ((c4 ^ (rr & 7)) << 4))));
         if (q4 * 32 + rr < nvalid) {
           const int t = t_base + rr;
-          const float4 pp = __ldg(reinterpret_cast<const float4*>(p.pos + (int64_t)t * VITK_DIM + col));
           *reinterpret_cast<float4*>(p.x0 + ((int64_t)b * VITK_NTOK + t) * VITK_DIM + col) =
-              make_float4(a.x + bb.x + pp.x, a.y + bb.y + pp.y, a.z + bb.z + pp.z, a.w + bb.w + pp.w);
+              make_float4(a.x + b4.x + pc[itr].x, a.y + b4.y + pc[itr].y, a.z + b4.z + pc[itr].z, a.w + b4.w + pc[itr].w);
         }
       }
       __syncwarp();
     }
+    trace_detail(trd, 15);                       // epilogue rows stored
     if (half == 0 && cw == 0) {              // x0[b, 0, :] = cls + pos[0]
       float* crow = p.x0 + (int64_t)b * VITK_NTOK * VITK_DIM + tn * BN;
       for (int j = lane * 4; j < BN; j += 128) {
@@ -343,11 +390,11 @@ constexpr uint32_t WG_A_BYTES = 2 * 8192;                    // bf16 dx0: 2 MN a
 constexpr uint32_t WG_B_BYTES = 4 * 8192;                    // bf16 patches: 4 MN atoms (64 k) x 64 tokens x 128 B
 constexpr uint32_t WG_STAGE = WG_A_BYTES + WG_B_BYTES;       // 48 KB
 constexpr int WG_STAGES = 2;
-constexpr uint32_t WG_RAW_BYTES = WG_ROWS * 1024;            // fp32 box {16, 16, 14, 4, 1}: 56 patches x 256 k = 57,344 B
+constexpr uint32_t WG_RAW_BYTES = WG_ROWS * 1024;            // fp32 box {224, 16, 4, 1}: 64 image rows x 896 B = 57,344 B
 constexpr uint32_t WG_RAW_OFF = WG_STAGES * WG_STAGE;        // 98,304
 constexpr uint32_t WG_BAR_OFF = WG_RAW_OFF + 2 * WG_RAW_BYTES;   // 212,992
 constexpr size_t WG_SMEM = 1024 + WG_BAR_OFF + 128;
-constexpr int WG_THREADS = 192;
+constexpr int WG_THREADS = 64 + 32 * NCW;
 constexpr int WG_TILES = (VITK_DIM / 128) * 3;               // 6 n tiles x 3 channels
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -373,8 +420,8 @@ patch_embed_wgrad_kernel(const __grid_constant__ CUtensorMap map_img, const __gr
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_img)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_dx)) : "memory");
-    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full_bar(s), 5); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 4); }
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full_bar(s), 1 + NCW); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), NCW); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -397,7 +444,7 @@ patch_embed_wgrad_kernel(const __grid_constant__ CUtensorMap map_img, const __gr
       mbar_wait(raw_empty(rs), ((it >> 1) & 1) ^ 1);
       if (leader) {
         mbar_expect_tx(raw_full(rs), WG_RAW_BYTES);
-        tma_load_5d(sbase + WG_RAW_OFF + rs * WG_RAW_BYTES, &map_img, raw_full(rs), 0, 0, 0, py0, b * 3 + c);
+        tma_load_4d(sbase + WG_RAW_OFF + rs * WG_RAW_BYTES, &map_img, raw_full(rs), 0, 0, py0, b * 3 + c);
       }
       mbar_wait(empty_bar(s), ((it / WG_STAGES) & 1) ^ 1);
       if (leader) {
@@ -438,7 +485,7 @@ patch_embed_wgrad_kernel(const __grid_constant__ CUtensorMap map_img, const __gr
       const uint32_t sb = sbase + s * WG_STAGE + WG_A_BYTES;
 #pragma unroll 1
       for (int ig = 0; ig < 4; ++ig)
-        convert_rows<false>(sbase + WG_RAW_OFF + rs * WG_RAW_BYTES, 1024u, (uint32_t)ig * 256u, sb + ig * 8192, WG_ROWS, 64, cw, lane, 0, 0.f, 1.f);
+        convert_rows<false>(sbase + WG_RAW_OFF + rs * WG_RAW_BYTES, 16, ig * 4, sb + ig * 8192, WG_ROWS, 64, cw, lane, 0, 0.f, 1.f);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -453,7 +500,7 @@ patch_embed_wgrad_kernel(const __grid_constant__ CUtensorMap map_img, const __gr
       tc_fence_after();
       float* drow = dw + (int64_t)(tn * 128 + q4 * 32 + lane) * VITK_DIM + c * 256;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = cw >> 2; ch < BN / 32; ch += 2) {
         uint32_t v[32];
         tm_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + ch * 32, v);
 #pragma unroll
@@ -539,19 +586,20 @@ static int encode(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (%s) failed: CUresult %d", what, (int)r); return VITK_ERR_DRIVER; }
   return VITK_OK;
 }
-// NCHW fp32 image as (j 16, i 16, px 14, py 14, b*3 + c); box {16, box_i, 14, box_py, 1}, no swizzle (read by the converter)
+// NCHW fp32 image as (x 224, i 16, py 14, b*3 + c) -- image row y = 16 py + i; box {224, box_i, box_py, 1}: whole image rows,
+// no swizzle (the converter warps read it)
 static int image_map_f32(const float* img, int batch, int box_i, int box_py, CUtensorMap* map) {
-  const cuuint64_t dims[5] = {16, 16, 14, 14, (cuuint64_t)batch * 3};
-  const cuuint64_t strides[4] = {VITK_IMG * 4, 16 * 4, 16 * VITK_IMG * 4, (cuuint64_t)VITK_IMG * VITK_IMG * 4};
-  const cuuint32_t box[5] = {16, (cuuint32_t)box_i, 14, (cuuint32_t)box_py, 1};
-  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, img, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, "image");
+  const cuuint64_t dims[4] = {VITK_IMG, 16, 14, (cuuint64_t)batch * 3};
+  const cuuint64_t strides[3] = {VITK_IMG * 4, 16 * VITK_IMG * 4, (cuuint64_t)VITK_IMG * VITK_IMG * 4};
+  const cuuint32_t box[4] = {VITK_IMG, (cuuint32_t)box_i, (cuuint32_t)box_py, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, img, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, "image");
 }
-// HWC uint8 image as (16 px x 3 ch = 48 B, i 16, px 14, py 14, b); box {48, 4, 14, 9, 1}, no swizzle
+// HWC uint8 image as (168 words = 224 px x 3 ch, i 16, py 14, b); box {168, 4, 9, 1}, no swizzle
 static int image_map_u8(const uint8_t* img, int batch, CUtensorMap* map) {
-  const cuuint64_t dims[5] = {48, 16, 14, 14, (cuuint64_t)batch};
-  const cuuint64_t strides[4] = {VITK_IMG * 3, 48, 16 * VITK_IMG * 3, (cuuint64_t)VITK_IMG * VITK_IMG * 3};
-  const cuuint32_t box[5] = {48, 4, 14, 9, 1};
-  return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, img, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, "uint8 image");
+  const cuuint64_t dims[4] = {VITK_IMG * 3 / 4, 16, 14, (cuuint64_t)batch};
+  const cuuint64_t strides[3] = {VITK_IMG * 3, 16 * VITK_IMG * 3, (cuuint64_t)VITK_IMG * VITK_IMG * 3};
+  const cuuint32_t box[4] = {VITK_IMG * 3 / 4, 4, 9, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, img, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, "uint8 image");
 }
 
 static int fwd_tc(const void* images, bool u8, const float* mean3, const float* std3, const void* wpe16, const float* bpe, const float* cls,
