@@ -165,12 +165,12 @@ def load_gemm_traffic():
     return d.get("dram_bytes_per_launch"), d.get("source")
 
 
-def train_config(n_gpus):
+def train_config(n_gpus, collective="none (single GPU)"):
     return {"workload": "ViT-B/16 224x224 binary PAD head full fine-tune step (fwd + focal loss + bwd + clip 1.0 + Adam "
                         "wd 1e-4), bf16, batch 64 per GPU, synthetic data (BASELINE configs[1]; N>1 = configs[4])",
             "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus, "img": 224, "depth": 12,
             "dropout": 0.1, "optimizer": "Adam(lr 1e-5, wd 1e-4) + clip_grad_norm 1.0 + cosine LR",
-            "parallelism": f"dp{n_gpus}",
+            "parallelism": f"dp{n_gpus}", "collective": collective,
             "l2": "per-step working set (~5 GB activations + 1 GB params/grads/moments) >> 126 MB L2; no flush needed"}
 
 
@@ -203,8 +203,11 @@ def run_ours(args):
     model.train()
     # VITK_GRAD_COMM=bf16 (opt-in, not the reported configuration): 16-bit gradient all-reduce, torch DDP's bf16_compress_hook
     comm_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(os.environ.get("VITK_GRAD_COMM", ""), None)
-    net = pkg.DataParallel(model, bucket_mb=float(os.environ.get("VITK_BUCKET_MB", "50")),
-                           grad_comm_dtype=comm_dtype) if world > 1 else model
+    # VITK_DP_MODE: auto (default) = the optimizer step fused with its collectives over NVSwitch multicast when the system has
+    # NVLS, else the bucketed NCCL all-reduce; nvls / nccl force one
+    net = pkg.DataParallel(model, bucket_mb=float(os.environ.get("VITK_BUCKET_MB", "50")), grad_comm_dtype=comm_dtype,
+                           mode=os.environ.get("VITK_DP_MODE", "auto")) if world > 1 else model
+    dp_mode = net.mode if world > 1 else "single"
     crit = pkg.FocalLoss(alpha=0.25, gamma=2.0)
     opt = pkg.FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4, adamw=False)
     total_sched_steps = 2 * (args.warmup + args.steps) + 64
@@ -320,6 +323,9 @@ def run_ours(args):
     barrier()
     model._flags = 0
 
+    if world > 1 and dp_mode == "nvls" and os.environ.get("VITK_NVLS_PROF") == "1":
+        rep = model._nvls.report()
+        sys.stderr.write(f"[rank {rank}] NVLS step phases (ms): {rep}\n")
     line = None
     if rank == 0:
         peaks = load_peaks()
@@ -363,6 +369,8 @@ def run_ours(args):
         # ---- batch-1 latency (CUDA-graph replay) and batch-256 throughput of the eval path (config 3)
         extra = {}
         try:
+            if args.no_extras:
+                raise RuntimeError("skipped (--no-extras)")
             model.eval()
             x1 = dev_imgs[0][:1].clone()
             with torch.no_grad():
@@ -423,6 +431,8 @@ def run_ours(args):
         # ---- HBM-bound kernels against the measured copy bandwidth, CUDA-event timed here: 20 back-to-back launches on
         # rotating bs-64 buffers (4 copies x 39..155 MB > the 126 MB L2); Adam over the model's own flat buffers
         try:
+            if args.no_extras:
+                raise RuntimeError("skipped (--no-extras)")
             extra["hbm_kernels"] = hbm_kernel_rooflines(torch, L, model, opt, dev, peaks["hbm_gbs"])
         except Exception as e:  # noqa: BLE001
             extra["hbm_kernels_error"] = repr(e)
@@ -458,7 +468,12 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": train_config(world), "clocks": sampler.summary(),
+                "config": train_config(world, {
+                    "single": "none (single GPU)",
+                    "nvls": "gradient reduce-scatter (multimem.ld_reduce) + Adam + parameter all-gather (multimem.st) fused in two "
+                            "kernels over NVSwitch multicast, after backward",
+                    "nccl": "bucketed fp32 ncclAllReduce (AVG) overlapped with backward, NCCL_MAX_CTAS=" + os.environ.get("NCCL_MAX_CTAS", "?"),
+                }[dp_mode]), "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "extra": extra}
@@ -519,15 +534,14 @@ def hbm_kernel_rooflines(torch, L, model, opt, dev, hbm_gbs):
     flat, g = model.flat_params(), model.flat_grads()
     n = flat.numel()
     p16 = model.flat_params16()
-    opt._ensure_state(flat)
+    bm, bv = torch.zeros_like(flat), torch.zeros_like(flat)      # scratch moments: the optimizer's own state is not touched
 
     def adam(i):
-        L.call("vitk_adam_step", L.ptr(flat), L.ptr(g), L.ptr(opt._m), L.ptr(opt._v), L.ptr(p16), n, 0.0, 0.9, 0.999, 1e-8, 0.0, 0,
+        L.call("vitk_adam_step", L.ptr(flat), L.ptr(g), L.ptr(bm), L.ptr(bv), L.ptr(p16), n, 0.0, 0.9, 0.999, 1e-8, 0.0, 0,
                1000, 1.0, None, 0.0, st)
 
-    snap_m, snap_v = opt._m.clone(), opt._v.clone()
     t = ev_time(adam)
-    opt._m.copy_(snap_m); opt._v.copy_(snap_v)
+    del bm, bv
     b = n * 30
     out["adam_kernel"] = {"bound": "hbm", "bytes": b, "us": t * 1e6, "achieved": b / t / 1e9, "peak": hbm_gbs, "unit": "GB/s",
                           "frac": b / t / 1e9 / hbm_gbs}
@@ -562,6 +576,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the inference / frozen-backbone / HBM-kernel extras (scaling sweeps)")
     ap.add_argument("--no-eager-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

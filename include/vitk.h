@@ -212,6 +212,32 @@ int vitk_adam_step(float* p, const float* g, float* m, float* v, void* p16, size
  * form of GradScaler.unscale_ (train_advanced.py:333) and clip_grad_norm_ (:334) for callers that pair them with stock
  * torch pieces instead of the fused Adam pass */
 int vitk_grad_scale(float* g, size_t n, float grad_mult, const float* sumsq, float max_norm, void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel optimizer step fused with its collectives over NVLink / NVSwitch multicast (csrc/dp_nvls.cu; new
+ * functionality for BASELINE configs[4], the reference is single-GPU).  Rank r owns `n` elements (its slice) of the flat
+ * buffers; `*_local` point at the slice in this rank's memory, `*_mc` at the same offset behind the MULTICAST address of the
+ * symmetric allocation (torch.distributed._symmetric_memory provides both).  The caller orders the ranks with three
+ * stream-ordered barriers: gradients final -> reduce_sumsq -> norm table complete -> adam_bcast -> parameters complete.
+ *   vitk_nvls_reduce_sumsq: g_local[i] = scale * sum_ranks g[i] (multimem.ld_reduce through the switch), and the slice's sum
+ *       of squares to entry `slot` of every rank's norm table (table_mc: multicast address of a float table with one entry per
+ *       (domain, rank)); partial = vitk_nvls_scratch_floats() floats of local scratch; max_ctas > 0 bounds the grid (a
+ *       reduce that runs on a side stream under the backward pass).
+ *   vitk_nvls_adam_bcast:   Adam / AdamW on the slice exactly as vitk_adam_step (clip coefficient from the sum of the `world`
+ *       table entries, max_norm <= 0 or sq_table == NULL: no clip), updated fp32 masters to p_mc and their bf16 shadow to
+ *       p16_mc (may be NULL): every rank's copy of the slice is written by the switch.  m, v: the slice's moments (local).
+ *       local_only_ranges (host array of n_ranges <= 64 [lo, hi) element pairs relative to the slice, multiples of 4): fp32
+ *       masters in these ranges are stored to p_local only -- the tensor-core GEMM weights, which every rank reads through
+ *       the bf16 shadow; vitk_nvls_bcast_f32 (a plain multicast copy with at most max_ctas CTAs, meant for a side stream under
+ *       the next forward pass) brings the other ranks' fp32 copies up to date.
+ * ------------------------------------------------------------------------------------------- */
+size_t vitk_nvls_scratch_floats(void);
+int vitk_nvls_reduce_sumsq(float* g_local, const float* g_mc, size_t n, float scale, float* partial, float* table_mc, int slot,
+                           int max_ctas, void* stream);
+int vitk_nvls_adam_bcast(float* p_local, float* p_mc, void* p16_mc, const float* g_local, float* m, float* v, size_t n,
+                         double lr, double beta1, double beta2, double eps, double weight_decay, int mode, int step,
+                         float grad_mult, const float* sq_table, int world, float max_norm,
+                         const int64_t* local_only_ranges, int n_ranges, void* stream);
+int vitk_nvls_bcast_f32(const float* src, float* dst_mc, size_t n, int max_ctas, void* stream);
 /* p16 = bf16(p) over a flat buffer (after load_state_dict / external optimizers) */
 int vitk_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 

@@ -22,6 +22,7 @@ from oracle import vit_oracle as vo  # noqa: E402  (checker)
 
 backend = sys.argv[1] if len(sys.argv) > 1 else "nccl"
 depth = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+dp_mode = sys.argv[3] if len(sys.argv) > 3 else "nccl"     # nccl: bucketed all-reduce under backward; nvls: fused step over multicast
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]) if backend == "nccl" else 0)
 torch.cuda.set_device(dev)
@@ -59,14 +60,77 @@ def check(tag, got, want, tol):
     assert err < tol and same, (tag, err, same)
 
 
-for precision, tol in (("fp32", 2e-4), ("bf16", 5e-2)):
+def nvls_check(precision, tol, overlap):
+    """NVLS mode reduces at the optimizer step, not per backward: compare PARAMETERS after three clipped Adam steps (the
+    second with two accumulated micro-batches) with a single-GPU run on the concatenated batches.  eps = 1 makes the update
+    ~ lr * g (linear in the gradient), so parameter differences measure gradient differences instead of sign flips of
+    near-zero gradients."""
     m = pkg.ViTFaceAntiSpoofing(dropout=0.0, depth=depth, precision=precision)
     m.load_state_dict(ref.state_dict())
     m = m.to(dev).train()
     single = pkg.ViTFaceAntiSpoofing(dropout=0.0, depth=depth, precision=precision)
     single.load_state_dict(ref.state_dict())
     single = single.to(dev).train()
-    net = pkg.DataParallel(m, bucket_mb=50.0 if depth >= 12 else 8.0)
+    net = pkg.DataParallel(m, mode="nvls", nvls_overlap=overlap, nvls_domains=3)
+    assert net.mode == "nvls"
+    o_dp = pkg.FusedAdam(m.parameters(), lr=1e-2, eps=1.0, weight_decay=1e-4, adamw=False)
+    o_s = pkg.FusedAdam(single.parameters(), lr=1e-2, eps=1.0, weight_decay=1e-4, adamw=False)
+    p0 = single.flat_params().clone()
+    # overlap=True reduce-scatters the first domains under backward (one backward per step); overlap=False also accumulates
+    for plan in (([0], [1], [0]) if overlap else ([0], [0, 1], [1])):
+        for k in plan:      # micro-steps accumulate locally; ONE reduce at the step
+            x, y = micro(k, rank)
+            (crit(net(x), y) / len(plan)).backward()
+            xs, ys = full(k)
+            (crit(single(xs), ys) / len(plan)).backward()
+        n_dp = pkg.clip_grad_norm_(m.parameters(), 0.05)
+        n_s = pkg.clip_grad_norm_(single.parameters(), 0.05)
+        o_dp.step(); o_s.step()
+        o_dp.zero_grad(set_to_none=True); o_s.zero_grad(set_to_none=True)
+        nerr = abs(float(n_dp) - float(n_s)) / float(n_s)
+        assert nerr < tol, ("global norm", precision, float(n_dp), float(n_s))
+    a, b = m.flat_params() - p0, single.flat_params() - p0
+    err = float((a - b).abs().max() / b.abs().max())
+    other = m.flat_params().clone()
+    dist.broadcast(other, src=0)
+    same = bool(torch.equal(other, m.flat_params()))
+    same16 = True
+    if precision == "bf16":
+        o16 = m.flat_params16().clone()
+        dist.broadcast(o16, src=0)
+        same16 = bool(torch.equal(o16, m.flat_params16())) and bool(torch.equal(m.flat_params16(), m.flat_params().to(torch.bfloat16)))
+    sd = o_dp.state_dict()      # moments are sharded: the state dict gathers them
+    msum = sum(float(v["exp_avg"].abs().sum()) for v in sd["state"].values())
+    ssum = sum(float(v["exp_avg"].abs().sum()) for v in o_s.state_dict()["state"].values())
+    if overlap:      # a second backward without a step must fail loudly
+        x, y = micro(0, rank)
+        crit(net(x), y).backward()
+        try:
+            crit(net(x), y).backward()
+            raised = False
+        except RuntimeError:
+            raised = True
+        assert raised, "gradient accumulation under nvls_overlap=True was not rejected"
+        o_dp.zero_grad(set_to_none=True)
+        dist.barrier()
+    print(f"rank {rank} [nvls {precision} overlap={overlap}] parameter-update rel err vs single GPU {err:.3e}; ranks identical {same}/{same16}; "
+          f"|m| {msum:.4e} vs {ssum:.4e}", flush=True)
+    assert err < tol * 5 and same and same16 and abs(msum - ssum) <= tol * 5 * ssum
+    del net, m, single
+
+
+for precision, tol in (("fp32", 2e-4), ("bf16", 5e-2)):
+    if dp_mode == "nvls":
+        nvls_check(precision, tol, overlap=False)
+        nvls_check(precision, tol, overlap=True)
+        continue
+    m = pkg.ViTFaceAntiSpoofing(dropout=0.0, depth=depth, precision=precision)
+    m.load_state_dict(ref.state_dict())
+    m = m.to(dev).train()
+    single = pkg.ViTFaceAntiSpoofing(dropout=0.0, depth=depth, precision=precision)
+    single.load_state_dict(ref.state_dict())
+    single = single.to(dev).train()
+    net = pkg.DataParallel(m, bucket_mb=50.0 if depth >= 12 else 8.0, mode="nccl")
 
     # single-GPU references: micro-step 0, micro-steps 0 + 1 accumulated
     crit(single(*full(0)[:1]), full(0)[1]).backward()

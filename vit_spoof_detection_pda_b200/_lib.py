@@ -63,6 +63,11 @@ PROTOTYPES = {
     "vitk_grad_sumsq": (i32, [vp, sz, vp, vp, vp]),
     "vitk_grad_scale": (i32, [vp, sz, f32, vp, f32, vp]),
     "vitk_adam_step": (i32, [vp, vp, vp, vp, vp, sz, f64, f64, f64, f64, f64, i32, i32, f32, vp, f32, vp]),
+    "vitk_nvls_scratch_floats": (sz, []),
+    "vitk_nvls_reduce_sumsq": (i32, [vp, vp, sz, f32, vp, vp, i32, i32, vp]),
+    "vitk_nvls_adam_bcast": (i32, [vp, vp, vp, vp, vp, vp, sz, f64, f64, f64, f64, f64, i32, i32, f32, vp, i32, f32,
+                             C.POINTER(i64), i32, vp]),
+    "vitk_nvls_bcast_f32": (i32, [vp, vp, sz, i32, vp]),
     "vitk_cast_f32_to_bf16": (i32, [vp, vp, sz, vp]),
     "vitk_param_layout": (i64, [i32, i32, C.POINTER(i64), C.POINTER(i64), i32]),
     "vitk_workspace_bytes": (sz, [i32, i32, i32, i32]),

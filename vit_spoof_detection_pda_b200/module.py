@@ -148,6 +148,9 @@ class ViTFaceAntiSpoofing(nn.Module):
         self._finish_hook = None   # set by DataParallel: fn() before gradients are handed to autograd
         self._pending_clip = None  # (sumsq tensor, max_norm) left by clip_grad_norm_ for FusedAdam
         self._sm_budget = 0        # set by DataParallel while a collective is in flight (vitk_model.sm_budget)
+        self._nvls = None          # set by DataParallel(mode="nvls"): the fused reduce + Adam + all-gather step (dp.NvlsStep)
+        self._masters_sync = None  # NVLS: waits for the background fp32-master copy (state_dict / flat_params call it)
+        self.register_state_dict_pre_hook(lambda mod, prefix, keep_vars: mod._masters_sync() if mod._masters_sync else None)
         self._flags = 0            # vitk_model.flags (L.FLAG_*)
         self.last_masks = None
         for p in self.parameters():
@@ -228,6 +231,24 @@ class ViTFaceAntiSpoofing(nn.Module):
         # version counters of the Parameters plus the flat buffer's own (writes through flat_params(), dist.broadcast)
         return sum(p._version for p in plist) + (self._flat._version if self._flat is not None else 0)
 
+    def adopt_flat_buffers(self, flat: torch.Tensor, flat16: Optional[torch.Tensor], grad: torch.Tensor):
+        """Move the flat fp32 masters / bf16 shadow / gradient storage into caller-provided buffers of (at least) the layout's
+        size -- used by DataParallel's NVLS mode, whose buffers are symmetric memory mapped behind a multicast address.
+        Current parameter values are copied; Parameters (and existing .grad views) are re-pointed."""
+        plist = self._ensure_flat()
+        total = self._total
+        assert flat.numel() >= total and flat.dtype == torch.float32 and grad.numel() >= total and grad.dtype == torch.float32
+        flat[:total].copy_(self._flat)
+        for p, off, n in zip(plist, self._offsets, self._sizes):
+            p.data = flat[off:off + n].view(p.shape)
+            p.grad = None
+        self._flat = flat[:total]
+        self._flat_grad = grad[:total]
+        self._flat_grad_alt = None
+        self._flat16 = flat16[:total] if flat16 is not None else None
+        self._shadow_version = -1
+        self.__dict__.pop("_plist_cache", None)
+
     def invalidate_shadow(self):
         """Force the bf16 weight shadow to be rebuilt before the next forward.  Call after writing the fp32 masters in a
         way that bypasses the Parameters' version counters (``p.data.copy_()``, raw writes through ``flat_params()`` on
@@ -251,6 +272,8 @@ class ViTFaceAntiSpoofing(nn.Module):
 
     def flat_params(self):
         self._ensure_flat()
+        if self._masters_sync is not None:
+            self._masters_sync()       # NVLS data parallel: the background copy of the other ranks' fp32 master slices
         return self._flat
 
     def flat_params16(self):

@@ -84,6 +84,16 @@ def clip_grad_norm_(parameters, max_norm: float):
         parameters = [parameters]
     owner, params = _owner_of(parameters, materialize=False)
     g = _gather_flat_grads(owner, params)
+    nvls = getattr(owner, "_nvls", None)
+    if nvls is not None:
+        # data parallel over NVSwitch multicast: the norm is that of the REDUCED gradient.  The reduce-scatter + partial sums
+        # of squares run here; the clip coefficient is applied by the fused Adam + all-gather kernel of FusedAdam.step()
+        fused_ref = getattr(owner, "_fused_opt", None)
+        if fused_ref is None or fused_ref() is None:
+            raise RuntimeError("DataParallel(mode='nvls') needs FusedAdam: the clip is applied inside its fused step")
+        nvls.reduce()
+        owner._pending_clip = ("nvls", float(max_norm))
+        return nvls.total_norm(getattr(owner, "_grad_mult", 1.0))
     sumsq = _sumsq(owner, g)
     mult = getattr(owner, "_grad_mult", 1.0)     # 1/scale after a LAZY FusedGradScaler.unscale_ (folded into the Adam pass)
     norm = sumsq.sqrt().reshape(())
@@ -117,9 +127,15 @@ class FusedAdam(torch.optim.Optimizer):
         self._v = None
 
     def _ensure_state(self, flat):
-        if self._m is None or self._m.device != flat.device or self._m.numel() != flat.numel():
-            self._m = torch.zeros_like(flat)
-            self._v = torch.zeros_like(flat)
+        nvls = getattr(self._owner, "_nvls", None)
+        if nvls is not None:       # NVLS data parallel: moments exist for this rank's slices only (one pair per domain)
+            if not isinstance(self._m, list):
+                self._m, self._v = nvls.alloc_moments()
+            return
+        n = flat.numel()
+        if self._m is None or isinstance(self._m, list) or self._m.device != flat.device or self._m.numel() != n:
+            self._m = torch.zeros(n, dtype=torch.float32, device=flat.device)
+            self._v = torch.zeros(n, dtype=torch.float32, device=flat.device)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -129,9 +145,13 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         owner = self._owner
         grp = self.param_groups[0]
-        flat = owner.flat_params()
+        owner._ensure_flat()
+        flat = owner._flat          # (not flat_params(): that accessor waits for the NVLS background master copy)
         self._ensure_state(flat)
         g = _gather_flat_grads(owner, grp["params"])
+        nvls = getattr(owner, "_nvls", None)
+        if nvls is not None:
+            return self._step_nvls(nvls, owner, grp, loss)
         sumsq, max_norm = None, 0.0
         if owner._pending_clip is not None:
             sumsq, max_norm = owner._pending_clip
@@ -157,6 +177,26 @@ class FusedAdam(torch.optim.Optimizer):
             owner.mark_shadow_fresh()
         return loss
 
+    def _step_nvls(self, nvls, owner, grp, loss):
+        """Data parallel over NVSwitch multicast (dp.NvlsStep): reduce-scatter (if clip_grad_norm_ has not done it yet) -> Adam
+        on this rank's slice -> all-gather of the updated masters and bf16 shadow, all inside two kernels."""
+        if any(not p.requires_grad for p in owner._param_list()):
+            raise RuntimeError("DataParallel(mode='nvls') does not support frozen parameters; use mode='nccl'")
+        max_norm = 0.0
+        if owner._pending_clip is not None:
+            max_norm = owner._pending_clip[1]
+            owner._pending_clip = None
+        elif self.max_grad_norm is not None:
+            max_norm = float(self.max_grad_norm)
+        nvls.reduce()
+        self._step += 1
+        mult = float(self.grad_mult) * float(getattr(owner, "_grad_mult", 1.0))
+        owner._grad_mult = 1.0
+        nvls.adam(self, grp, self._m, self._v, self._step, mult, max_norm)
+        if owner._flat16 is not None:
+            owner.mark_shadow_fresh()
+        return loss
+
     def _launch(self, flat, g, p16, lo, hi, grp, b1, b2, sumsq, max_norm):
         n = hi - lo
         if n <= 0:
@@ -171,14 +211,34 @@ class FusedAdam(torch.optim.Optimizer):
         self._owner._gathered_serial = None   # .grad tensors changed: the next clip / step re-validates them
 
     # torch.optim.AdamW-compatible state layout so save_checkpoint (train_advanced.py:475-489) round-trips
+    def _full_moments(self):
+        """(m, v) over the whole flat index space.  NVLS data parallel keeps only this rank's slice: gather the others."""
+        nvls = getattr(self._owner, "_nvls", None)
+        if nvls is None:
+            return self._m, self._v
+        import torch.distributed as dist
+        dev = self._m[0].device
+        fm = torch.zeros(nvls.total, dtype=torch.float32, device=dev)
+        fv = torch.zeros_like(fm)
+        for k, d in enumerate(nvls.domains):      # every rank's slice of the domain, padded to the common slice length
+            for src, dst in ((self._m[k], fm), (self._v[k], fv)):
+                mine = torch.zeros(d["per"], dtype=torch.float32, device=dev)
+                mine[:d["n"]].copy_(src[:d["n"]])
+                allp = torch.empty(d["per"] * nvls.world, dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(allp, mine, group=nvls.group)
+                n = d["hi"] - d["lo"]
+                dst[d["lo"]:d["hi"]].copy_(allp[:n])
+        return fm, fv
+
     def state_dict(self):
         owner = self._owner
         state = {}
         if self._m is not None:
+            fm, fv = self._full_moments()
             for i, (p, off, n) in enumerate(zip(owner._param_list(), owner._offsets, owner._sizes)):
                 state[i] = {"step": torch.tensor(float(self._step)),
-                            "exp_avg": self._m[off:off + n].view(p.shape).clone(),
-                            "exp_avg_sq": self._v[off:off + n].view(p.shape).clone()}
+                            "exp_avg": fm[off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": fv[off:off + n].view(p.shape).clone()}
         grp = {k: v for k, v in self.param_groups[0].items() if k != "params"}
         grp["params"] = list(range(len(owner._param_list())))
         return {"state": state, "param_groups": [grp]}
@@ -190,13 +250,20 @@ class FusedAdam(torch.optim.Optimizer):
         for k, v in sd["param_groups"][0].items():
             if k != "params":
                 self.param_groups[0][k] = v
+        nvls = getattr(owner, "_nvls", None)
+        fm, fv = (self._m, self._v) if nvls is None else (torch.zeros(nvls.total, dtype=torch.float32, device=flat.device),
+                                                          torch.zeros(nvls.total, dtype=torch.float32, device=flat.device))
         for i, (p, off, n) in enumerate(zip(owner._param_list(), owner._offsets, owner._sizes)):
             st = sd["state"].get(i)
             if st is None:
                 continue
-            self._m[off:off + n].copy_(st["exp_avg"].reshape(-1))
-            self._v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            fm[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            fv[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
             self._step = int(float(st["step"]))
+        if nvls is not None:      # keep this rank's slices
+            for k, d in enumerate(nvls.domains):
+                self._m[k][:d["n"]].copy_(fm[d["a"]:d["a"] + d["n"]])
+                self._v[k][:d["n"]].copy_(fv[d["a"]:d["a"] + d["n"]])
 
 
 class FusedGradScaler:
