@@ -209,7 +209,10 @@ def run_ours(args):
                            mode=os.environ.get("VITK_DP_MODE", "auto")) if world > 1 else model
     dp_mode = net.mode if world > 1 else "single"
     crit = pkg.FocalLoss(alpha=0.25, gamma=2.0)
-    opt = pkg.FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4, adamw=False)
+    # single GPU: the step is captured into a CUDA graph (pkg.GraphedTrainStep; VITK_GRAPH=0 keeps the eager launches); the
+    # data-parallel modes use the eager step (their collectives / hooks run between the backward stages)
+    use_graph = world == 1 and os.environ.get("VITK_GRAPH", "1") != "0"
+    opt = pkg.FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4, adamw=False, capturable=use_graph)
     total_sched_steps = 2 * (args.warmup + args.steps) + 64
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=total_sched_steps, eta_min=1e-6)
 
@@ -221,7 +224,7 @@ def run_ours(args):
     dev_imgs = [t.to(dev) for t in host_imgs]
     dev_lbls = [t.to(dev) for t in host_lbls]
 
-    def step(images, labels):
+    def eager_step(images, labels):
         out = net(images)
         loss, met = crit(out, labels, with_metrics=True)
         loss.backward()
@@ -230,6 +233,22 @@ def run_ours(args):
         opt.zero_grad(set_to_none=True)
         sched.step()
         return loss, met
+
+    launches_per_step = None
+    if use_graph:
+        eager_step(dev_imgs[0], dev_lbls[0])                   # also counts the kernels one step launches
+        torch.cuda.synchronize()
+        l0 = lib.vitk_launch_count()
+        eager_step(dev_imgs[1], dev_lbls[1])
+        launches_per_step = lib.vitk_launch_count() - l0
+        gstep = pkg.GraphedTrainStep(model, crit, opt, dev_imgs[0], dev_lbls[0], max_grad_norm=1.0)
+
+        def step(images, labels):
+            loss, met = gstep(images, labels)
+            sched.step()
+            return loss, met
+    else:
+        step = eager_step
 
     def barrier():
         if world > 1:
@@ -247,6 +266,8 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = lib.vitk_launch_count() - l0
+        if launches_per_step is not None:
+            launches = launches_per_step * steps             # graph replays launch the captured kernels
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -273,6 +294,11 @@ def run_ours(args):
         sus_sampler.stop()
         sustained = {"steps": n_sus, "ms_per_step": ms_sus / n_sus, "img_s": world * B * n_sus / (ms_sus / 1e3),
                      "clocks": sus_sampler.summary()}
+
+    eager_ms = None
+    if use_graph:       # the same step with eager launches, for the record (extra.eager_ms_per_step)
+        ms_eager, _ = timed(lambda i: eager_step(dev_imgs[i % n_pool], dev_lbls[i % n_pool]), max(10, args.steps // 2))
+        eager_ms = ms_eager / max(10, args.steps // 2)
 
     # ---- end to end through the public API with host buffers ("e2e"): every step copies its own batch from pinned
     # host memory (DevicePrefetcher: the copy of batch i+1 overlaps step i) and reads loss + accuracy back
@@ -319,7 +345,7 @@ def run_ours(args):
     if rank == 0:
         lib.vitk_prof_enable(1)
     for i in range(2):
-        step(dev_imgs[i % n_pool], dev_lbls[i % n_pool])
+        eager_step(dev_imgs[i % n_pool], dev_lbls[i % n_pool])      # per-launch events need the eager launches
     barrier()
     model._flags = 0
 
@@ -451,6 +477,9 @@ def run_ours(args):
             except Exception as e:  # noqa: BLE001
                 extra["torch_eager_error"] = repr(e)
 
+        extra["step_mode"] = "cuda graph replay (pkg.GraphedTrainStep)" if use_graph else "eager launches"
+        if eager_ms is not None:
+            extra["eager_ms_per_step"] = eager_ms
         per_gpu = value / world
         extra.update({
             "tflops_per_gpu": per_gpu * TRAIN_FLOP_PER_IMG / 1e12,

@@ -208,6 +208,12 @@ int vitk_grad_sumsq(const float* g, size_t n, float* partial, float* sumsq, void
 int vitk_adam_step(float* p, const float* g, float* m, float* v, void* p16, size_t n, double lr,
                    double beta1, double beta2, double eps, double weight_decay, int mode, int step,
                    float grad_mult, const float* sumsq, float max_norm, void* stream);
+/* The same step for a CUDA-GRAPH-CAPTURED training loop: the step count and the learning rate are read from device memory
+ * (step_dev is incremented by the launch itself; lr_dev is written by the host between replays), the bias corrections are
+ * computed on the device into hyper (3 floats of caller scratch). */
+int vitk_adam_step_graph(float* p, const float* g, float* m, float* v, void* p16, size_t n, const float* lr_dev,
+                         int* step_dev, float* hyper, double beta1, double beta2, double eps, double weight_decay, int mode,
+                         float grad_mult, const float* sumsq, float max_norm, void* stream);
 /* g *= grad_mult * clipcoef in place, clipcoef as in vitk_adam_step (1 when sumsq == NULL or max_norm <= 0): the eager
  * form of GradScaler.unscale_ (train_advanced.py:333) and clip_grad_norm_ (:334) for callers that pair them with stock
  * torch pieces instead of the fused Adam pass */

@@ -56,6 +56,35 @@ print(f"host enqueue {t_cpu / N * 1e3:.3f} ms/step (queue drained before every s
 for k, v in acc.items():
     print(f"  {k:10s} {v / N * 1e3:7.3f} ms")
 
+# ---- the same step captured into a CUDA graph (pkg.GraphedTrainStep): host cost of one replay
+opt_g = pkg.FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4, adamw=False, capturable=True)
+gstep = pkg.GraphedTrainStep(model, crit, opt_g, x, y, max_grad_norm=1.0)
+for _ in range(3):
+    gstep(x, y)
+torch.cuda.synchronize()
+t_cpu = 0.0
+e0.record()
+for _ in range(N):
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    gstep(x, y)
+    t_cpu += time.perf_counter() - t1
+e1.record()
+torch.cuda.synchronize()
+print(f"graphed step: host enqueue {t_cpu / N * 1e3:.3f} ms/step, wall incl. drains {e0.elapsed_time(e1) / N:.3f} ms/step")
+e0.record()
+for _ in range(N):
+    gstep(x, y)
+e1.record()
+torch.cuda.synchronize()
+print(f"graphed step back to back: {e0.elapsed_time(e1) / N:.3f} ms/step")
+e0.record()
+for _ in range(N):
+    step()
+e1.record()
+torch.cuda.synchronize()
+print(f"eager step back to back:   {e0.elapsed_time(e1) / N:.3f} ms/step")
+
 if os.environ.get("PROFILE"):
     import cProfile
     import pstats

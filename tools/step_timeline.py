@@ -165,7 +165,7 @@ def main():
     if a.detail:
         hb = buf.cpu()
         with open(a.out + "_detail.md", "w") as f:
-            for kid in (3, 12):
+            for kid in (2, 3, 12):
                 d = detail_of(hb, kid)
                 if not d:
                     continue

@@ -10,7 +10,7 @@ from .dp import DataParallel, DevicePrefetcher, HostScalars
 from .loss import FocalLoss, eval_postprocess
 from .metrics import ThresholdSweep, confusion_counts, find_optimal_threshold
 from .module import ViTFaceAntiSpoofing
-from .optim import FusedAdam, FusedGradScaler, clip_grad_norm_
+from .optim import FusedAdam, FusedGradScaler, GraphedTrainStep, clip_grad_norm_
 
-__all__ = ["ViTFaceAntiSpoofing", "FocalLoss", "FusedAdam", "FusedGradScaler", "clip_grad_norm_", "DataParallel", "DevicePrefetcher", "HostScalars", "eval_postprocess", "ThresholdSweep",
+__all__ = ["ViTFaceAntiSpoofing", "FocalLoss", "FusedAdam", "FusedGradScaler", "clip_grad_norm_", "GraphedTrainStep", "DataParallel", "DevicePrefetcher", "HostScalars", "eval_postprocess", "ThresholdSweep",
            "find_optimal_threshold", "confusion_counts", "save_checkpoint", "load_checkpoint", "extract_model_state_dict", "_lib"]

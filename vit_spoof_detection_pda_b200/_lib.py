@@ -61,6 +61,7 @@ PROTOTYPES = {
     "vitk_threshold_counts": (i32, [vp, i32, vp, vp]),
     "vitk_grad_sumsq_scratch_floats": (sz, []),
     "vitk_grad_sumsq": (i32, [vp, sz, vp, vp, vp]),
+    "vitk_adam_step_graph": (i32, [vp, vp, vp, vp, vp, sz, vp, vp, vp, f64, f64, f64, f64, i32, f32, vp, f32, vp]),
     "vitk_grad_scale": (i32, [vp, sz, f32, vp, f32, vp]),
     "vitk_adam_step": (i32, [vp, vp, vp, vp, vp, sz, f64, f64, f64, f64, f64, i32, i32, f32, vp, f32, vp]),
     "vitk_nvls_scratch_floats": (sz, []),

@@ -71,10 +71,29 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p = p - a.step_size * (m / denom);
 }
 
+// Step-dependent scalars computed ON THE DEVICE (CUDA-graph capture of the training step: a replayed launch cannot carry a new
+// step count or learning rate in its arguments): step = ++*step_dev; hyper = {step_size, sqrt(bias correction 2), decay}
+__global__ void adam_prepare_kernel(const float* __restrict__ lr_dev, int* __restrict__ step_dev, double beta1, double beta2,
+                                    double wd, float* __restrict__ hyper) {
+  pdl_sync_traced(TK_ADAM);
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int step = *step_dev + 1;
+    *step_dev = step;
+    const double lr = (double)lr_dev[0];
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    hyper[0] = (float)(lr / bc1);
+    hyper[1] = (float)sqrt(bc2);
+    hyper[2] = (float)(1.0 - lr * wd);
+  }
+  trace_end(TK_ADAM);
+}
+
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            bf16* __restrict__ p16, size_t n, AdamArgs a, const float* __restrict__ sumsq) {
+            bf16* __restrict__ p16, size_t n, AdamArgs a, const float* __restrict__ sumsq, const float* __restrict__ hyper) {
   pdl_sync_traced(TK_ADAM);
+  if (hyper) { a.step_size = hyper[0]; a.bc2_sqrt = hyper[1]; a.decay = hyper[2]; }
   float gm = a.grad_mult;
   if (sumsq && a.max_norm > 0.f) {
     const float total = sqrtf(sumsq[0]) * a.grad_mult;
@@ -192,7 +211,25 @@ extern "C" int vitk_adam_step(float* p, const float* g, float* m, float* v, void
   a.step_size = (float)(lr / bc1);
   a.bc2_sqrt = (float)sqrt(bc2);
   a.decay = (float)(1.0 - lr * weight_decay);
-  VITK_LAUNCH((adam_kernel), stream_grid(n / 4), 256, 0, (cudaStream_t)stream, p, g, m, v, (bf16*)p16, n, a, sumsq);
+  VITK_LAUNCH((adam_kernel), stream_grid(n / 4), 256, 0, (cudaStream_t)stream, p, g, m, v, (bf16*)p16, n, a, sumsq, (const float*)nullptr);
+  return VITK_OK;
+}
+
+extern "C" int vitk_adam_step_graph(float* p, const float* g, float* m, float* v, void* p16, size_t n, const float* lr_dev,
+                                    int* step_dev, float* hyper, double beta1, double beta2, double eps, double weight_decay,
+                                    int mode, float grad_mult, const float* sumsq, float max_norm, void* stream) {
+  VITK_CHECK_ARG(p && g && m && v && lr_dev && step_dev && hyper && (mode == 0 || mode == 1));
+  VITK_CHECK_ARG(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0);
+  VITK_CHECK_ARG(p16 == nullptr || ((uintptr_t)p16 % 8) == 0);
+  AdamArgs a;
+  a.lr = 0.f; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps; a.wd = (float)weight_decay;
+  a.mode = mode;
+  a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
+  a.grad_mult = grad_mult; a.max_norm = max_norm;
+  a.step_size = 0.f; a.bc2_sqrt = 1.f; a.decay = 1.f;      // replaced by `hyper` on the device
+  cudaStream_t st = (cudaStream_t)stream;
+  VITK_LAUNCH((adam_prepare_kernel), 1, 32, 0, st, lr_dev, step_dev, beta1, beta2, weight_decay, hyper);
+  VITK_LAUNCH((adam_kernel), stream_grid(n / 4), 256, 0, st, p, g, m, v, (bf16*)p16, n, a, sumsq, (const float*)hyper);
   return VITK_OK;
 }
 

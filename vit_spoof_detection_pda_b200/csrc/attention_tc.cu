@@ -29,6 +29,7 @@ namespace atc {
 
 constexpr int N_TOK = VITK_NTOK;            // 197
 constexpr int NK = 208;                     // key columns of S (multiple of 16)
+constexpr uint32_t O0_COL = 2 * NK;         // O of the 128-row tile: the 64 tensor-memory columns behind the two S tiles
 constexpr int THREADS = 320;
 constexpr uint32_t Q_BYTES = 256 * 128;     // 32 KB  (two 128-row A tiles)
 constexpr uint32_t KV_BYTES = NK * 128;     // 26 KB
@@ -292,15 +293,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const bool leader = elect_one();
     constexpr uint32_t IDESC_S = make_idesc(NK, 0, 0);    // S = Q K^T : both K-major, N = 208
     constexpr uint32_t IDESC_O = make_idesc(64, 0, 1);    // O = P V   : A in TMEM, B = V MN-major, N = 64
+    unsigned long long* trd = lane == 0 ? trace_detail_base(TK_ATTN_FWD) : nullptr;
     for (int it = 0; it < n_my; ++it) {
       const int s = it & 1;
       const uint32_t par = it & 1;
       const uint32_t sq = sbase + s * STAGE_BYTES, sk = sq + Q_BYTES, sv = sk + KV_BYTES;
+      trace_detail(trd, 8, it);              // MMA warp reaches item
       mbar_wait(ld_full(s), (it >> 1) & 1);
+      trace_detail(trd, 9, it);              // operands landed
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        mbar_wait(t_free(t), par ^ 1);     // the previous item's O_t has been read out of tensor memory
+        // S_1 overwrites the columns of the previous item's O_1; O_0 lives in the spare columns (416..479) so that S_0 of the
+        // next item -- the 128-row tile is the critical chain -- does not wait for the previous O_0 to be stored
+        if (t == 1) mbar_wait(t_free(1), par ^ 1);
         tc_fence_after();
+        trace_detail(trd, 10 + t, it);         // S_t issued
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -312,11 +319,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         mbar_wait(p_full(t), par);         // P_t (bf16) is in tensor memory columns [208t, 208t + 104)
+        if (t == 0) mbar_wait(t_free(0), par ^ 1);     // the previous item's O_0 has been read out of the spare columns
         tc_fence_after();
+        trace_detail(trd, 12 + t, it);         // O_t issued
         if (leader) {
 #pragma unroll
           for (int ks = 0; ks < NK / 16; ++ks)
-            mma_ts(tmem_base + t * NK + 128, tmem_base + t * NK + ks * 8, desc_lo(sv + ks * 2048), DESC_HI, IDESC_O, ks > 0 ? 1u : 0u);
+            mma_ts(tmem_base + (t == 0 ? O0_COL : NK + 128), tmem_base + t * NK + ks * 8, desc_lo(sv + ks * 2048), DESC_HI, IDESC_O, ks > 0 ? 1u : 0u);
           tc_commit(o_full(t));
           if (t == 1) tc_commit(ld_empty(s));   // every MMA reading this stage has retired
         }
@@ -331,14 +340,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int row = qr * 32 + lane;      // row inside the tile
     const int q = t * 128 + row;         // query index
     const bool warp_valid = (t * 128 + qr * 32) < N_TOK;
-    const uint32_t taddr = tmem_base + ((uint32_t)(qr * 32) << 16) + (uint32_t)(t * NK);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(qr * 32) << 16);
+    const uint32_t taddr = lane_base + (uint32_t)(t * NK);
     const float sl2 = SCALE * LOG2E;
+    unsigned long long* trd = (qr == 0 && lane == 0) ? trace_detail_base(TK_ATTN_FWD) : nullptr;
     for (int it = 0; it < n_my; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int b = item / VITK_HEADS, h = item % VITK_HEADS;
       const uint32_t par = it & 1;
       mbar_wait(s_full(t), par);
       tc_fence_after();
+      trace_detail(trd, 14 + t, it);           // S_t complete: softmax starts
       float m = -INFINITY, l = 0.f;
       if (warp_valid) {
         // ---- ONE pass over the 208 scores (tensor-memory reads are the scarce resource: ~64 B/clk/SM).  p = 2^((s - m)*c)
@@ -413,9 +425,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(t));
-      // ---- O_t = P_t V is accumulated into columns [208t + 128, 208t + 192)
+      trace_detail(trd, 16 + t, it);           // P_t handed over
+      // ---- O_t = P_t V is accumulated into columns [416, 480) (t = 0) / [208 + 128, 208 + 192) (t = 1)
       mbar_wait(o_full(t), par);
       tc_fence_after();
+      trace_detail(trd, 18 + t, it);           // O_t complete
       if (warp_valid) {
         uint32_t o[32];
         // 1/l of every row of this warp (the staging transpose hands rows to other lanes)
@@ -424,7 +438,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         bf16* obase = out + ((int64_t)b * N_TOK) * VITK_DIM + h * VITK_HEAD_DIM;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          tm_ld32(taddr + 128 + half * 32, o);
+          tm_ld32((t == 0 ? lane_base + O0_COL : taddr + 128) + half * 32, o);
           tm_ld_wait();
           store_slab32(sbase + STG_OFF + (uint32_t)we * 2048, lane, o, inv,
                        [&](int r) -> bf16* { return (q0w + r < N_TOK) ? obase + (int64_t)(q0w + r) * VITK_DIM + half * 32 : nullptr; });
@@ -434,6 +448,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_free(t));
+      trace_detail(trd, 20 + t, it);           // O_t stored, tensor memory released
     }
   }
 

@@ -112,7 +112,7 @@ class FusedAdam(torch.optim.Optimizer):
     """One kernel over the flat buffers: (optional) clip scale -> Adam/AdamW update -> bf16 shadow write."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, adamw=True,
-                 max_grad_norm=None, grad_mult: float = 1.0):
+                 max_grad_norm=None, grad_mult: float = 1.0, capturable: bool = False):
         params = list(params)
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, adamw=adamw)
         super().__init__(params, defaults)
@@ -125,8 +125,18 @@ class FusedAdam(torch.optim.Optimizer):
         self._step = 0
         self._m = None
         self._v = None
+        # capturable: step count and learning rate live in device memory (bias corrections computed on the device), so that the
+        # whole training step can be captured into a CUDA graph and replayed (GraphedTrainStep)
+        self.capturable = bool(capturable)
+        self._step_dev = self._lr_dev = self._hyper = self._lr_host = None
 
     def _ensure_state(self, flat):
+        if self.capturable and self._step_dev is None:      # device-side step count / learning rate (before the step is counted)
+            dev = flat.device
+            self._lr_host = torch.full((1,), float("nan"), dtype=torch.float32).pin_memory()
+            self._lr_dev = torch.empty(1, dtype=torch.float32, device=dev)
+            self._step_dev = torch.full((1,), self._step, dtype=torch.int32, device=dev)
+            self._hyper = torch.zeros(4, dtype=torch.float32, device=dev)
         nvls = getattr(self._owner, "_nvls", None)
         if nvls is not None:       # NVLS data parallel: moments exist for this rank's slices only (one pair per domain)
             if not isinstance(self._m, list):
@@ -197,9 +207,26 @@ class FusedAdam(torch.optim.Optimizer):
             owner.mark_shadow_fresh()
         return loss
 
+    def _sync_lr(self, non_blocking: bool = True):
+        """capturable mode: hand the current param_group lr (set by an LR scheduler on the host) to the device."""
+        lr = float(self.param_groups[0]["lr"])
+        if float(self._lr_host[0]) != lr:
+            self._lr_host[0] = lr
+            self._lr_dev.copy_(self._lr_host, non_blocking=non_blocking)
+
     def _launch(self, flat, g, p16, lo, hi, grp, b1, b2, sumsq, max_norm):
         n = hi - lo
         if n <= 0:
+            return
+        if self.capturable:
+            if lo != 0 or hi != flat.numel():
+                raise RuntimeError("FusedAdam(capturable=True) does not support frozen parameter ranges")
+            if not torch.cuda.is_current_stream_capturing():
+                self._sync_lr()
+            L.call("vitk_adam_step_graph", flat.data_ptr(), g.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
+                   p16.data_ptr() if p16 is not None else None, n, L.ptr(self._lr_dev), L.ptr(self._step_dev), L.ptr(self._hyper),
+                   float(b1), float(b2), float(grp["eps"]), float(grp["weight_decay"]), 1 if grp["adamw"] else 0,
+                   float(self._grad_mult_now), L.ptr(sumsq), float(max_norm), L.stream_ptr())
             return
         L.call("vitk_adam_step", flat.data_ptr() + 4 * lo, g.data_ptr() + 4 * lo, self._m.data_ptr() + 4 * lo,
                self._v.data_ptr() + 4 * lo, (p16.data_ptr() + 2 * lo) if p16 is not None else None, n,
@@ -260,6 +287,8 @@ class FusedAdam(torch.optim.Optimizer):
             fm[off:off + n].copy_(st["exp_avg"].reshape(-1))
             fv[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
             self._step = int(float(st["step"]))
+        if self._step_dev is not None:
+            self._step_dev.fill_(self._step)
         if nvls is not None:      # keep this rank's slices
             for k, d in enumerate(nvls.domains):
                 self._m[k][:d["n"]].copy_(fm[d["a"]:d["a"] + d["n"]])
@@ -380,3 +409,66 @@ def _complement(ranges, total):
         out.append((cur, total))
     # launches need 16-byte aligned starts: offsets are multiples of 64 elements by construction
     return out
+
+
+class GraphedTrainStep:
+    """The reference's optimisation step (train_advanced.py:322-346: forward, focal loss, backward, clip_grad_norm_, optimizer
+    step, zero_grad) captured ONCE into a CUDA graph and replayed: ~290 kernel launches and the autograd / ctypes walk of a step
+    become one graph launch, so the host side of a step costs tens of microseconds instead of ~4 ms.
+
+        step = GraphedTrainStep(model, criterion, optimizer, images, labels, max_grad_norm=1.0)
+        for images, labels in loader:
+            loss, metrics = step(images, labels)       # static tensors: read (or copy) them before the next call
+            scheduler.step()                           # the new lr reaches the device before the next replay
+
+    ``optimizer`` must be ``FusedAdam(capturable=True)``; batch shape and dtype are fixed by the example batch.  Construction
+    runs warm-up steps and the capture on the example batch and then restores parameters, moments and step count: it has no
+    training side effect.  Single-process path (data-parallel modes use the eager step)."""
+
+    def __init__(self, model, criterion, optimizer, images, labels, max_grad_norm=1.0, warmup: int = 3):
+        if not isinstance(optimizer, FusedAdam) or not optimizer.capturable:
+            raise TypeError("GraphedTrainStep needs FusedAdam(capturable=True)")
+        owner = optimizer._owner
+        if getattr(owner, "_nvls", None) is not None or owner._bucket_hook is not None:
+            raise RuntimeError("GraphedTrainStep is the single-process path; data-parallel modes use the eager step")
+        self.model, self.criterion, self.opt, self.max_grad_norm = model, criterion, optimizer, max_grad_norm
+        self.static_x = images.detach().clone()
+        self.static_y = labels.detach().clone()
+        owner._ensure_flat()
+        optimizer._ensure_state(owner._flat)
+        optimizer._sync_lr(non_blocking=False)
+        snap = (owner._flat.clone(), optimizer._m.clone(), optimizer._v.clone(), optimizer._step)
+        side = torch.cuda.Stream(device=images.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.metrics, self.grad_norm = self._eager()
+        # undo the training effect of warm-up and capture
+        owner._flat.copy_(snap[0]); optimizer._m.copy_(snap[1]); optimizer._v.copy_(snap[2])
+        optimizer._step = snap[3]
+        optimizer._step_dev.fill_(snap[3])
+        owner.invalidate_shadow()
+        owner._ensure_shadow(owner._param_list())
+        torch.cuda.synchronize()
+
+    def _eager(self):
+        out = self.model(self.static_x)
+        loss, met = self.criterion(out, self.static_y, with_metrics=True)
+        loss.backward()
+        norm = clip_grad_norm_(self.model.parameters(), self.max_grad_norm) if self.max_grad_norm else None
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
+        return loss, met, norm
+
+    def __call__(self, images, labels):
+        self.static_x.copy_(images, non_blocking=True)
+        self.static_y.copy_(labels, non_blocking=True)
+        self.opt._sync_lr()
+        self.graph.replay()
+        self.opt._step += 1
+        return self.loss, self.metrics
