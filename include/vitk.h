@@ -107,6 +107,19 @@ int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, co
                       float* dx_colsum, int M, int N, int K, int dtype, int engine, void* stream);
 int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, float* dw, float* db,
                       int M, int N, int K, int dtype, int engine, void* stream);
+/* The same two calls with an fp32 scratch of `scratch_floats` elements (all zero on entry; handed back all zero) that
+ * permits the row-tail split of the tcgen05 engine: when the output tiles leave the last wave of the persistent grid
+ * nearly empty and the reduction is deep (bs 64: fc2 forward, fc1 dgrad, qkv dgrad -- 150 tiles on 74 CTA pairs), the
+ * rows of the full waves keep the fused-epilogue kernel and the remaining >= 256 rows run as a split-K pass over all
+ * CTA pairs into the scratch plus a thin epilogue kernel (csrc/linear.cu: run_gemm_split; plan: vitk_gemm_tail_plan).
+ * The tail rows' partial sums meet in fp32 atomics: same rounding, not bit-reproducible run to run -- vitk_model_fwd
+ * passes a scratch in training mode only.  512 * N floats always suffice; scratch == NULL is the plain call. */
+int vitk_linear_fwd_ws(const void* x, int x_layout, const void* w, const float* bias, void* y, void* aux,
+                       int M, int N, int K, int epilogue, int dtype, int engine, float* scratch, size_t scratch_floats,
+                       void* stream);
+int vitk_linear_dgrad_ws(const void* dy, int dy_layout, const void* w, void* dx, const void* gelu_grad,
+                         float* dx_colsum, int M, int N, int K, int dtype, int engine, float* scratch,
+                         size_t scratch_floats, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Patch embedding (timm PatchEmbed.proj = Conv2d(3,768,k16,s16) + _pos_embed; K1,K2) as an im2col-free GEMM: the patch
@@ -320,6 +333,9 @@ int vitk_trace_stop(void);
 int vitk_gemm_plan(int I, int J, int R, int accumulate, int b_mn_major, int* block_n, int* cta_group, int* mode,
                    int* n_clusters, int* n_tiles_m, int* n_tiles_n, int* kb_total);
 int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_mn_major, int cluster, int* items, int max_items);
+/* Row-tail split of a non-accumulating GEMM (vitk_linear_fwd_ws / _dgrad_ws): *main_rows = leading rows (a multiple of 256)
+ * that keep the whole-tile launch, 0 = single launch.  Host-only. */
+int vitk_gemm_tail_plan(int I, int J, int R, int b_mn_major, int* main_rows);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long vitk_launch_count(void);
 /* per-launch GEMM timing with CUDA events on the launching stream (bench.py's live roofline):

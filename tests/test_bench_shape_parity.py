@@ -155,6 +155,49 @@ def test_bench_gemm_shapes_m12608(name, N, Kd):
     assert K.rel_err(dw, wref) < 5e-3      # fp32 accumulation of exact bf16 products: only the summation order differs
 
 
+@pytest.mark.parametrize("which", ["fc2_fwd", "fc1_dgrad", "qkv_dgrad"])
+def test_row_tail_split_m12608(which):
+    """The three deep J = 768 GEMMs of a bs-64 step with the row-tail split (vitk_linear_*_ws: rows 0..12287 = two full waves of
+    the whole-tile kernel, rows 12288..12607 = split-K pass + thin epilogue) against the fp32 product AND against the single
+    launch; the scratch comes back all zero, twice in a row (it is reused by the next GEMM of the step)."""
+    import ctypes as C
+    E = L.ENGINE_TCGEN05
+    rows = C.c_int(-1)
+    scratch = torch.zeros(512 * 768, dtype=torch.float32, device=DEV)
+    if which == "fc2_fwd":
+        x = _randn(M, 3072, seed=51).to(torch.bfloat16)
+        w = _randn(768, 3072, seed=52, scale=0.03).to(torch.bfloat16)
+        b = _randn(768, seed=53, scale=0.5)
+        res = _randn(M, 768, seed=54)
+        assert L.load().vitk_gemm_tail_plan(M, 768, 3072, 0, C.byref(rows)) == 0
+        ref = x.float() @ w.float().t() + b + res
+        run = lambda s: K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, E, residual=res, scratch=s)   # noqa: E731
+    elif which == "fc1_dgrad":
+        dy = _randn(M, 3072, seed=55).to(torch.bfloat16)
+        w = _randn(3072, 768, seed=56, scale=0.03).to(torch.bfloat16)
+        assert L.load().vitk_gemm_tail_plan(M, 768, 3072, 1, C.byref(rows)) == 0
+        ref = dy.float() @ w.float()
+        run = lambda s: K.linear_dgrad(dy, w, E, scratch=s)   # noqa: E731
+    else:
+        dy = _randn(M, 2304, seed=57).to(torch.bfloat16)
+        w = _randn(2304, 768, seed=58, scale=0.03).to(torch.bfloat16)
+        dyh = K.to_headmajor(dy)
+        assert L.load().vitk_gemm_tail_plan(M, 768, 2304, 1, C.byref(rows)) == 0
+        ref = dy.float() @ w.float()
+        run = lambda s: K.linear_dgrad(dyh, w, E, dy_layout=L.LAYOUT_HEADMAJOR, scratch=s)   # noqa: E731
+    assert rows.value == 12288
+    single = run(None).float()
+    for _ in range(2):
+        split = run(scratch).float()
+        torch.cuda.synchronize()
+        assert int(torch.count_nonzero(scratch)) == 0
+        assert K.rel_err(split, ref) < 2e-2
+        assert K.rel_err(split[rows.value:], ref[rows.value:]) < 2e-2
+        # same arithmetic up to the fp32 summation order of the tail's k-slices (and one bf16 rounding step where that flips)
+        assert float((split - single).abs().max()) <= 2e-2 * float(ref.abs().max())
+        assert float((split[rows.value:] - single[rows.value:]).abs().mean()) <= 2e-3 * float(ref.abs().mean())
+
+
 def test_attention_bs64_vs_sdpa():
     """the full-size attention grids (768 (batch, head) items on 148 persistent CTAs: 5.2 items per CTA)."""
     qkv = _randn(M, 2304, seed=41, scale=1.0).to(torch.bfloat16)

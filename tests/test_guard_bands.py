@@ -1,0 +1,187 @@
+"""Memory-safety and race evidence without compute-sanitizer (it is closed on this GPU pool: every run under it is refused
+-- profiles/r2_sanitizer_unavailable.md).  Two substitutes that run on the plain GPU:
+
+  * guard bands: every OUTPUT buffer of every C-ABI kernel family is carved from one sentinel-filled arena
+    (kernels_api.GuardArena, 64 KB of 0xA5 on both sides of each buffer) at ragged sizes -- M = 3 x 197 = 591 rows (not a
+    multiple of any tile), batch 3 / 5 attention and patch grids, an odd Adam length -- and after the kernels ran every byte
+    that is not payload must still be the sentinel: no kernel wrote outside what it was given (memcheck's write side);
+  * repeatability: the kernels that use no floating-point atomics (LayerNorm fwd, every non-accumulating tcgen05 GEMM
+    epilogue, attention fwd and bwd, classifier head fwd, focal loss, Adam) are run repeatedly on the same inputs and must
+    return bit-identical outputs -- a missing barrier / mbarrier phase bug / TMEM or smem buffer reuse race shows up as
+    run-to-run differences long before it shows up as a tolerance failure (racecheck's / synccheck's observable effect).
+
+Reference call sites of the kernels: see tests/test_gpu_kernels.py."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from vit_spoof_detection_pda_b200 import _lib as L
+    import kernels_api as K
+    DEV = torch.device("cuda:0")
+else:
+    L = K = DEV = None
+
+M = 3 * 197
+
+
+def _rn(*shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device=DEV) * scale).to(dtype)
+
+
+@pytest.fixture
+def arena():
+    K.GUARD = K.GuardArena(DEV)
+    try:
+        yield K.GUARD
+    finally:
+        K.GUARD = None
+
+
+def test_guard_bands_layernorm_linear_attention(arena):
+    bf = torch.bfloat16
+    E = L.ENGINE_TCGEN05
+    x = _rn(M, 768, seed=1)
+    gamma, beta = 1 + 0.1 * _rn(768, seed=2), 0.1 * _rn(768, seed=3)
+    for out_dtype in (torch.float32, bf):
+        y, mean, rstd = K.layernorm_fwd(x, gamma, beta, 1e-6, out_dtype)
+        K.layernorm_bwd(_rn(M, 768, seed=4).to(out_dtype), x, gamma, mean, rstd, want16=True)
+    # every Linear of a block, forward with its fused epilogue + dgrad + wgrad, tcgen05 and SIMT engines
+    for name, N, Kd in (("qkv", 2304, 768), ("proj", 768, 768), ("fc1", 3072, 768), ("fc2", 768, 3072)):
+        for eng, dt in ((E, bf), (L.ENGINE_SIMT, torch.float32)):
+            xx, w = _rn(M, Kd, seed=5, dtype=dt), _rn(N, Kd, seed=6, scale=0.03, dtype=dt)
+            b, dy = _rn(N, seed=7), _rn(M, N, seed=8, dtype=dt)
+            if name == "qkv":
+                K.linear_fwd(xx, w, b, L.EPI_QKV_SCATTER, eng)
+                K.linear_dgrad(K.to_headmajor(dy), w, eng, dy_layout=L.LAYOUT_HEADMAJOR)
+                K.linear_wgrad(K.to_headmajor(dy), xx, N, Kd, eng, dy_layout=L.LAYOUT_HEADMAJOR)
+            else:
+                if name == "fc1":
+                    K.linear_fwd(xx, w, b, L.EPI_BIAS_GELU, eng)
+                else:
+                    K.linear_fwd(xx, w, b, L.EPI_BIAS_RESIDUAL, eng, residual=_rn(M, N, seed=9))
+                if name == "fc2":
+                    K.linear_dgrad(dy, w, eng, gelu_grad=_rn(M, Kd, seed=10, dtype=dt), want_colsum=True)
+                else:
+                    K.linear_dgrad(dy, w, eng, want_colsum=(name == "proj"))
+                K.linear_wgrad(dy, xx, N, Kd, eng)
+            K.linear_fwd(xx, w, b, L.EPI_BIAS, eng)
+    # the row-tail split at the smallest size that takes it on 74 CTA pairs, with the scratch inside the arena as well
+    rows = C.c_int(0)
+    for batch in range(20, 70):
+        L.load().vitk_gemm_tail_plan(batch * 197, 768, 3072, 0, C.byref(rows))
+        if rows.value:
+            Mt = batch * 197
+            scratch = K._zeros(512 * 768, dtype=torch.float32, device=DEV)
+            K.linear_fwd(_rn(Mt, 3072, seed=11, dtype=bf), _rn(768, 3072, seed=12, scale=0.03, dtype=bf), _rn(768, seed=13),
+                         L.EPI_BIAS_RESIDUAL, E, residual=_rn(Mt, 768, seed=14), scratch=scratch)
+            K.linear_dgrad(_rn(Mt, 3072, seed=15, dtype=bf), _rn(3072, 768, seed=16, scale=0.03, dtype=bf), E, scratch=scratch)
+            break
+    assert rows.value, "no batch size in 20..69 takes the row-tail split"
+    # attention forward / backward, both precisions, a batch that is not a multiple of anything
+    for dt in (bf, torch.float32):
+        for batch in (3, 5):
+            qkv = K.to_headmajor(_rn(batch * 197, 2304, seed=17, dtype=dt))
+            out, lse = K.attn_fwd(qkv, batch)
+            K.attn_bwd(qkv, out, _rn(batch * 197, 768, seed=18, dtype=dt), lse, batch)
+    assert arena.check() > 0
+
+
+def test_guard_bands_patch_head_loss_adam_eval(arena):
+    lib = L.load()
+    f32 = torch.float32
+    for batch in (3, 5):
+        img = _rn(batch, 3, 224, 224, seed=21)
+        w, b = _rn(768, 3, 16, 16, seed=22, scale=0.03), _rn(768, seed=23)
+        cls, pos = _rn(768, seed=24), _rn(197, 768, seed=25)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        u8 = torch.randint(0, 256, (batch, 224, 224, 3), generator=g, device=DEV, dtype=torch.uint8)
+        m3, s3 = (C.c_float * 3)(0.485, 0.456, 0.406), (C.c_float * 3)(0.229, 0.224, 0.225)
+        for precision in (L.PREC_BF16, L.PREC_FP32):
+            x0 = arena.alloc((batch * 197, 768), f32, False)
+            L.call("vitk_patch_embed_fwd", L.ptr(img), L.ptr(w), L.ptr(w.to(torch.bfloat16)), L.ptr(b), L.ptr(cls), L.ptr(pos),
+                   L.ptr(x0), batch, precision, L.ENGINE_AUTO, L.stream_ptr())
+            x1, nchw = arena.alloc((batch * 197, 768), f32, False), arena.alloc((batch, 3, 224, 224), f32, False)
+            L.call("vitk_patch_embed_fwd_u8", L.ptr(u8), m3, s3, L.ptr(w), L.ptr(w.to(torch.bfloat16)), L.ptr(b), L.ptr(cls),
+                   L.ptr(pos), L.ptr(x1), L.ptr(nchw), batch, precision, L.ENGINE_AUTO, L.stream_ptr())
+            dx0 = _rn(batch * 197, 768, seed=26)
+            outs = [arena.alloc(t.shape, f32, True) for t in (w, b, cls, pos)]
+            L.call("vitk_patch_embed_wgrad", L.ptr(dx0), L.ptr(dx0.to(torch.bfloat16)), L.ptr(img), *[L.ptr(t) for t in outs],
+                   batch, precision, L.ENGINE_AUTO, L.stream_ptr())
+    # classifier head + focal loss
+    for B in (1, 5, 64):
+        Cn = 2
+        feat = _rn(B, 768, seed=31)
+        ln_w, ln_b = 1 + 0.1 * _rn(768, seed=32), 0.1 * _rn(768, seed=33)
+        w1, b1 = _rn(512, 768, seed=34, scale=0.05), _rn(512, seed=35, scale=0.1)
+        w2, b2 = _rn(Cn, 512, seed=36, scale=0.05), _rn(Cn, seed=37, scale=0.1)
+        logits = arena.alloc((B, Cn), f32, False)
+        save = arena.alloc((lib.vitk_head_save_floats(B),), f32, False)
+        L.call("vitk_head_fwd", *[L.ptr(t) for t in (feat, ln_w, ln_b, w1, b1, w2, b2, None, None, logits, save)], B, Cn,
+               L.stream_ptr())
+        labels = torch.randint(0, Cn, (B,), device=DEV)
+        alpha = torch.full((Cn,), 0.25, device=DEV)
+        per, loss, dl, p1 = (arena.alloc(s, f32, False) for s in ((B,), (1,), (B, Cn), (B,)))
+        preds, ncorrect = arena.alloc((B,), torch.int64, False), arena.alloc((1,), torch.int32, False)
+        L.call("vitk_focal_fwd_bwd", L.ptr(logits), L.ptr(labels), L.ptr(alpha), 2.0, 0, 1.0, L.ptr(per), L.ptr(loss), L.ptr(dl),
+               L.ptr(p1), L.ptr(preds), L.ptr(ncorrect), B, Cn, L.stream_ptr())
+        outs = [arena.alloc(t.shape, f32, True) for t in (feat, ln_w, ln_b, w1, b1, w2, b2)]
+        L.call("vitk_head_bwd", L.ptr(dl), L.ptr(save), L.ptr(ln_w), L.ptr(w1), L.ptr(w2), None, None,
+               *[L.ptr(t) for t in outs], B, Cn, L.stream_ptr())
+    # gradient norm + Adam over an odd length (vector tails)
+    n = 1_000_003
+    p, m, v = (arena.alloc((n,), f32, True) for _ in range(3))
+    p.copy_(_rn(n, seed=41, scale=0.05))
+    p16 = arena.alloc((n,), torch.bfloat16, False)
+    part = arena.alloc((lib.vitk_grad_sumsq_scratch_floats(),), f32, False)
+    sumsq = arena.alloc((1,), f32, True)
+    g = _rn(n, seed=42, scale=0.01)
+    L.call("vitk_grad_sumsq", L.ptr(g), n, L.ptr(part), L.ptr(sumsq), L.stream_ptr())
+    L.call("vitk_adam_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(p16), n, 1e-5, 0.9, 0.999, 1e-8, 1e-4, 0, 1, 1.0,
+           L.ptr(sumsq), 1.0, L.stream_ptr())
+    assert torch.equal(p16, p.to(torch.bfloat16))
+    assert arena.check() > 0
+
+
+def test_repeatability_of_atomic_free_kernels():
+    """bit-identical outputs over repeated launches on the same inputs (see module docstring)."""
+    bf = torch.bfloat16
+    E = L.ENGINE_TCGEN05
+    runs = 6
+    Mr = 26 * 197      # 5122 rows: 21 tile rows over 74 CTA pairs, 312 attention items over 148 persistent CTAs
+
+    def same(fn):
+        first = fn()
+        first = first if isinstance(first, tuple) else (first,)
+        first = [t.clone() for t in first]
+        for _ in range(runs - 1):
+            again = fn()
+            again = again if isinstance(again, tuple) else (again,)
+            for a, b in zip(first, again):
+                assert torch.equal(a, b)
+
+    x = _rn(Mr, 768, seed=51)
+    gamma, beta = 1 + 0.1 * _rn(768, seed=52), 0.1 * _rn(768, seed=53)
+    same(lambda: K.layernorm_fwd(x, gamma, beta, 1e-6, bf))
+    xb = x.to(bf)
+    for N, Kd, epi in ((2304, 768, L.EPI_QKV_SCATTER), (3072, 768, L.EPI_BIAS_GELU), (768, 768, L.EPI_BIAS)):
+        w, b = _rn(N, Kd, seed=54, scale=0.03, dtype=bf), _rn(N, seed=55)
+        same(lambda: K.linear_fwd(xb, w, b, epi, E))
+    g = _rn(Mr, 3072, seed=56, dtype=bf)
+    w2, b2, res = _rn(768, 3072, seed=57, scale=0.03, dtype=bf), _rn(768, seed=58), _rn(Mr, 768, seed=59)
+    same(lambda: K.linear_fwd(g, w2, b2, L.EPI_BIAS_RESIDUAL, E, residual=res))
+    dy = _rn(Mr, 768, seed=60, dtype=bf)
+    u = _rn(Mr, 3072, seed=61, dtype=bf)
+    same(lambda: K.linear_dgrad(dy, w2, E, gelu_grad=u))                       # MN-major B operand, GELU' epilogue
+    dq = K.to_headmajor(_rn(Mr, 2304, seed=62, dtype=bf))
+    wq = _rn(2304, 768, seed=63, scale=0.03, dtype=bf)
+    same(lambda: K.linear_dgrad(dq, wq, E, dy_layout=L.LAYOUT_HEADMAJOR))      # head-major A operand
+    qkv = K.to_headmajor(_rn(Mr, 2304, seed=64, dtype=bf))
+    same(lambda: K.attn_fwd(qkv, 26))
+    out, lse = K.attn_fwd(qkv, 26)
+    dout = _rn(Mr, 768, seed=65, dtype=bf)
+    same(lambda: K.attn_bwd(qkv, out, dout, lse, 26)[0])                       # dqkv (the column sums use atomics)

@@ -209,6 +209,48 @@ def test_gemm_plan_bench_shapes_pick_documented_decompositions():
         lib.vitk_set_sm_budget(prev)
 
 
+def _tail_plan(lib, I, J, R, b_mn):
+    import ctypes as C
+    rows = C.c_int(-1)
+    assert lib.vitk_gemm_tail_plan(I, J, R, b_mn, C.byref(rows)) == 0
+    return rows.value
+
+
+def test_gemm_row_tail_split_plan():
+    """at bs 64 the deep J = 768 GEMMs (fc2 forward, fc1 dgrad, qkv dgrad: 150 tiles of 256 x 256 on 74 CTA
+    pairs = two waves + a wave of two tiles) keep 48 tile rows = 144 tiles = two full waves in the whole-tile launch and hand
+    the last 320 rows to the split-K tail; shallow reductions, full last waves and reduced SM budgets are left alone.  Whatever
+    the shape: the leading rows are whole 256-row tiles, fit the full waves, and the tail is 256..512 rows."""
+    from vit_spoof_detection_pda_b200 import _lib as L
+    lib = L.load()
+    prev = lib.vitk_set_sm_budget(0)
+    try:
+        assert _tail_plan(lib, M64, 768, 3072, 0) == 12288      # fc2 forward
+        assert _tail_plan(lib, M64, 768, 3072, 1) == 12288      # fc1 dgrad
+        assert _tail_plan(lib, M64, 768, 2304, 1) == 12288      # qkv dgrad
+        assert _tail_plan(lib, M64, 768, 768, 0) == 0           # proj: 12 k-blocks, a split-K pass costs more than the wave
+        assert _tail_plan(lib, M64, 3072, 768, 0) == 0          # fc1 forward: shallow
+        assert _tail_plan(lib, 256 * 197, 768, 3072, 0) == 0    # bs 256: 591 tiles = 7.99 waves
+        assert _tail_plan(lib, 197, 768, 3072, 0) == 0          # bs 1
+        for batch in range(1, 130):
+            for J, R, bmn in ((768, 3072, 0), (768, 3072, 1), (768, 2304, 1), (3072, 3072, 0), (1536, 4096, 1)):
+                I = batch * 197
+                rows = _tail_plan(lib, I, J, R, bmn)
+                if rows == 0:
+                    continue
+                assert rows % 256 == 0 and 256 <= I - rows <= 512, (I, J, R, rows)
+                plan, _ = _plan(lib, rows, J, R, 0, bmn)
+                full, _ = _plan(lib, I, J, R, 0, bmn)
+                assert plan["cg"] == 2
+                waves = -(-(plan["tm"] * plan["tn"]) // 74)
+                waves_full = -(-(full["tm"] * full["tn"]) // (148 // full["cg"]))
+                assert waves * plan["bn"] < waves_full * full["bn"], (I, J, R, rows, plan, full)
+        lib.vitk_set_sm_budget(116)
+        assert _tail_plan(lib, M64, 768, 3072, 0) == 0          # 58 CTA pairs: 150 tiles = 2.6 waves, last wave well filled
+    finally:
+        lib.vitk_set_sm_budget(prev)
+
+
 
 # ---------------------------------------------------------------------------------------------
 # checkpoint container of the reference (train_advanced.py:475-489 / test.py:167-188): written and read unchanged, on CPU

@@ -1,4 +1,6 @@
-"""Runs 3 training steps of the bench workload (bs 64, bf16) -- the command ncu wraps for the launch list."""
+"""Runs 3 training steps of the bench workload (bs 64, bf16, eager launches) -- the command ncu wraps for the launch list.
+The third step is bracketed by cudaProfilerStart/Stop: `ncu --profile-from-start off ...` captures exactly one whole step
+(no -s / -c arithmetic); without that flag every launch is captured as before."""
 import os
 import sys
 
@@ -16,10 +18,14 @@ opt = pkg.FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4, adamw=False)
 x = torch.randn(B, 3, 224, 224, device=dev)
 y = torch.randint(0, 2, (B,), device=dev)
 for step in range(3):
+    if step == 2:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     loss, _ = crit(model(x), y, with_metrics=True)
     loss.backward()
     pkg.clip_grad_norm_(model.parameters(), 1.0)
     opt.step()
     opt.zero_grad(set_to_none=True)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("loss", loss.item())

@@ -22,7 +22,7 @@ from vit_spoof_detection_pda_b200 import _lib as L  # noqa: E402
 
 KID = {1: "gemm_tc", 2: "attn_fwd", 3: "attn_bwd", 4: "ln_fwd", 5: "ln_bwd", 6: "adam", 7: "sumsq/scale", 8: "cast", 9: "head",
        10: "focal", 11: "colsum", 12: "patch_embed", 13: "embed_grads", 14: "scatter_cls", 15: "gemm_simt", 16: "attn_simt",
-       17: "eval", 18: "patch_wgrad"}
+       17: "eval", 18: "patch_wgrad", 19: "gemm_tail_epilogue"}
 
 
 DETAIL_PHASES, DETAIL_SLOTS = 24, 64

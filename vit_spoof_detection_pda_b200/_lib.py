@@ -47,6 +47,8 @@ PROTOTYPES = {
     "vitk_linear_fwd": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "vitk_linear_dgrad": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "vitk_linear_wgrad": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "vitk_linear_fwd_ws": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
+    "vitk_linear_dgrad_ws": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]),
     "vitk_patch_embed_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "vitk_patch_embed_fwd_u8": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "vitk_u8_to_nchw": (i32, [vp, vp, vp, vp, i32, vp]),
@@ -79,10 +81,37 @@ PROTOTYPES = {
     "vitk_set_sm_budget": (i32, [i32]),
     "vitk_gemm_plan": (i32, [i32, i32, i32, i32, i32] + [C.POINTER(i32)] * 7),
     "vitk_gemm_plan_items": (i32, [i32, i32, i32, i32, i32, i32, C.POINTER(i32), i32]),
+    "vitk_gemm_tail_plan": (i32, [i32, i32, i32, i32, C.POINTER(i32)]),
     "vitk_launch_count": (C.c_longlong, []),
     "vitk_prof_enable": (i32, [i32]),
     "vitk_prof_read": (i32, [C.POINTER(C.c_float), C.POINTER(i32), i32]),
 }
+
+# VITK_NVTX=1: NVTX ranges around the forward call, every backward stage, the gradient-norm / clip pass and the optimizer step
+# (the ranges an nsys / ncu --nvtx capture filters on).  Off by default: the range calls are host work in a loop
+# whose host side otherwise costs ~50 us per step when graphed.
+NVTX = os.environ.get("VITK_NVTX") == "1"
+
+
+class nvtx_range:
+    """`with nvtx_range("vitk/forward"):` -- torch.cuda.nvtx push/pop when VITK_NVTX=1, nothing otherwise."""
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
+
 
 _lib = None
 launch_count = 0  # number of C-ABI compute calls made by this process (bench.py reports kernels separately)

@@ -76,7 +76,8 @@ bool pdl_enabled();
 enum TraceKernel {
   TK_GEMM_TC = 1, TK_ATTN_FWD = 2, TK_ATTN_BWD = 3, TK_LN_FWD = 4, TK_LN_BWD = 5, TK_ADAM = 6, TK_SUMSQ = 7, TK_CAST = 8,
   TK_HEAD = 9, TK_FOCAL = 10, TK_COLSUM = 11, TK_PATCH_EMBED = 12, TK_EMBED_GRADS = 13, TK_SCATTER_CLS = 14,
-  TK_GEMM_SIMT = 15, TK_ATTN_SIMT = 16, TK_EVAL = 17, TK_PATCH_WGRAD = 18
+  TK_GEMM_SIMT = 15, TK_ATTN_SIMT = 16, TK_EVAL = 17, TK_PATCH_WGRAD = 18,
+  TK_GEMM_TAIL = 19
 };
 #ifdef VITK_DEV
 void trace_register(void (*setter)(unsigned long long*));   // api.cu: one setter per translation unit

@@ -927,7 +927,7 @@ static int make_operand_map(const void* base, const MatLayout& l, int rows, int 
 
 // Tuning overrides (vitk_debug_set): process-wide, for tests and A/B timing; every one of them yields valid results.
 //   1 whole-K tiles for accumulate GEMMs, 2 forced BLOCK_N, 4 CTA group, 5 per-thread epilogue IO, 6 no programmatic
-//   dependent launch, 13 stream-K instead of sliced split-K (> 1: fill threshold in percent).
+//   dependent launch, 9 no row-tail split, 13 stream-K instead of sliced split-K (> 1: fill threshold in percent).
 // Development build only (libvitk_dev.so): 0 swap LBO/SBO of MN-major operands, 7 timing-only bit mask (results INVALID),
 //   12 whole qkv bias gradient from the attention kernel.
 static int g_tc_debug[16] = {0};
@@ -935,7 +935,7 @@ static bool knob_allowed(int key) {
 #ifdef VITK_DEV
   return key >= 0 && key < 16;
 #else
-  return key == 1 || key == 2 || key == 4 || key == 5 || key == 6 || key == 13;
+  return key == 1 || key == 2 || key == 4 || key == 5 || key == 6 || key == 9 || key == 13;
 #endif
 }
 int tune_knob(int key) { return knob_allowed(key) ? g_tc_debug[key] : 0; }
@@ -1055,6 +1055,45 @@ static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* b
   }
   *bn_out = bn;
   *cg_out = cg;
+}
+
+// ---- row-tail split (pure host logic).  M = B*197 rows rarely fill the last wave of the persistent grid: 12608 x 768 on 74
+// CTA pairs is 150 tiles of 256 x 256 = two full waves and a third one with TWO tiles in it -- a third of the kernel's time
+// for 1.3 % of its work.  When the reduction is deep enough for a split-K pass to be cheaper than that wave (>= 32 k-blocks:
+// fc2 forward, fc1 dgrad, qkv dgrad), the caller (linear.cu: run_gemm_split) runs the leading rows -- as many 256-row tile
+// rows as fit into the FULL waves -- through the whole-tile kernel with its fused epilogue, and the remaining rows (>= 256,
+// so the CTA-pair kernel applies) as a sliced split-K accumulate GEMM over all CTA pairs into an fp32 scratch, followed by a
+// thin epilogue pass.  Returns the number of leading rows, 0 = keep the single launch.
+int tc_tail_split_rows(int I, int J, int R, bool b_mn) {
+  if (g_tc_debug[9] == 1) return 0;
+  const long kb = (R + TC_BK - 1) / TC_BK;
+  if (kb < 32 || J % 256 != 0) return 0;
+  int bn = 0, cg = 0;
+  tc_pick_tile(I, J, R, false, b_mn, &bn, &cg);
+  if (cg != 2 || bn == 0) return 0;
+  const long slots = sm_count() / 2;
+  const long rows_per_tile = TC_BM * 2;
+  auto waves_for = [&](long rows, int n) { const long t = ((rows + rows_per_tile - 1) / rows_per_tile) * (J / n); return (t + slots - 1) / slots; };
+  // candidates: the tile width the single launch would use and the widest one (fewer operand bytes per FLOP)
+  for (int n : {256, bn}) {
+    if (J % n != 0 || (b_mn && (n / 2) % 64 != 0)) continue;
+    const long tiles_n = J / n;
+    const long tiles = ((I + rows_per_tile - 1) / rows_per_tile) * tiles_n;
+    const long full = tiles / slots, rem = tiles % slots;
+    if (full < 1 || rem == 0 || rem * 4 > slots) continue;        // last wave at least a quarter full: leave it alone
+    long main_tm = (full * slots) / tiles_n;
+    if ((long)I - main_tm * rows_per_tile < rows_per_tile) --main_tm;   // keep >= 256 tail rows: the CTA-pair accumulate kernel
+    if (main_tm < 1) continue;
+    const long main_rows = main_tm * rows_per_tile;
+    if ((long)I - main_rows > 2 * rows_per_tile) continue;        // the tail must stay thin
+    // the leading rows must really take `full` waves with the tile shape the heuristic picks for them
+    int bn2 = 0, cg2 = 0;
+    tc_pick_tile((int)main_rows, J, R, false, b_mn, &bn2, &cg2);
+    if (cg2 != 2 || waves_for(main_rows, bn2) > full) continue;
+    if (waves_for(main_rows, bn2) * bn2 >= waves_for(I, bn) * bn) continue;   // no fewer tensor clocks than the single launch
+    return (int)main_rows;
+  }
+  return 0;
 }
 
 template <int BN, int CG, int EK>
@@ -1215,6 +1254,12 @@ extern "C" int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_m
     ++n;
   }
   return n;
+}
+// Host-only view of the row-tail split (no launch): *main_rows = leading rows of the whole-tile launch (0: single launch).
+extern "C" int vitk_gemm_tail_plan(int I, int J, int R, int b_mn_major, int* main_rows) {
+  VITK_CHECK_ARG(I > 0 && J > 0 && R > 0 && J % 128 == 0 && main_rows);
+  *main_rows = vitk::tc_tail_split_rows(I, J, R, b_mn_major != 0);
+  return VITK_OK;
 }
 extern "C" int vitk_debug_set(int key, int value) {
   if (!vitk::knob_allowed(key)) {

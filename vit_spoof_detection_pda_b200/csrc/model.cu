@@ -93,7 +93,10 @@ struct Plan {
   size_t meanf, rstdf, feat, head_save;
   // backward transients
   size_t dx, dx16, du, dh, dqkv, dfeat, dxc;
+  // fp32 scratch of the GEMMs' row-tail split (training, bf16; linear.cu run_gemm_split): TAIL_FLOATS floats, kept all zero
+  size_t tail;
 };
+constexpr size_t TAIL_FLOATS = (size_t)512 * D;
 
 static void make_plan(int B, int depth, int precision, int training, int frozen, Plan* p) {
   const size_t T = precision == VITK_PREC_BF16 ? 2 : 4;
@@ -134,6 +137,7 @@ static void make_plan(int B, int depth, int precision, int training, int frozen,
   } else {
     p->dx = p->dx16 = p->du = p->dh = p->dqkv = 0;
   }
+  p->tail = (training && precision == VITK_PREC_BF16) ? take(TAIL_FLOATS * 4) : 0;
   p->total = cur;
 }
 
@@ -176,6 +180,8 @@ struct Ctx {
   bool save;
   char* ws;
   cudaStream_t st;
+  float* tail;          // row-tail split scratch (nullptr: eval / fp32-validate -- every GEMM is a single launch)
+  size_t tail_floats;
   const void* W(int64_t off) const {
     return dt == VITK_BF16 ? (const void*)((const bf16*)m->params16 + off) : (const void*)(m->params + off);
   }
@@ -198,6 +204,9 @@ static int make_ctx(const vitk_model* m, void* stream, Ctx* c) {
   c->save = m->training && !m->frozen_backbone;
   c->ws = (char*)m->workspace;
   c->st = (cudaStream_t)stream;
+  const bool split = m->training && m->precision == VITK_PREC_BF16;
+  c->tail = split ? (float*)(c->ws + c->pl.tail) : nullptr;
+  c->tail_floats = split ? TAIL_FLOATS : 0;
   return VITK_OK;
 }
 
@@ -236,6 +245,9 @@ extern "C" int vitk_model_fwd(const vitk_model* m, void* stream) {
   auto xin = [&](int l) { return (float*)(ws + pl.x_in + pl.x_stride * (size_t)(c.save ? l : (l & 1))); };
   auto w16 = [&](int64_t off) -> const void* { return dt == VITK_BF16 ? (const void*)((const bf16*)m->params16 + off) : nullptr; };
 
+  // the split GEMMs hand the scratch back zeroed; clearing it once per call makes that independent of what the caller's
+  // workspace held before (first use, a different plan in the same allocation)
+  if (c.tail) VITK_CUDA(cudaMemsetAsync(c.tail, 0, c.tail_floats * 4, c.st));
   if (m->images_u8)   // uint8 HWC pixels: ToTensor + Normalize fused into the patch loader
     VITK_TRY(vitk_patch_embed_fwd_u8(m->images_u8, m->norm_mean, m->norm_std, c.P(po.pew), w16(po.pew), c.P(po.peb), c.P(po.cls),
                                      c.P(po.pos), xin(0), (float*)(ws + pl.nchw), m->batch, m->precision, eng, st));
@@ -268,8 +280,8 @@ extern "C" int vitk_model_fwd(const vitk_model* m, void* stream) {
     VITK_TRY(vitk_layernorm_fwd(xmid, D, c.P(b.n2w), c.P(b.n2b), ln2, dt, mean2, rstd2, M, 1e-6f, st));
     VITK_TRY(vitk_linear_fwd(ln2, VITK_LAYOUT_ROWMAJOR, c.W(b.fc1w), c.P(b.fc1b), g, u, M, MLP, D,
                              VITK_EPI_BIAS_GELU, dt, eng, st));
-    VITK_TRY(vitk_linear_fwd(g, VITK_LAYOUT_ROWMAJOR, c.W(b.fc2w), c.P(b.fc2b), xout, xmid, M, D, MLP,
-                             VITK_EPI_BIAS_RESIDUAL, dt, eng, st));
+    VITK_TRY(vitk_linear_fwd_ws(g, VITK_LAYOUT_ROWMAJOR, c.W(b.fc2w), c.P(b.fc2b), xout, xmid, M, D, MLP,
+                                VITK_EPI_BIAS_RESIDUAL, dt, eng, c.tail, c.tail_floats, st));
   }
   // final norm on the CLS rows only (global_pool='token': only x[:,0] is consumed), then the head
   float* xl = xin(m->depth);
@@ -299,6 +311,7 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   void* dx16 = dt == VITK_BF16 ? (void*)(ws + pl.dx16) : nullptr;
 
   if (stage == 0) {
+    if (c.tail) VITK_CUDA(cudaMemsetAsync(c.tail, 0, c.tail_floats * 4, c.st));
     float* dfeat = (float*)(ws + pl.dfeat);
     VITK_TRY(vitk_head_bwd(m->dlogits, (float*)(ws + pl.head_save), c.P(po.hlnw), c.P(po.hw1), c.P(po.hw2), m->mask1,
                            m->mask2, dfeat, c.G(po.hlnw), c.G(po.hlnb), c.G(po.hw1), c.G(po.hb1), c.G(po.hw2),
@@ -357,7 +370,8 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   VITK_TRY(vitk_linear_dgrad(dxa, VITK_LAYOUT_ROWMAJOR, c.W(b.fc2w), du, u, c.G(b.fc1b), M, D, MLP, dt, eng, st));
   VITK_TRY(after(2, ms, ss ? ss->s : ms));   // du ready
   VITK_TRY(vitk_linear_wgrad(du, VITK_LAYOUT_ROWMAJOR, ln2, c.G(b.fc1w), nullptr, M, MLP, D, dt, eng, wst));
-  VITK_TRY(vitk_linear_dgrad(du, VITK_LAYOUT_ROWMAJOR, c.W(b.fc1w), dh, nullptr, nullptr, M, MLP, D, dt, eng, st));
+  VITK_TRY(vitk_linear_dgrad_ws(du, VITK_LAYOUT_ROWMAJOR, c.W(b.fc1w), dh, nullptr, nullptr, M, MLP, D, dt, eng, c.tail,
+                                c.tail_floats, st));
   if (ss) VITK_CUDA(cudaStreamWaitEvent(ms, ss->ev[1], 0));              // the LayerNorm backward overwrites dx16
   VITK_TRY(vitk_layernorm_bwd(dh, dt, xmid, D, c.P(b.n2w), (float*)c.at(pl.mean2, pl.stat_stride, l),
                               (float*)c.at(pl.rstd2, pl.stat_stride, l), dx, dx, dx16, c.G(b.n2w), c.G(b.n2b), c.G(b.projb), M, st));
@@ -380,7 +394,8 @@ extern "C" int vitk_model_bwd_stage(const vitk_model* m, int stage, void* stream
   VITK_TRY(after(5, ms, ss ? ss->s : ms));   // dqkv ready
   if (split_bias) VITK_TRY(colsum_headmajor(dqkv, dt, M, D, c.G(b.qkvb), (cudaStream_t)wst));   // q section: heads 0..11 of dqkv
   VITK_TRY(vitk_linear_wgrad(dqkv, VITK_LAYOUT_HEADMAJOR, ln1, c.G(b.qkvw), nullptr, M, 3 * D, D, dt, eng, wst));
-  VITK_TRY(vitk_linear_dgrad(dqkv, VITK_LAYOUT_HEADMAJOR, c.W(b.qkvw), dh, nullptr, nullptr, M, 3 * D, D, dt, eng, st));
+  VITK_TRY(vitk_linear_dgrad_ws(dqkv, VITK_LAYOUT_HEADMAJOR, c.W(b.qkvw), dh, nullptr, nullptr, M, 3 * D, D, dt, eng, c.tail,
+                                c.tail_floats, st));
   if (ss) VITK_CUDA(cudaStreamWaitEvent(ms, ss->ev[4], 0));              // the LayerNorm backward overwrites dx16
   VITK_TRY(vitk_layernorm_bwd(dh, dt, x, D, c.P(b.n1w), (float*)c.at(pl.mean1, pl.stat_stride, l),
                               (float*)c.at(pl.rstd1, pl.stat_stride, l), dx, dx, dx16, c.G(b.n1w), c.G(b.n1b),

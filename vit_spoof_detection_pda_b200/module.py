@@ -382,7 +382,8 @@ class ViTFaceAntiSpoofing(nn.Module):
         m = self._model_struct(B, training, frozen, ws, images=x, logits=logits, masks=masks)
         if training:
             self._start_prezero(plist)
-        L.call("vitk_model_fwd", C.byref(m), L.stream_ptr())
+        with L.nvtx_range(f"vitk/forward bs={B} {'train' if training else 'eval'}"):
+            L.call("vitk_model_fwd", C.byref(m), L.stream_ptr())
         self._gen += 1
         if training:
             self._saved = (x, masks, frozen, ws, self._gen)
@@ -436,7 +437,8 @@ class ViTFaceAntiSpoofing(nn.Module):
         ranges = self.stage_ranges()
         n_stages = 1 if frozen else self.depth + 2
         for s in range(n_stages):
-            L.call("vitk_model_bwd_stage", C.byref(m), s, st)
+            with L.nvtx_range(f"vitk/backward stage {s}"):
+                L.call("vitk_model_bwd_stage", C.byref(m), s, st)
             # data parallel: every backward reduces the gradient IT produced -- also the micro-step gradients of a
             # gradient-accumulation loop and the backward after zero_grad(set_to_none=False), which land in the second
             # buffer (`aliased`) before autograd adds them to .grad.  The all-reduce is linear, so reducing each micro-step

@@ -71,7 +71,8 @@ def _sumsq(owner, g):
     if getattr(owner, "_sumsq_scratch", None) is None:
         owner._sumsq_scratch = torch.empty(lib.vitk_grad_sumsq_scratch_floats(), dtype=torch.float32, device=g.device)
         owner._sumsq = torch.zeros(1, dtype=torch.float32, device=g.device)
-    L.call("vitk_grad_sumsq", L.ptr(g), g.numel(), L.ptr(owner._sumsq_scratch), L.ptr(owner._sumsq), L.stream_ptr())
+    with L.nvtx_range("vitk/grad_norm"):
+        L.call("vitk_grad_sumsq", L.ptr(g), g.numel(), L.ptr(owner._sumsq_scratch), L.ptr(owner._sumsq), L.stream_ptr())
     return owner._sumsq
 
 
@@ -215,6 +216,10 @@ class FusedAdam(torch.optim.Optimizer):
             self._lr_dev.copy_(self._lr_host, non_blocking=non_blocking)
 
     def _launch(self, flat, g, p16, lo, hi, grp, b1, b2, sumsq, max_norm):
+        with L.nvtx_range("vitk/adam_step"):
+            self._launch_range(flat, g, p16, lo, hi, grp, b1, b2, sumsq, max_norm)
+
+    def _launch_range(self, flat, g, p16, lo, hi, grp, b1, b2, sumsq, max_norm):
         n = hi - lo
         if n <= 0:
             return
