@@ -107,13 +107,15 @@ int vitk_linear_dgrad(const void* dy, int dy_layout, const void* w, void* dx, co
                       float* dx_colsum, int M, int N, int K, int dtype, int engine, void* stream);
 int vitk_linear_wgrad(const void* dy, int dy_layout, const void* x, float* dw, float* db,
                       int M, int N, int K, int dtype, int engine, void* stream);
-/* The same two calls with an fp32 scratch of `scratch_floats` elements (all zero on entry; handed back all zero) that
- * permits the row-tail split of the tcgen05 engine: when the output tiles leave the last wave of the persistent grid
- * nearly empty and the reduction is deep (bs 64: fc2 forward, fc1 dgrad, qkv dgrad -- 150 tiles on 74 CTA pairs), the
- * rows of the full waves keep the fused-epilogue kernel and the remaining >= 256 rows run as a split-K pass over all
- * CTA pairs into the scratch plus a thin epilogue kernel (csrc/linear.cu: run_gemm_split; plan: vitk_gemm_tail_plan).
- * The tail rows' partial sums meet in fp32 atomics: same rounding, not bit-reproducible run to run -- vitk_model_fwd
- * passes a scratch in training mode only.  512 * N floats always suffice; scratch == NULL is the plain call. */
+/* The same two calls with a scratch of `scratch_floats` 4-byte elements (all zero on entry; handed back all zero;
+ * vitk_gemm_tail_scratch_floats(N of the output) always suffices) that permits the SPLIT TAIL of the tcgen05 engine: when
+ * the output tiles leave the last wave of the persistent grid at most a quarter full and the reduction is >= 24 k-blocks deep
+ * (bs 64: fc2 forward, fc1 dgrad, qkv dgrad -- 150 tiles on 74 CTA pairs = two waves + a wave of two tiles), the tiles of
+ * the full waves stay whole-K items with the fused epilogue and the k-blocks of the remaining tiles are dealt out to all
+ * CTA pairs of the SAME launch; partial accumulators meet in the scratch (red.global.add.v4.f32) and the last CTA to arrive
+ * at a region's ticket applies the epilogue (csrc/gemm_tc.cu: tc_tail_plan, "partial item"; plan query: vitk_gemm_tail_plan).
+ * The tail tiles' sums are rounded like the others but their fp32 summation order is not reproducible run to run --
+ * vitk_model_fwd / _bwd_stage pass a scratch in training mode only.  scratch == NULL is the plain call. */
 int vitk_linear_fwd_ws(const void* x, int x_layout, const void* w, const float* bias, void* y, void* aux,
                        int M, int N, int K, int epilogue, int dtype, int engine, float* scratch, size_t scratch_floats,
                        void* stream);
@@ -325,17 +327,20 @@ int vitk_trace_stop(void);
 /* Host-only view of the tcgen05 GEMM's work decomposition for C[I][J] += over R (no launch; only the SM count / budget is
  * consulted): tile width BLOCK_N, CTA group (1 single CTAs with 128-row tiles, 2 CTA pairs with 256-row tiles), mode
  * (0 whole-K tiles strided over the persistent clusters, 1 contiguous stream-K ranges, 2 sliced split-K: one k-slice of
- * one tile per cluster), number of clusters launched, tile grid and number of 64-deep k-blocks.  accumulate != 0 is the
- * weight-gradient epilogue (fp32 +=); b_mn_major != 0 says the B operand is stored with its row index contiguous
+ * one tile per cluster, 3 split tail), number of clusters launched, tile grid and number of 64-deep k-blocks.  accumulate == 1
+ * is the weight-gradient epilogue (fp32 +=), 2 a non-accumulating GEMM with a tail scratch; b_mn_major != 0 says the B operand is stored with its row index contiguous
  * (dgrad's W, wgrad's X).  vitk_gemm_plan_items writes the (tile, first k-block, end k-block) triples cluster `cluster`
  * walks -- the same iterator code the kernel's warps run -- and returns their count (negative VITK_ERR_* on bad
  * arguments); tests/test_host_logic.py checks that all clusters together cover every (tile, k-block) exactly once. */
 int vitk_gemm_plan(int I, int J, int R, int accumulate, int b_mn_major, int* block_n, int* cta_group, int* mode,
                    int* n_clusters, int* n_tiles_m, int* n_tiles_n, int* kb_total);
 int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_mn_major, int cluster, int* items, int max_items);
-/* Row-tail split of a non-accumulating GEMM (vitk_linear_fwd_ws / _dgrad_ws): *main_rows = leading rows (a multiple of 256)
- * that keep the whole-tile launch, 0 = single launch.  Host-only. */
-int vitk_gemm_tail_plan(int I, int J, int R, int b_mn_major, int* main_rows);
+/* Split tail of a non-accumulating GEMM (vitk_linear_fwd_ws / _dgrad_ws) given vitk_gemm_tail_scratch_floats(J) of scratch:
+ * *n_whole tiles keep whole-K items with the fused epilogue, the k-blocks of the last *n_tail tiles (0: plain launch) are
+ * dealt out to all clusters, *tail_row0 = first matrix row of the first tail tile.  vitk_gemm_plan / _plan_items with
+ * accumulate == 2 describe the same launch (mode 3) item by item.  Host-only. */
+int vitk_gemm_tail_plan(int I, int J, int R, int b_mn_major, int* n_whole, int* n_tail, int* tail_row0);
+size_t vitk_gemm_tail_scratch_floats(int J);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long vitk_launch_count(void);
 /* per-launch GEMM timing with CUDA events on the launching stream (bench.py's live roofline):

@@ -155,47 +155,83 @@ def test_bench_gemm_shapes_m12608(name, N, Kd):
     assert K.rel_err(dw, wref) < 5e-3      # fp32 accumulation of exact bf16 products: only the summation order differs
 
 
-@pytest.mark.parametrize("which", ["fc2_fwd", "fc1_dgrad", "qkv_dgrad"])
-def test_row_tail_split_m12608(which):
-    """The three deep J = 768 GEMMs of a bs-64 step with the row-tail split (vitk_linear_*_ws: rows 0..12287 = two full waves of
-    the whole-tile kernel, rows 12288..12607 = split-K pass + thin epilogue) against the fp32 product AND against the single
-    launch; the scratch comes back all zero, twice in a row (it is reused by the next GEMM of the step)."""
+def _tail_plan(I, J, R, b_mn):
     import ctypes as C
+    nw, nt, r0 = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+    assert L.load().vitk_gemm_tail_plan(I, J, R, b_mn, C.byref(nw), C.byref(nt), C.byref(r0)) == 0
+    return nw.value, nt.value, r0.value
+
+
+@pytest.mark.parametrize("which", ["fc2_fwd", "fc1_dgrad", "qkv_dgrad"])
+def test_split_tail_m12608(which):
+    """The three deep J = 768 GEMMs of a bs-64 step with the split tail (vitk_linear_*_ws: 148 whole tiles with the fused
+    epilogue, the k-blocks of the last two tiles dealt out to all 74 CTA pairs, last-arriver epilogue) against the fp32
+    product AND against the plain launch; the scratch (tickets + partial sums) comes back all zero, five times in a row --
+    it is reused by the next GEMM of the step."""
     E = L.ENGINE_TCGEN05
-    rows = C.c_int(-1)
-    scratch = torch.zeros(512 * 768, dtype=torch.float32, device=DEV)
+    scratch = torch.zeros(L.load().vitk_gemm_tail_scratch_floats(768), dtype=torch.float32, device=DEV)
     if which == "fc2_fwd":
         x = _randn(M, 3072, seed=51).to(torch.bfloat16)
         w = _randn(768, 3072, seed=52, scale=0.03).to(torch.bfloat16)
         b = _randn(768, seed=53, scale=0.5)
         res = _randn(M, 768, seed=54)
-        assert L.load().vitk_gemm_tail_plan(M, 768, 3072, 0, C.byref(rows)) == 0
+        plan = _tail_plan(M, 768, 3072, 0)
         ref = x.float() @ w.float().t() + b + res
         run = lambda s: K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, E, residual=res, scratch=s)   # noqa: E731
     elif which == "fc1_dgrad":
         dy = _randn(M, 3072, seed=55).to(torch.bfloat16)
         w = _randn(3072, 768, seed=56, scale=0.03).to(torch.bfloat16)
-        assert L.load().vitk_gemm_tail_plan(M, 768, 3072, 1, C.byref(rows)) == 0
+        plan = _tail_plan(M, 768, 3072, 1)
         ref = dy.float() @ w.float()
         run = lambda s: K.linear_dgrad(dy, w, E, scratch=s)   # noqa: E731
     else:
         dy = _randn(M, 2304, seed=57).to(torch.bfloat16)
         w = _randn(2304, 768, seed=58, scale=0.03).to(torch.bfloat16)
         dyh = K.to_headmajor(dy)
-        assert L.load().vitk_gemm_tail_plan(M, 768, 2304, 1, C.byref(rows)) == 0
+        plan = _tail_plan(M, 768, 2304, 1)
         ref = dy.float() @ w.float()
         run = lambda s: K.linear_dgrad(dyh, w, E, dy_layout=L.LAYOUT_HEADMAJOR, scratch=s)   # noqa: E731
-    assert rows.value == 12288
+    assert plan == (148, 2, 49 * 256)
+    r0 = plan[2]
     single = run(None).float()
-    for _ in range(2):
+    for _ in range(5):
         split = run(scratch).float()
         torch.cuda.synchronize()
         assert int(torch.count_nonzero(scratch)) == 0
         assert K.rel_err(split, ref) < 2e-2
-        assert K.rel_err(split[rows.value:], ref[rows.value:]) < 2e-2
-        # same arithmetic up to the fp32 summation order of the tail's k-slices (and one bf16 rounding step where that flips)
+        assert K.rel_err(split[r0:], ref[r0:]) < 2e-2
+        # same arithmetic up to the fp32 summation order of the tail tiles' k-ranges (and one bf16 rounding step where that flips)
         assert float((split - single).abs().max()) <= 2e-2 * float(ref.abs().max())
-        assert float((split[rows.value:] - single[rows.value:]).abs().mean()) <= 2e-3 * float(ref.abs().mean())
+        assert float((split[r0:] - single[r0:]).abs().mean()) <= 2e-3 * float(ref.abs().mean())
+
+
+@pytest.mark.parametrize("batch", [32, 34, 50, 66])
+def test_split_tail_other_batches(batch):
+    """other tail geometries: one tail tile (bs 32), eleven tail tiles over two tile rows with cluster ranges that straddle
+    tiles (bs 34), tails that start in the middle of a tile row (bs 50, 66)."""
+    E = L.ENGINE_TCGEN05
+    Mb = batch * 197
+    assert _tail_plan(Mb, 768, 3072, 0)[1] > 0 and _tail_plan(Mb, 768, 2304, 1)[1] > 0
+    scratch = torch.zeros(L.load().vitk_gemm_tail_scratch_floats(768), dtype=torch.float32, device=DEV)
+    x = _randn(Mb, 3072, seed=61).to(torch.bfloat16)
+    w = _randn(768, 3072, seed=62, scale=0.03).to(torch.bfloat16)
+    b = _randn(768, seed=63, scale=0.5)
+    res = _randn(Mb, 768, seed=64)
+    ref = x.float() @ w.float().t() + b + res
+    for _ in range(2):
+        y = K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, E, residual=res, scratch=scratch)
+        assert K.rel_err(y, ref) < 2e-2
+        assert K.rel_err(y, K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, E, residual=res)) < 1e-4
+    dy = _randn(Mb, 2304, seed=65).to(torch.bfloat16)
+    wq = _randn(2304, 768, seed=66, scale=0.03).to(torch.bfloat16)
+    dyh = K.to_headmajor(dy)
+    dref = dy.float() @ wq.float()
+    for _ in range(2):
+        dx = K.linear_dgrad(dyh, wq, E, dy_layout=L.LAYOUT_HEADMAJOR, scratch=scratch).float()
+        assert K.rel_err(dx, dref) < 2e-2
+        assert float((dx - K.linear_dgrad(dyh, wq, E, dy_layout=L.LAYOUT_HEADMAJOR).float()).abs().max()) <= 2e-2 * float(dref.abs().max())
+    torch.cuda.synchronize()
+    assert int(torch.count_nonzero(scratch)) == 0
 
 
 def test_attention_bs64_vs_sdpa():

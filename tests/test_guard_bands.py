@@ -70,18 +70,20 @@ def test_guard_bands_layernorm_linear_attention(arena):
                     K.linear_dgrad(dy, w, eng, want_colsum=(name == "proj"))
                 K.linear_wgrad(dy, xx, N, Kd, eng)
             K.linear_fwd(xx, w, b, L.EPI_BIAS, eng)
-    # the row-tail split at the smallest size that takes it on 74 CTA pairs, with the scratch inside the arena as well
-    rows = C.c_int(0)
+    # the split tail at the smallest batch that takes it on 74 CTA pairs, tickets and partial sums inside the arena as well
+    nw, nt, r0 = C.c_int(0), C.c_int(0), C.c_int(0)
     for batch in range(20, 70):
-        L.load().vitk_gemm_tail_plan(batch * 197, 768, 3072, 0, C.byref(rows))
-        if rows.value:
+        L.load().vitk_gemm_tail_plan(batch * 197, 768, 3072, 0, C.byref(nw), C.byref(nt), C.byref(r0))
+        if nt.value:
             Mt = batch * 197
-            scratch = K._zeros(512 * 768, dtype=torch.float32, device=DEV)
+            scratch = K._zeros(L.load().vitk_gemm_tail_scratch_floats(768), dtype=torch.float32, device=DEV)
             K.linear_fwd(_rn(Mt, 3072, seed=11, dtype=bf), _rn(768, 3072, seed=12, scale=0.03, dtype=bf), _rn(768, seed=13),
                          L.EPI_BIAS_RESIDUAL, E, residual=_rn(Mt, 768, seed=14), scratch=scratch)
             K.linear_dgrad(_rn(Mt, 3072, seed=15, dtype=bf), _rn(3072, 768, seed=16, scale=0.03, dtype=bf), E, scratch=scratch)
+            torch.cuda.synchronize()
+            assert int(torch.count_nonzero(scratch)) == 0
             break
-    assert rows.value, "no batch size in 20..69 takes the row-tail split"
+    assert nt.value, "no batch size in 20..69 takes the split tail"
     # attention forward / backward, both precisions, a batch that is not a multiple of anything
     for dt in (bf, torch.float32):
         for batch in (3, 5):

@@ -211,87 +211,58 @@ def test_gemm_plan_bench_shapes_pick_documented_decompositions():
 
 def _tail_plan(lib, I, J, R, b_mn):
     import ctypes as C
-    rows = C.c_int(-1)
-    assert lib.vitk_gemm_tail_plan(I, J, R, b_mn, C.byref(rows)) == 0
-    return rows.value
+    nw, nt, r0 = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+    assert lib.vitk_gemm_tail_plan(I, J, R, b_mn, C.byref(nw), C.byref(nt), C.byref(r0)) == 0
+    return nw.value, nt.value, r0.value
 
 
-def test_gemm_row_tail_split_plan():
+def test_gemm_split_tail_plan():
     """at bs 64 the deep J = 768 GEMMs (fc2 forward, fc1 dgrad, qkv dgrad: 150 tiles of 256 x 256 on 74 CTA
-    pairs = two waves + a wave of two tiles) keep 48 tile rows = 144 tiles = two full waves in the whole-tile launch and hand
-    the last 320 rows to the split-K tail; shallow reductions, full last waves and reduced SM budgets are left alone.  Whatever
-    the shape: the leading rows are whole 256-row tiles, fit the full waves, and the tail is 256..512 rows."""
+    pairs = two waves + a wave of two tiles) keep 148 whole tiles and deal the 2 x kb k-blocks of the last two tiles out to all
+    74 clusters (mode 3); shallow reductions, well-filled last waves and reduced SM budgets keep the plain launch.  Whatever
+    the shape, the items of all clusters cover every (tile, k-block) exactly once, every whole tile is ONE item, and a
+    cluster's partial items come after its whole tiles."""
     from vit_spoof_detection_pda_b200 import _lib as L
     lib = L.load()
     prev = lib.vitk_set_sm_budget(0)
     try:
-        assert _tail_plan(lib, M64, 768, 3072, 0) == 12288      # fc2 forward
-        assert _tail_plan(lib, M64, 768, 3072, 1) == 12288      # fc1 dgrad
-        assert _tail_plan(lib, M64, 768, 2304, 1) == 12288      # qkv dgrad
-        assert _tail_plan(lib, M64, 768, 768, 0) == 0           # proj: 12 k-blocks, a split-K pass costs more than the wave
-        assert _tail_plan(lib, M64, 3072, 768, 0) == 0          # fc1 forward: shallow
-        assert _tail_plan(lib, 256 * 197, 768, 3072, 0) == 0    # bs 256: 591 tiles = 7.99 waves
-        assert _tail_plan(lib, 197, 768, 3072, 0) == 0          # bs 1
-        for batch in range(1, 130):
-            for J, R, bmn in ((768, 3072, 0), (768, 3072, 1), (768, 2304, 1), (3072, 3072, 0), (1536, 4096, 1)):
+        assert lib.vitk_gemm_tail_scratch_floats(768) == 1024 + 512 * 768
+        for (J, R, bmn) in ((768, 3072, 0), (768, 3072, 1), (768, 2304, 1)):     # fc2 forward, fc1 dgrad, qkv dgrad
+            assert _tail_plan(lib, M64, J, R, bmn) == (148, 2, 49 * 256)
+            plan, items = _plan(lib, M64, J, R, 2, bmn)
+            assert (plan["mode"], plan["bn"], plan["cg"], plan["clusters"]) == (3, 256, 2, 74)
+        assert _tail_plan(lib, M64, 768, 768, 0)[1] == 0            # proj: 12 k-blocks, the fix-up costs what the wave costs
+        assert _tail_plan(lib, M64, 3072, 768, 0)[1] == 0           # fc1 forward: shallow
+        assert _tail_plan(lib, 256 * 197, 768, 3072, 0)[1] == 0     # bs 256: 591 tiles = 7.99 waves
+        assert _tail_plan(lib, 197, 768, 3072, 0)[1] == 0           # bs 1
+        seen_mode3 = 0
+        for batch in list(range(1, 70)) + [96, 128, 200]:
+            for J, R, bmn in ((768, 3072, 0), (768, 3072, 1), (768, 2304, 1), (1536, 4096, 1)):
                 I = batch * 197
-                rows = _tail_plan(lib, I, J, R, bmn)
-                if rows == 0:
-                    continue
-                assert rows % 256 == 0 and 256 <= I - rows <= 512, (I, J, R, rows)
-                plan, _ = _plan(lib, rows, J, R, 0, bmn)
-                full, _ = _plan(lib, I, J, R, 0, bmn)
-                assert plan["cg"] == 2
-                waves = -(-(plan["tm"] * plan["tn"]) // 74)
-                waves_full = -(-(full["tm"] * full["tn"]) // (148 // full["cg"]))
-                assert waves * plan["bn"] < waves_full * full["bn"], (I, J, R, rows, plan, full)
+                nw, nt, r0 = _tail_plan(lib, I, J, R, bmn)
+                plan, items = _plan(lib, I, J, R, 2, bmn)
+                tiles = plan["tm"] * plan["tn"]
+                assert nw + nt == tiles
+                cover = {}
+                for cl in items:
+                    partial_seen = False
+                    for tile, kb0, kb1 in cl:
+                        if tile >= nw:
+                            partial_seen = True
+                        else:
+                            assert not partial_seen and (kb0, kb1) == (0, plan["kb"])
+                        for kb in range(kb0, kb1):
+                            cover[(tile, kb)] = cover.get((tile, kb), 0) + 1
+                assert len(cover) == tiles * plan["kb"] and set(cover.values()) == {1}, (I, J, R, plan)
+                if nt:
+                    seen_mode3 += 1
+                    assert plan["mode"] == 3 and plan["kb"] >= 24 and nt * 4 <= 148 // plan["cg"]
+                    assert nw % plan["clusters"] == 0 and r0 == (nw // plan["tn"]) * 128 * plan["cg"]
+                    assert (I - r0) * J <= 512 * J        # the scratch rows the model provides
+                else:
+                    assert plan["mode"] == 0
+        assert seen_mode3 >= 10
         lib.vitk_set_sm_budget(116)
-        assert _tail_plan(lib, M64, 768, 3072, 0) == 0          # 58 CTA pairs: 150 tiles = 2.6 waves, last wave well filled
+        assert _tail_plan(lib, M64, 768, 3072, 0)[1] == 0           # 58 CTA pairs: 150 tiles = 2.6 waves, last wave well filled
     finally:
         lib.vitk_set_sm_budget(prev)
-
-
-
-# ---------------------------------------------------------------------------------------------
-# checkpoint container of the reference (train_advanced.py:475-489 / test.py:167-188): written and read unchanged, on CPU
-# ---------------------------------------------------------------------------------------------
-def test_checkpoint_container_roundtrip_with_reference_model(pkg, tmp_path):
-    class Cfg:
-        model_name = "vit_base_patch16_224"
-        pretrained = False
-        num_classes = 2
-        dropout = 0.1
-
-    cfg = Cfg()
-    cfg.save_dir = str(tmp_path / "checkpoints_advanced")
-    ref = vo.OracleViTFaceAntiSpoofing(depth=12)
-    vo.seeded_init_(ref, seed=7)
-    opt = torch.optim.AdamW(ref.parameters(), lr=3e-4, weight_decay=0.05)
-    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=10)
-    scaler = torch.amp.GradScaler("cuda", enabled=False)
-    # the reference side writes (its own save_checkpoint body == pkg.save_checkpoint), our module reads
-    path = pkg.save_checkpoint(ref, opt, sched, scaler, 3, {"val_acc": 0.9}, cfg, "best_model_run_test.pth")
-    ck = torch.load(path, weights_only=False)
-    assert list(ck.keys()) == ["epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict",
-                               "scaler_state_dict", "metrics", "config"]
-    assert ck["config"]["save_dir"] == cfg.save_dir          # vars(config), as the reference stores it
-    m = pkg.ViTFaceAntiSpoofing(Cfg)
-    m2, ck2 = pkg.load_checkpoint(str(path), m, "cpu")
-    assert m2 is m and ck2["epoch"] == 3 and ck2["metrics"] == {"val_acc": 0.9}
-    for (n, a), (_, b) in zip(m.state_dict().items(), ref.state_dict().items()):
-        assert torch.equal(a, b), n
-    # the published-weights variants evaluate_all_models.py:293-298 tolerates: 'state_dict' wrapper and a bare state dict
-    for i, obj in enumerate(({"state_dict": ref.state_dict()}, ref.state_dict())):
-        p2 = tmp_path / f"variant{i}.pth"
-        torch.save(obj, p2)
-        mm = pkg.ViTFaceAntiSpoofing(Cfg)
-        pkg.load_checkpoint(str(p2), mm, "cpu")
-        assert torch.equal(mm.state_dict()["classifier.5.weight"], ref.state_dict()["classifier.5.weight"])
-    # wrong architecture fails loudly (strict), a missing file raises the reference's exception type
-    bad = dict(ref.state_dict())
-    bad.pop("vit.norm.weight")
-    torch.save({"model_state_dict": bad}, tmp_path / "bad.pth")
-    with pytest.raises(RuntimeError):
-        pkg.load_checkpoint(str(tmp_path / "bad.pth"), pkg.ViTFaceAntiSpoofing(Cfg), "cpu")
-    with pytest.raises(FileNotFoundError):
-        pkg.load_checkpoint(str(tmp_path / "nope.pth"), m, "cpu")

@@ -67,8 +67,8 @@ struct GemmProblem {
   MatLayout la, lb;
   int32_t in_dtype;  // VITK_F32 / VITK_BF16
   EpiParams ep;
-  // optional fp32 scratch (all zero on entry, left all zero) for the row-tail split of the tcgen05 engine (linear.cu:
-  // run_gemm_split); nullptr = never split
+  // optional scratch (all zero on entry, left all zero) for the split tail of the tcgen05 engine (gemm_tc.cu: tc_tail_plan);
+  // nullptr = whole tiles only
   float* tail_scratch;
   int64_t tail_scratch_floats;
 };
@@ -122,8 +122,5 @@ __device__ __forceinline__ void epilogue_scalar(const EpiParams& ep, int i, int 
 int gemm_simt(const GemmProblem& p, int splits, cudaStream_t st);
 // tcgen05/TMEM engine (bf16 operands only). Returns VITK_ERR_UNSUPPORTED for shapes it does not take.
 int gemm_tc(const GemmProblem& p, cudaStream_t st);
-// Row-tail split of a non-accumulating tcgen05 GEMM (pure host logic, gemm_tc.cu): number of leading rows the whole-tile
-// launch keeps (a multiple of 256), 0 = do not split.  See linear.cu: run_gemm_split.
-int tc_tail_split_rows(int I, int J, int R, bool b_mn);
 
 }  // namespace vitk

@@ -64,8 +64,15 @@ struct TcParams {
   OpCoord ca, cb;
   int32_t n_tiles_m, n_tiles_n, kb_total;
   int32_t streamk;          // 0: tile-strided, full K per tile; 1: contiguous (tile, k-block) unit range per CTA;
-                            // 2: sliced split-K, CTA c owns k-slice c / tiles of tile c % tiles
-  int64_t units_per_cta;    // stream-K: ceil(tiles * kb_total / gridDim.x); sliced split-K: number of k-slices
+                            // 2: sliced split-K, CTA c owns k-slice c / tiles of tile c % tiles;
+                            // 3: split tail -- tiles [0, n_whole) tile-strided with the fused epilogue, then the (tile, k-block)
+                            //    units of the last tiles [n_whole, tiles) in contiguous ranges over ALL clusters (see tc_tail_plan)
+  int64_t units_per_cta;    // stream-K: ceil(tiles * kb_total / gridDim.x); sliced split-K: number of k-slices; split tail:
+                            // ceil((tiles - n_whole) * kb_total / gridDim.x)
+  int32_t n_whole;          // split tail: number of whole-K tiles
+  int32_t tail_row0;        // split tail: first matrix row of the first tail tile (scratch row 0)
+  float* tail_acc;          // split tail: fp32 [I - tail_row0][J] partial sums, all zero between launches
+  int* tail_tickets;        // split tail: arrival counters, one per (tail tile, CTA rank, epilogue warp); zero between launches
   uint32_t idesc;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // bytes
   uint32_t a_kstep, b_kstep;            // bytes advanced per UMMA_K=16 step
@@ -396,6 +403,7 @@ struct TcWork {
 };
 struct TcWorkIter {
   int64_t cur, end;  // stream-K: unit cursor / end ; tile-strided: next tile / number of tiles
+  int64_t tcur, tend;   // split tail: this cluster's unit range in the (tail tile, k-block) space
   int stride;
   // the CTAs of one cluster (CTA pair) walk the same sequence; `cluster` of `n_clusters`.  Host-callable: the plan query of
   // the C-ABI (vitk_gemm_plan_items) walks the very same code, and tests/test_host_logic.py checks that the items of all
@@ -403,7 +411,14 @@ struct TcWorkIter {
   __host__ __device__ __forceinline__ void init(const TcParams& p, int cluster, int n_clusters) {
     const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n;
     stride = n_clusters;
-    if (p.streamk == 2) {          // sliced split-K: exactly one (tile, k-slice) item per CTA (pair)
+    tcur = tend = 0;
+    if (p.streamk == 3) {          // whole tiles first, then one contiguous range of the tail's units
+      cur = cluster;
+      end = p.n_whole;
+      const int64_t total = (tiles - p.n_whole) * p.kb_total;
+      tcur = (int64_t)cluster * p.units_per_cta;
+      tend = tcur + p.units_per_cta < total ? tcur + p.units_per_cta : total;
+    } else if (p.streamk == 2) {   // sliced split-K: exactly one (tile, k-slice) item per CTA (pair)
       cur = cluster;
       end = cur + 1;
     } else if (p.streamk) {
@@ -422,6 +437,22 @@ struct TcWorkIter {
     return true;
   }
   __host__ __device__ __forceinline__ bool next_raw(const TcParams& p, TcWork& w) {
+    if (p.streamk == 3) {
+      if (cur < end) {             // whole-K tile, fused epilogue
+        w.tile = (int)cur;
+        w.kb0 = 0;
+        w.kb1 = p.kb_total;
+        cur += stride;
+        return true;
+      }
+      if (tcur >= tend) return false;
+      w.tile = p.n_whole + (int)(tcur / p.kb_total);    // partial item of a tail tile (w.tile >= p.n_whole)
+      w.kb0 = (int)(tcur % p.kb_total);
+      const int64_t left = tend - tcur;
+      w.kb1 = (int)((int64_t)(p.kb_total - w.kb0) < left ? p.kb_total : w.kb0 + left);
+      tcur += w.kb1 - w.kb0;
+      return true;
+    }
     if (cur >= end) return false;
     if (p.streamk == 2) {
       const int tiles = p.n_tiles_m * p.n_tiles_n, S = (int)p.units_per_cta;
@@ -698,6 +729,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int i0 = w.tm * (TC_BM * CG) + (int)rank * TC_BM, j0 = w.tn * BN;
         const int row0 = i0 + q * 32;
         const bool active = row0 < p.I;   // warps whose 32 rows are all past the end of the matrix have nothing to do
+        if (p.streamk == 3 && w.tile >= p.n_whole) {
+          // ---- partial item of a tail tile (always after this cluster's whole tiles): this warp's 32 rows x BN/2 columns
+          // of the partial accumulator are added to the fp32 scratch; the warp that completes a region -- the last of the
+          // clusters sharing the tile to arrive at the region's ticket -- reads the sums back, clears them and applies
+          // the epilogue with per-thread global IO (epilogue_rows8: the same arithmetic as the fused TMA epilogue).
+          if (lane == 0) bulk_wait_read<0>();      // the staging tiles double as the transpose buffer: stores have read them out
+          __syncwarp();
+          mbar_wait(tfull_bar(acc), acc_phase);
+          tc_fence_after();
+          if (active) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            const int sub_row = lane >> 3, c4 = lane & 7;
+            float* const srow = p.tail_acc + (int64_t)(row0 + sub_row - p.tail_row0) * p.J + j0 + c4 * 4;
+#pragma unroll 1
+            for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
+              uint32_t raw[32];
+              tc_ld32(taddr + c * 32, raw);
+#pragma unroll
+              for (int cg = 0; cg < 8; ++cg)
+                sts128(stg + row_off_128(lane, cg), raw[cg * 4], raw[cg * 4 + 1], raw[cg * 4 + 2], raw[cg * 4 + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const uint4 u = lds128(stg + row_off_128(it * 4 + sub_row, c4));
+                if (row0 + sub_row + it * 4 < p.I)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(srow + (int64_t)(it * 4) * p.J + c * 32),
+                               "f"(__uint_as_float(u.x)), "f"(__uint_as_float(u.y)), "f"(__uint_as_float(u.z)), "f"(__uint_as_float(u.w)) : "memory");
+              }
+              __syncwarp();
+            }
+          }
+          release_tmem();
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          if (active) {
+            // contributors of this tile: the clusters whose unit ranges intersect [tt * kb_total, (tt + 1) * kb_total)
+            const int tt = w.tile - p.n_whole;
+            const int64_t u0 = (int64_t)tt * p.kb_total;
+            const int ncontrib = (int)((u0 + p.kb_total - 1) / p.units_per_cta - u0 / p.units_per_cta) + 1;
+            __threadfence();
+            __syncwarp();
+            int last = 0;
+            if (lane == 0) {
+              int* ticket = p.tail_tickets + (tt * CG + (int)rank) * TC_EPI_WARPS + we;
+              last = (atomicAdd(ticket, 1) + 1 == ncontrib);
+              if (last) *ticket = 0;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+              __threadfence();
+              const int sub_row = lane >> 3, c4 = lane & 7;
+              float* const srow = p.tail_acc + (int64_t)(row0 + sub_row - p.tail_row0) * p.J + j0 + c4 * 4;
+#pragma unroll 1
+              for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
+                float4 v[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  float4* sp = reinterpret_cast<float4*>(srow + (int64_t)(it * 4) * p.J + c * 32);
+                  if (row0 + sub_row + it * 4 < p.I) {
+                    v[it] = __ldcg(sp);
+                    __stcg(sp, make_float4(0.f, 0.f, 0.f, 0.f));
+                  } else {
+                    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
+                }
+                epilogue_rows8(p.ep, row0 + sub_row, j0 + c * 32 + c4 * 4, p.I, v);
+              }
+            }
+          }
+          continue;
+        }
         // ---- before the accumulator is ready: bias values of this warp's columns, and the first second-operand tile
         float bv[NCH];
 #pragma unroll
@@ -989,8 +1090,37 @@ static int epilogue_kind(const EpiParams& ep) {
   }
 }
 
+// ---- split tail (pure host logic).  M = B*197 rows rarely fill the last wave of the persistent grid: 12608 x 768 on 74 CTA
+// pairs is 150 tiles of 256 x 256 = two full waves and a third one with TWO tiles in it -- a third of the kernel's time for
+// 1.3 % of its work.  When the last wave is at most a quarter full and the reduction is deep enough (>= 24 k-blocks: fc2
+// forward, fc1 dgrad, qkv dgrad), the tiles of the full waves stay whole-K items with the fused epilogue and the k-blocks of
+// the remaining tiles are dealt out to ALL clusters as contiguous ranges (decomposition mode 3); partial accumulators meet
+// in an fp32 scratch and the last cluster to arrive at a region's ticket applies the epilogue (kernel: "partial item").
+// The caller provides the scratch (GemmProblem::tail_scratch, all zero between launches): TC_TAIL_TICKETS ints of tickets,
+// then fp32 [rows of the tail tiles][J].
+constexpr int TC_TAIL_TICKETS = 1024;
+struct TcTailPlan { int n_whole, tail_row0; int64_t units_per_cluster; };
+static bool tc_tail_plan(int I, int J, int R, int BN, int CG, int64_t scratch_floats, TcTailPlan* tp) {
+  if (g_tc_debug[9] == 1 || scratch_floats <= TC_TAIL_TICKETS) return false;
+  const int kb = (R + TC_BK - 1) / TC_BK;
+  const int rows_per_tile = TC_BM * CG;
+  const int tiles_n = J / BN, tiles_m = (I + rows_per_tile - 1) / rows_per_tile;
+  const int tiles = tiles_m * tiles_n, slots = sm_count() / CG;
+  const int full = tiles / slots, rem = tiles % slots;
+  if (kb < 24 || full < 1 || rem == 0 || rem * 4 > slots) return false;
+  const int n_whole = tiles - rem;
+  const int tail_row0 = (n_whole / tiles_n) * rows_per_tile;
+  if ((int64_t)(I - tail_row0) * J > scratch_floats - TC_TAIL_TICKETS) return false;
+  if (rem * CG * TC_EPI_WARPS > TC_TAIL_TICKETS) return false;
+  tp->n_whole = n_whole;
+  tp->tail_row0 = tail_row0;
+  tp->units_per_cluster = ((int64_t)rem * kb + slots - 1) / slots;
+  return true;
+}
+
 // ---- work decomposition (pure host logic; p.I / p.J / p.R set).  Returns the number of clusters (CTAs / CG) to launch.
-static int tc_decompose(TcParams& p, bool accumulate, int BN, int CG) {
+// tail_floats > 0: a non-accumulating GEMM whose epilogue mode permits the split tail, with that much scratch.
+static int tc_decompose(TcParams& p, bool accumulate, int BN, int CG, int64_t tail_floats = 0) {
   p.n_tiles_m = (p.I + TC_BM * CG - 1) / (TC_BM * CG);
   p.n_tiles_n = p.J / BN;
   p.kb_total = (p.R + TC_BK - 1) / TC_BK;
@@ -999,6 +1129,16 @@ static int tc_decompose(TcParams& p, bool accumulate, int BN, int CG) {
   int grid = tiles < slots ? tiles : slots;
   p.streamk = 0;
   p.units_per_cta = 0;
+  p.n_whole = tiles;
+  p.tail_row0 = 0;
+  TcTailPlan tp;
+  if (!accumulate && tail_floats > 0 && tc_tail_plan(p.I, p.J, p.R, BN, CG, tail_floats, &tp)) {
+    p.streamk = 3;
+    p.n_whole = tp.n_whole;
+    p.tail_row0 = tp.tail_row0;
+    p.units_per_cta = tp.units_per_cluster;
+    return slots;
+  }
   if (accumulate && g_tc_debug[1] != 1) {
     const int64_t total = (int64_t)tiles * p.kb_total;
     grid = total < slots ? (int)total : slots;
@@ -1026,8 +1166,9 @@ static int tc_decompose(TcParams& p, bool accumulate, int BN, int CG) {
 // and the loads switched off in turn (vitk_debug_set(7, .)), the mainloop sustains ~36 B/clk/SM of operand traffic
 // -- it, not the tensor pipe, bounds every shape here -- so wider tiles win unless they cost a whole extra wave: with
 // M = B*197 the tile count is rarely a multiple of the slot count (12608 x 768 on 74 CTA pairs: 150 tiles of 256x256 =
-// 3 waves for 2.03 waves of work, 200 tiles of 256x192 = 3 waves of 7/8 the bytes).
-static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* bn_out, int* cg_out) {
+// 3 waves for 2.03 waves of work, 200 tiles of 256x192 = 3 waves of 7/8 the bytes).  With a tail scratch (tail_floats > 0) a
+// nearly empty last wave costs only its share of k-blocks plus a fixed fix-up (tc_tail_plan): 150 tiles = 2 waves + 2 k-blocks.
+static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* bn_out, int* cg_out, int64_t tail_floats = 0) {
   int cg = 0, bn = 0;
   const int forced_bn = (g_tc_debug[2] == 128 || g_tc_debug[2] == 192 || g_tc_debug[2] == 256) ? g_tc_debug[2] : 0;
   if (accumulate) {
@@ -1048,7 +1189,11 @@ static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* b
         const long tiles = tiles_m * (J / cand);
         const long waves = (tiles + slots - 1) / slots;
         const double ingest = (128.0 + cand / c) * 128.0 / 36.0, mma = 2.0 * cand;
-        const double cost = (double)waves * ((double)kb * (ingest > mma ? ingest : mma) + 1200.0);
+        const double per_kb = ingest > mma ? ingest : mma;
+        double cost = (double)waves * ((double)kb * per_kb + 1200.0);
+        TcTailPlan tp;
+        if (tail_floats > 0 && tc_tail_plan(I, J, R, cand, c, tail_floats, &tp))
+          cost = (double)(tiles / slots) * ((double)kb * per_kb + 1200.0) + (double)tp.units_per_cluster * per_kb + 6000.0;
         if (best < 0.0 || cost < best) { best = cost; bn = cand; cg = c; }
       }
     }
@@ -1057,43 +1202,13 @@ static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* b
   *cg_out = cg;
 }
 
-// ---- row-tail split (pure host logic).  M = B*197 rows rarely fill the last wave of the persistent grid: 12608 x 768 on 74
-// CTA pairs is 150 tiles of 256 x 256 = two full waves and a third one with TWO tiles in it -- a third of the kernel's time
-// for 1.3 % of its work.  When the reduction is deep enough for a split-K pass to be cheaper than that wave (>= 32 k-blocks:
-// fc2 forward, fc1 dgrad, qkv dgrad), the caller (linear.cu: run_gemm_split) runs the leading rows -- as many 256-row tile
-// rows as fit into the FULL waves -- through the whole-tile kernel with its fused epilogue, and the remaining rows (>= 256,
-// so the CTA-pair kernel applies) as a sliced split-K accumulate GEMM over all CTA pairs into an fp32 scratch, followed by a
-// thin epilogue pass.  Returns the number of leading rows, 0 = keep the single launch.
-int tc_tail_split_rows(int I, int J, int R, bool b_mn) {
-  if (g_tc_debug[9] == 1) return 0;
-  const long kb = (R + TC_BK - 1) / TC_BK;
-  if (kb < 32 || J % 256 != 0) return 0;
-  int bn = 0, cg = 0;
-  tc_pick_tile(I, J, R, false, b_mn, &bn, &cg);
-  if (cg != 2 || bn == 0) return 0;
-  const long slots = sm_count() / 2;
-  const long rows_per_tile = TC_BM * 2;
-  auto waves_for = [&](long rows, int n) { const long t = ((rows + rows_per_tile - 1) / rows_per_tile) * (J / n); return (t + slots - 1) / slots; };
-  // candidates: the tile width the single launch would use and the widest one (fewer operand bytes per FLOP)
-  for (int n : {256, bn}) {
-    if (J % n != 0 || (b_mn && (n / 2) % 64 != 0)) continue;
-    const long tiles_n = J / n;
-    const long tiles = ((I + rows_per_tile - 1) / rows_per_tile) * tiles_n;
-    const long full = tiles / slots, rem = tiles % slots;
-    if (full < 1 || rem == 0 || rem * 4 > slots) continue;        // last wave at least a quarter full: leave it alone
-    long main_tm = (full * slots) / tiles_n;
-    if ((long)I - main_tm * rows_per_tile < rows_per_tile) --main_tm;   // keep >= 256 tail rows: the CTA-pair accumulate kernel
-    if (main_tm < 1) continue;
-    const long main_rows = main_tm * rows_per_tile;
-    if ((long)I - main_rows > 2 * rows_per_tile) continue;        // the tail must stay thin
-    // the leading rows must really take `full` waves with the tile shape the heuristic picks for them
-    int bn2 = 0, cg2 = 0;
-    tc_pick_tile((int)main_rows, J, R, false, b_mn, &bn2, &cg2);
-    if (cg2 != 2 || waves_for(main_rows, bn2) > full) continue;
-    if (waves_for(main_rows, bn2) * bn2 >= waves_for(I, bn) * bn) continue;   // no fewer tensor clocks than the single launch
-    return (int)main_rows;
-  }
-  return 0;
+// epilogue modes whose partial items the kernel's per-thread fix-up path may finish (epilogue_rows8 implements every mode; the
+// fused column sums and the two-output GELU epilogue stay whole-tile only)
+static int64_t plan_tail_floats(int J) { return (int64_t)TC_TAIL_TICKETS + (int64_t)512 * J; }
+static int64_t tail_floats_of(const GemmProblem& pr) {
+  if (!pr.tail_scratch || pr.ep.colsum || ((uintptr_t)pr.tail_scratch & 15)) return 0;
+  if (!(pr.ep.mode == E_BIAS_RESIDUAL || pr.ep.mode == E_STORE)) return 0;
+  return pr.tail_scratch_floats;
 }
 
 template <int BN, int CG, int EK>
@@ -1145,7 +1260,9 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
     if (b_mn) { p.b_sbo = TC_BK * 128; p.b_lbo = 1024; }
   }
 #endif
-  const int grid = tc_decompose(p, pr.ep.mode == E_ACCUM, BN, CG);
+  const int grid = tc_decompose(p, pr.ep.mode == E_ACCUM, BN, CG, EK == EK_LEGACY ? 0 : tail_floats_of(pr));
+  p.tail_tickets = reinterpret_cast<int*>(pr.tail_scratch);
+  p.tail_acc = pr.tail_scratch ? pr.tail_scratch + TC_TAIL_TICKETS : nullptr;
   p.ep = pr.ep;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid * CG, 1, 1);
@@ -1192,9 +1309,9 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
   if (pr.J % 128 != 0 || pr.ep.ldc % 8 != 0) { set_error("gemm_tc: J must be a multiple of 128 (got %d)", pr.J); return VITK_ERR_UNSUPPORTED; }
   const bool b_mn = pr.lb.s_row == 1 && pr.lb.s_col != 1;   // MN-major B: staged in 64-row atoms
   int cg = 0, bn = 0;
-  tc_pick_tile(pr.I, pr.J, pr.R, pr.ep.mode == E_ACCUM, b_mn, &bn, &cg);
-  if (bn == 0 || pr.J % bn != 0) { set_error("gemm_tc: no BLOCK_N divides J=%d", pr.J); return VITK_ERR_UNSUPPORTED; }
   const int ek = epilogue_kind(pr.ep);
+  tc_pick_tile(pr.I, pr.J, pr.R, pr.ep.mode == E_ACCUM, b_mn, &bn, &cg, ek == EK_LEGACY ? 0 : tail_floats_of(pr));
+  if (bn == 0 || pr.J % bn != 0) { set_error("gemm_tc: no BLOCK_N divides J=%d", pr.J); return VITK_ERR_UNSUPPORTED; }
   if (pr.ep.colsum && !(ek == EK_GELU_BWD || (ek == EK_STORE_BF16 && !pr.ep.bias) || pr.ep.mode == E_GELU_BWD)) {
     set_error("gemm_tc: fused column sums need the TMA epilogue of a bias-free bf16 store or of the GELU' multiply");
     return VITK_ERR_UNSUPPORTED;
@@ -1221,11 +1338,12 @@ extern "C" int vitk_gemm_plan(int I, int J, int R, int accumulate, int b_mn_majo
                               int* n_clusters, int* n_tiles_m, int* n_tiles_n, int* kb_total) {
   VITK_CHECK_ARG(I > 0 && J > 0 && R > 0 && J % 128 == 0);
   int bn = 0, cg = 0;
-  vitk::tc_pick_tile(I, J, R, accumulate != 0, b_mn_major != 0, &bn, &cg);
+  const int64_t tail_floats = accumulate == 2 ? vitk::plan_tail_floats(J) : 0;   // 2: no accumulation, tail scratch available
+  vitk::tc_pick_tile(I, J, R, accumulate == 1, b_mn_major != 0, &bn, &cg, tail_floats);
   if (bn == 0 || J % bn != 0) { vitk::set_error("vitk_gemm_plan: no BLOCK_N divides J=%d", J); return VITK_ERR_UNSUPPORTED; }
   vitk::TcParams p{};
   p.I = I; p.J = J; p.R = R;
-  const int grid = vitk::tc_decompose(p, accumulate != 0, bn, cg);
+  const int grid = vitk::tc_decompose(p, accumulate == 1, bn, cg, tail_floats);
   if (block_n) *block_n = bn;
   if (cta_group) *cta_group = cg;
   if (mode) *mode = p.streamk;
@@ -1239,11 +1357,12 @@ extern "C" int vitk_gemm_plan(int I, int J, int R, int accumulate, int b_mn_majo
 extern "C" int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_mn_major, int cluster, int* items, int max_items) {
   if (!(I > 0 && J > 0 && R > 0 && J % 128 == 0 && items && max_items > 0)) return -VITK_ERR_ARG;
   int bn = 0, cg = 0;
-  vitk::tc_pick_tile(I, J, R, accumulate != 0, b_mn_major != 0, &bn, &cg);
+  const int64_t tail_floats = accumulate == 2 ? vitk::plan_tail_floats(J) : 0;
+  vitk::tc_pick_tile(I, J, R, accumulate == 1, b_mn_major != 0, &bn, &cg, tail_floats);
   if (bn == 0 || J % bn != 0) return -VITK_ERR_UNSUPPORTED;
   vitk::TcParams p{};
   p.I = I; p.J = J; p.R = R;
-  const int grid = vitk::tc_decompose(p, accumulate != 0, bn, cg);
+  const int grid = vitk::tc_decompose(p, accumulate == 1, bn, cg, tail_floats);
   if (cluster < 0 || cluster >= grid) return -VITK_ERR_ARG;
   vitk::TcWorkIter wi;
   wi.init(p, cluster, grid);
@@ -1255,12 +1374,25 @@ extern "C" int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_m
   }
   return n;
 }
-// Host-only view of the row-tail split (no launch): *main_rows = leading rows of the whole-tile launch (0: single launch).
-extern "C" int vitk_gemm_tail_plan(int I, int J, int R, int b_mn_major, int* main_rows) {
-  VITK_CHECK_ARG(I > 0 && J > 0 && R > 0 && J % 128 == 0 && main_rows);
-  *main_rows = vitk::tc_tail_split_rows(I, J, R, b_mn_major != 0);
+// Host-only view of the split tail (no launch) for a non-accumulating GEMM given a scratch of vitk_gemm_tail_scratch_floats(J)
+// floats: *n_whole = tiles that stay whole-K items with the fused epilogue, *n_tail = tiles whose k-blocks are dealt out to
+// all clusters (0: plain tile-strided launch), *tail_row0 = first matrix row of the first tail tile.
+extern "C" int vitk_gemm_tail_plan(int I, int J, int R, int b_mn_major, int* n_whole, int* n_tail, int* tail_row0) {
+  VITK_CHECK_ARG(I > 0 && J > 0 && R > 0 && J % 128 == 0 && n_whole && n_tail && tail_row0);
+  int bn = 0, cg = 0;
+  const int64_t tail_floats = vitk::plan_tail_floats(J);
+  vitk::tc_pick_tile(I, J, R, false, b_mn_major != 0, &bn, &cg, tail_floats);
+  if (bn == 0 || J % bn != 0) { vitk::set_error("vitk_gemm_tail_plan: no BLOCK_N divides J=%d", J); return VITK_ERR_UNSUPPORTED; }
+  vitk::TcParams p{};
+  p.I = I; p.J = J; p.R = R;
+  vitk::tc_decompose(p, false, bn, cg, tail_floats);
+  *n_whole = p.n_whole;
+  *n_tail = p.n_tiles_m * p.n_tiles_n - p.n_whole;
+  *tail_row0 = p.streamk == 3 ? p.tail_row0 : 0;
   return VITK_OK;
 }
+// floats of scratch that always suffice for a GEMM with J output columns: the tickets + 512 rows of partial sums
+extern "C" size_t vitk_gemm_tail_scratch_floats(int J) { return J > 0 ? (size_t)vitk::plan_tail_floats(J) : 0; }
 extern "C" int vitk_debug_set(int key, int value) {
   if (!vitk::knob_allowed(key)) {
     vitk::set_error("vitk_debug_set: key %d is not available in this build (development-only keys need libvitk_dev.so)", key);

@@ -18,75 +18,8 @@ static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 
-// ---- row-tail split of the non-accumulating tcgen05 GEMMs (plan: gemm_tc.cu tc_tail_split_rows) ------------------
-// epilogue of the tail rows: out[row0 + r][j] = epilogue(scratch[r][j]); the scratch is handed back all zero
-__global__ void __launch_bounds__(256)
-tail_epilogue_kernel(float* __restrict__ scratch, EpiParams ep, int row0, int rows, int J) {
-  pdl_sync_traced(TK_GEMM_TAIL);
-  const int jq = J >> 2;
-  const int64_t total = (int64_t)rows * jq;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(idx / jq), j = (int)(idx % jq) * 4;
-    float4* sp = reinterpret_cast<float4*>(scratch + (int64_t)r * J + j);
-    float4 v = *sp;
-    *sp = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ep.bias) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + j));
-      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-    }
-    const int64_t o = (int64_t)(row0 + r) * ep.ldc + j;
-    if (ep.mode == E_BIAS_RESIDUAL) {
-      const float4 x = *reinterpret_cast<const float4*>(ep.residual + o);
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o) = make_float4(x.x + v.x, x.y + v.y, x.z + v.z, x.w + v.w);
-    } else if (ep.out_dtype == VITK_BF16) {
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-    } else {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + o) = v;
-    }
-  }
-  trace_end(TK_GEMM_TAIL);
-}
-
-// Leading rows: the whole-tile kernel with its fused epilogue (full waves only).  Tail rows: sliced split-K accumulate GEMM
-// of all CTA pairs into the zeroed fp32 scratch, then tail_epilogue_kernel.  The three launches are chained by programmatic
-// dependent launch like every other kernel of the library.  Partial sums of the tail meet in fp32 atomics, so the tail rows
-// are rounded like the others but not bit-reproducible run to run -- the model only passes a scratch in training mode
-// (model.cu), where the weight gradients already are accumulated that way; eval keeps its bit-exact batch invariance.
-static int run_gemm_split(const GemmProblem& p, int main_rows, cudaStream_t st) {
-  GemmProblem head = p;
-  head.I = main_rows;
-  head.tail_scratch = nullptr;
-  VITK_TRY(gemm_tc(head, st));
-  GemmProblem tail = p;
-  tail.I = p.I - main_rows;
-  tail.A = reinterpret_cast<const bf16*>(p.A) + p.la.at(main_rows, 0);
-  tail.tail_scratch = nullptr;
-  tail.ep = EpiParams{};
-  tail.ep.mode = E_ACCUM; tail.ep.out = p.tail_scratch; tail.ep.ldc = p.J; tail.ep.out_dtype = VITK_F32;
-  VITK_TRY(gemm_tc(tail, st));
-  const int64_t total = (int64_t)tail.I * (p.J / 4);
-  const int grid = (int)((total + 255) / 256);
-  VITK_LAUNCH((tail_epilogue_kernel), grid, 256, 0, st, p.tail_scratch, p.ep, main_rows, tail.I, p.J);
-  return VITK_OK;
-}
-
-static bool tail_split_applies(const GemmProblem& p, int* main_rows) {
-  if (!p.tail_scratch || p.in_dtype != VITK_BF16 || p.ep.colsum || p.J % 4 != 0) return false;
-  if (!(p.ep.mode == E_BIAS_RESIDUAL || (p.ep.mode == E_STORE && p.ep.ldc % 4 == 0))) return false;
-  if (p.la.split >= 3) return false;
-  const bool b_mn = p.lb.s_row == 1 && p.lb.s_col != 1;
-  const int rows = tc_tail_split_rows(p.I, p.J, p.R, b_mn);
-  if (rows <= 0 || (int64_t)(p.I - rows) * p.J > p.tail_scratch_floats) return false;
-  *main_rows = rows;
-  return true;
-}
-
 static int run_gemm_impl(const GemmProblem& p, int engine, int simt_splits, cudaStream_t st) {
-  if (engine == VITK_ENGINE_TCGEN05) {
-    int main_rows = 0;
-    if (tail_split_applies(p, &main_rows)) return run_gemm_split(p, main_rows, st);
-    return gemm_tc(p, st);
-  }
+  if (engine == VITK_ENGINE_TCGEN05) return gemm_tc(p, st);
   return gemm_simt(p, simt_splits, st);
 }
 

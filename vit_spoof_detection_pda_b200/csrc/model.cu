@@ -93,10 +93,10 @@ struct Plan {
   size_t meanf, rstdf, feat, head_save;
   // backward transients
   size_t dx, dx16, du, dh, dqkv, dfeat, dxc;
-  // fp32 scratch of the GEMMs' row-tail split (training, bf16; linear.cu run_gemm_split): TAIL_FLOATS floats, kept all zero
+  // scratch of the GEMMs' split tail (training, bf16; gemm_tc.cu tc_tail_plan): TAIL_FLOATS floats, kept all zero
   size_t tail;
 };
-constexpr size_t TAIL_FLOATS = (size_t)512 * D;
+constexpr size_t TAIL_FLOATS = (size_t)512 * D + 1024;   // = vitk_gemm_tail_scratch_floats(768): tickets + 512 rows
 
 static void make_plan(int B, int depth, int precision, int training, int frozen, Plan* p) {
   const size_t T = precision == VITK_PREC_BF16 ? 2 : 4;
@@ -180,7 +180,7 @@ struct Ctx {
   bool save;
   char* ws;
   cudaStream_t st;
-  float* tail;          // row-tail split scratch (nullptr: eval / fp32-validate -- every GEMM is a single launch)
+  float* tail;          // split-tail scratch (nullptr: eval / fp32-validate -- whole-K tiles only)
   size_t tail_floats;
   const void* W(int64_t off) const {
     return dt == VITK_BF16 ? (const void*)((const bf16*)m->params16 + off) : (const void*)(m->params + off);
