@@ -328,7 +328,7 @@ int vitk_trace_stop(void);
  * consulted): tile width BLOCK_N, CTA group (1 single CTAs with 128-row tiles, 2 CTA pairs with 256-row tiles), mode
  * (0 whole-K tiles strided over the persistent clusters, 1 contiguous stream-K ranges, 2 sliced split-K: one k-slice of
  * one tile per cluster, 3 split tail), number of clusters launched, tile grid and number of 64-deep k-blocks.  accumulate == 1
- * is the weight-gradient epilogue (fp32 +=), 2 a non-accumulating GEMM with a tail scratch; b_mn_major != 0 says the B operand is stored with its row index contiguous
+ * is the weight-gradient epilogue (fp32 +=), 2 / 3 a non-accumulating GEMM with a tail scratch and bf16 / fp32 output; b_mn_major != 0 says the B operand is stored with its row index contiguous
  * (dgrad's W, wgrad's X).  vitk_gemm_plan_items writes the (tile, first k-block, end k-block) triples cluster `cluster`
  * walks -- the same iterator code the kernel's warps run -- and returns their count (negative VITK_ERR_* on bad
  * arguments); tests/test_host_logic.py checks that all clusters together cover every (tile, k-block) exactly once. */
@@ -337,9 +337,10 @@ int vitk_gemm_plan(int I, int J, int R, int accumulate, int b_mn_major, int* blo
 int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_mn_major, int cluster, int* items, int max_items);
 /* Split tail of a non-accumulating GEMM (vitk_linear_fwd_ws / _dgrad_ws) given vitk_gemm_tail_scratch_floats(J) of scratch:
  * *n_whole tiles keep whole-K items with the fused epilogue, the k-blocks of the last *n_tail tiles (0: plain launch) are
- * dealt out to all clusters, *tail_row0 = first matrix row of the first tail tile.  vitk_gemm_plan / _plan_items with
- * accumulate == 2 describe the same launch (mode 3) item by item.  Host-only. */
-int vitk_gemm_tail_plan(int I, int J, int R, int b_mn_major, int* n_whole, int* n_tail, int* tail_row0);
+ * dealt out to all clusters, *tail_row0 = first matrix row of the first tail tile; f32_out != 0: the epilogue writes fp32
+ * (bias + residual), else bf16.  vitk_gemm_plan / _plan_items with accumulate == 2 (bf16 out) / 3 (fp32 out) describe the
+ * same launch (mode 3) item by item.  Host-only. */
+int vitk_gemm_tail_plan(int I, int J, int R, int b_mn_major, int f32_out, int* n_whole, int* n_tail, int* tail_row0);
 size_t vitk_gemm_tail_scratch_floats(int J);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long vitk_launch_count(void);

@@ -155,29 +155,32 @@ def test_bench_gemm_shapes_m12608(name, N, Kd):
     assert K.rel_err(dw, wref) < 5e-3      # fp32 accumulation of exact bf16 products: only the summation order differs
 
 
-def _tail_plan(I, J, R, b_mn):
+def _tail_plan(I, J, R, b_mn, f32_out=0):
     import ctypes as C
     nw, nt, r0 = C.c_int(-1), C.c_int(-1), C.c_int(-1)
-    assert L.load().vitk_gemm_tail_plan(I, J, R, b_mn, C.byref(nw), C.byref(nt), C.byref(r0)) == 0
+    assert L.load().vitk_gemm_tail_plan(I, J, R, b_mn, f32_out, C.byref(nw), C.byref(nt), C.byref(r0)) == 0
     return nw.value, nt.value, r0.value
 
 
-@pytest.mark.parametrize("which", ["fc2_fwd", "fc1_dgrad", "qkv_dgrad"])
+def _tail_scratch():
+    return torch.zeros(L.load().vitk_gemm_tail_scratch_floats(768), dtype=torch.float32, device=DEV)
+
+
+@pytest.mark.parametrize("which", ["fc1_dgrad", "qkv_dgrad", "bf16_fwd"])
 def test_split_tail_m12608(which):
-    """The three deep J = 768 GEMMs of a bs-64 step with the split tail (vitk_linear_*_ws: 148 whole tiles with the fused
-    epilogue, the k-blocks of the last two tiles dealt out to all 74 CTA pairs, last-arriver epilogue) against the fp32
-    product AND against the plain launch; the scratch (tickets + partial sums) comes back all zero, five times in a row --
-    it is reused by the next GEMM of the step."""
+    """The deep J = 768 bf16-output GEMMs of a bs-64 step with the split tail (vitk_linear_*_ws: 148 whole tiles with the fused
+    epilogue, the k-blocks of the last two tiles dealt out to all 74 CTA pairs, last-arriver epilogue) against the fp32 product
+    AND against the plain launch; the scratch (tickets + partial sums) comes back all zero, five times in a row -- it is
+    reused by the next GEMM of the step."""
     E = L.ENGINE_TCGEN05
-    scratch = torch.zeros(L.load().vitk_gemm_tail_scratch_floats(768), dtype=torch.float32, device=DEV)
-    if which == "fc2_fwd":
+    scratch = _tail_scratch()
+    if which == "bf16_fwd":
         x = _randn(M, 3072, seed=51).to(torch.bfloat16)
         w = _randn(768, 3072, seed=52, scale=0.03).to(torch.bfloat16)
         b = _randn(768, seed=53, scale=0.5)
-        res = _randn(M, 768, seed=54)
         plan = _tail_plan(M, 768, 3072, 0)
-        ref = x.float() @ w.float().t() + b + res
-        run = lambda s: K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, E, residual=res, scratch=s)   # noqa: E731
+        ref = x.float() @ w.float().t() + b
+        run = lambda s: K.linear_fwd(x, w, b, L.EPI_BIAS, E, scratch=s)   # noqa: E731
     elif which == "fc1_dgrad":
         dy = _randn(M, 3072, seed=55).to(torch.bfloat16)
         w = _randn(3072, 768, seed=56, scale=0.03).to(torch.bfloat16)
@@ -203,33 +206,57 @@ def test_split_tail_m12608(which):
         # same arithmetic up to the fp32 summation order of the tail tiles' k-ranges (and one bf16 rounding step where that flips)
         assert float((split - single).abs().max()) <= 2e-2 * float(ref.abs().max())
         assert float((split[r0:] - single[r0:]).abs().mean()) <= 2e-3 * float(ref.abs().mean())
+        print(f"{which}: whole-tile rows bit-identical to the plain launch: {bool(torch.equal(split[:r0], single[:r0]))}")
 
 
-@pytest.mark.parametrize("batch", [32, 34, 50, 66])
-def test_split_tail_other_batches(batch):
-    """other tail geometries: one tail tile (bs 32), eleven tail tiles over two tile rows with cluster ranges that straddle
-    tiles (bs 34), tails that start in the middle of a tile row (bs 50, 66)."""
+@pytest.mark.parametrize("batch", [32, 33, 49, 50])
+def test_split_tail_fp32_residual_epilogue(batch):
+    """fc2 forward (bias + fp32 residual, fp32 out) at the batch sizes whose tile grids take a split tail with a >= 5-stage
+    ring: 256 x 128 tiles with 2 / 8 tail tiles (bs 32 / 33), 256 x 192 tiles with 4 / 8 tail tiles (bs 49 / 50) -- cluster
+    ranges that straddle tail tiles, tails that start in the middle of a tile row."""
     E = L.ENGINE_TCGEN05
     Mb = batch * 197
-    assert _tail_plan(Mb, 768, 3072, 0)[1] > 0 and _tail_plan(Mb, 768, 2304, 1)[1] > 0
-    scratch = torch.zeros(L.load().vitk_gemm_tail_scratch_floats(768), dtype=torch.float32, device=DEV)
+    nw, nt, r0 = _tail_plan(Mb, 768, 3072, 0, 1)
+    assert nt > 0
+    scratch = _tail_scratch()
     x = _randn(Mb, 3072, seed=61).to(torch.bfloat16)
     w = _randn(768, 3072, seed=62, scale=0.03).to(torch.bfloat16)
     b = _randn(768, seed=63, scale=0.5)
     res = _randn(Mb, 768, seed=64)
     ref = x.float() @ w.float().t() + b + res
-    for _ in range(2):
+    single = K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, E, residual=res)
+    for _ in range(3):
         y = K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, E, residual=res, scratch=scratch)
+        torch.cuda.synchronize()
+        assert int(torch.count_nonzero(scratch)) == 0
         assert K.rel_err(y, ref) < 2e-2
-        assert K.rel_err(y, K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, E, residual=res)) < 1e-4
-    dy = _randn(Mb, 2304, seed=65).to(torch.bfloat16)
-    wq = _randn(2304, 768, seed=66, scale=0.03).to(torch.bfloat16)
-    dyh = K.to_headmajor(dy)
-    dref = dy.float() @ wq.float()
-    for _ in range(2):
-        dx = K.linear_dgrad(dyh, wq, E, dy_layout=L.LAYOUT_HEADMAJOR, scratch=scratch).float()
+        assert K.rel_err(y, single) < 1e-4       # fp32 outputs: only the summation order of the tail tiles differs
+
+
+@pytest.mark.parametrize("batch", [16, 17, 33, 66])
+def test_split_tail_dgrad_other_batches(batch):
+    """fc1 dgrad (row-major dY) and qkv dgrad (head-major dY) with other tail geometries: 256 x 128 tiles with 4 / 10 tail tiles
+    (bs 16 / 17), 256 x 256 tiles with 4 / 5 tail tiles (bs 33 / 66)."""
+    E = L.ENGINE_TCGEN05
+    Mb = batch * 197
+    scratch = _tail_scratch()
+    assert _tail_plan(Mb, 768, 3072, 1)[1] > 0
+    dy = _randn(Mb, 3072, seed=65).to(torch.bfloat16)
+    w = _randn(3072, 768, seed=66, scale=0.03).to(torch.bfloat16)
+    dref = dy.float() @ w.float()
+    single = K.linear_dgrad(dy, w, E).float()
+    for _ in range(3):
+        dx = K.linear_dgrad(dy, w, E, scratch=scratch).float()
         assert K.rel_err(dx, dref) < 2e-2
-        assert float((dx - K.linear_dgrad(dyh, wq, E, dy_layout=L.LAYOUT_HEADMAJOR).float()).abs().max()) <= 2e-2 * float(dref.abs().max())
+        assert float((dx - single).abs().max()) <= 2e-2 * float(dref.abs().max())
+    if _tail_plan(Mb, 768, 2304, 1)[1] > 0:
+        dy = _randn(Mb, 2304, seed=67).to(torch.bfloat16)
+        wq = _randn(2304, 768, seed=68, scale=0.03).to(torch.bfloat16)
+        dyh = K.to_headmajor(dy)
+        dref = dy.float() @ wq.float()
+        for _ in range(3):
+            dx = K.linear_dgrad(dyh, wq, E, dy_layout=L.LAYOUT_HEADMAJOR, scratch=scratch).float()
+            assert K.rel_err(dx, dref) < 2e-2
     torch.cuda.synchronize()
     assert int(torch.count_nonzero(scratch)) == 0
 

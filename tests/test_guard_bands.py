@@ -73,7 +73,7 @@ def test_guard_bands_layernorm_linear_attention(arena):
     # the split tail at the smallest batch that takes it on 74 CTA pairs, tickets and partial sums inside the arena as well
     nw, nt, r0 = C.c_int(0), C.c_int(0), C.c_int(0)
     for batch in range(20, 70):
-        L.load().vitk_gemm_tail_plan(batch * 197, 768, 3072, 0, C.byref(nw), C.byref(nt), C.byref(r0))
+        L.load().vitk_gemm_tail_plan(batch * 197, 768, 3072, 0, 1, C.byref(nw), C.byref(nt), C.byref(r0))
         if nt.value:
             Mt = batch * 197
             scratch = K._zeros(L.load().vitk_gemm_tail_scratch_floats(768), dtype=torch.float32, device=DEV)

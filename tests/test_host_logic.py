@@ -209,60 +209,66 @@ def test_gemm_plan_bench_shapes_pick_documented_decompositions():
         lib.vitk_set_sm_budget(prev)
 
 
-def _tail_plan(lib, I, J, R, b_mn):
+def _tail_plan(lib, I, J, R, b_mn, f32_out=0):
     import ctypes as C
     nw, nt, r0 = C.c_int(-1), C.c_int(-1), C.c_int(-1)
-    assert lib.vitk_gemm_tail_plan(I, J, R, b_mn, C.byref(nw), C.byref(nt), C.byref(r0)) == 0
+    assert lib.vitk_gemm_tail_plan(I, J, R, b_mn, f32_out, C.byref(nw), C.byref(nt), C.byref(r0)) == 0
     return nw.value, nt.value, r0.value
 
 
 def test_gemm_split_tail_plan():
-    """at bs 64 the deep J = 768 GEMMs (fc2 forward, fc1 dgrad, qkv dgrad: 150 tiles of 256 x 256 on 74 CTA
-    pairs = two waves + a wave of two tiles) keep 148 whole tiles and deal the 2 x kb k-blocks of the last two tiles out to all
-    74 clusters (mode 3); shallow reductions, well-filled last waves and reduced SM budgets keep the plain launch.  Whatever
-    the shape, the items of all clusters cover every (tile, k-block) exactly once, every whole tile is ONE item, and a
-    cluster's partial items come after its whole tiles."""
+    """at bs 64 the deep J = 768 dgrad GEMMs (fc1 dgrad, qkv dgrad: 150 tiles of 256 x 256 on 74 CTA pairs =
+    two waves + a wave of two tiles) keep 148 whole tiles and deal the 2 x kb k-blocks of the last two tiles out to all 74
+    clusters (mode 3); fc2 forward (fp32 staging: a 256-wide tile would leave a 4-stage ring) keeps three waves of 256 x 192;
+    shallow reductions, well-filled last waves and reduced SM budgets keep the plain launch.  Whatever the shape, the items of
+    all clusters cover every (tile, k-block) exactly once, every whole tile is ONE item, and a cluster's partial items come
+    before its whole tiles."""
     from vit_spoof_detection_pda_b200 import _lib as L
     lib = L.load()
     prev = lib.vitk_set_sm_budget(0)
     try:
         assert lib.vitk_gemm_tail_scratch_floats(768) == 1024 + 512 * 768
-        for (J, R, bmn) in ((768, 3072, 0), (768, 3072, 1), (768, 2304, 1)):     # fc2 forward, fc1 dgrad, qkv dgrad
+        for (J, R, bmn) in ((768, 3072, 1), (768, 2304, 1), (768, 3072, 0)):     # fc1 dgrad, qkv dgrad, (bf16-out forward)
             assert _tail_plan(lib, M64, J, R, bmn) == (148, 2, 49 * 256)
             plan, items = _plan(lib, M64, J, R, 2, bmn)
             assert (plan["mode"], plan["bn"], plan["cg"], plan["clusters"]) == (3, 256, 2, 74)
+        assert _tail_plan(lib, M64, 768, 3072, 0, f32_out=1)[1] == 0   # fc2 forward
+        plan, _ = _plan(lib, M64, 768, 3072, 3, 0)
+        assert (plan["mode"], plan["bn"], plan["cg"]) == (0, 192, 2)
         assert _tail_plan(lib, M64, 768, 768, 0)[1] == 0            # proj: 12 k-blocks, the fix-up costs what the wave costs
         assert _tail_plan(lib, M64, 3072, 768, 0)[1] == 0           # fc1 forward: shallow
-        assert _tail_plan(lib, 256 * 197, 768, 3072, 0)[1] == 0     # bs 256: 591 tiles = 7.99 waves
-        assert _tail_plan(lib, 197, 768, 3072, 0)[1] == 0           # bs 1
-        seen_mode3 = 0
+        assert _tail_plan(lib, 256 * 197, 768, 3072, 1)[1] == 0     # bs 256: 591 tiles = 7.99 waves
+        assert _tail_plan(lib, 197, 768, 3072, 1)[1] == 0           # bs 1
+        seen_mode3 = {0: 0, 1: 0}
         for batch in list(range(1, 70)) + [96, 128, 200]:
-            for J, R, bmn in ((768, 3072, 0), (768, 3072, 1), (768, 2304, 1), (1536, 4096, 1)):
+            for J, R, bmn, f32 in ((768, 3072, 0, 1), (768, 3072, 1, 0), (768, 2304, 1, 0), (1536, 4096, 1, 0), (768, 1536, 0, 1)):
                 I = batch * 197
-                nw, nt, r0 = _tail_plan(lib, I, J, R, bmn)
-                plan, items = _plan(lib, I, J, R, 2, bmn)
+                nw, nt, r0 = _tail_plan(lib, I, J, R, bmn, f32)
+                plan, items = _plan(lib, I, J, R, 3 if f32 else 2, bmn)
                 tiles = plan["tm"] * plan["tn"]
                 assert nw + nt == tiles
                 cover = {}
                 for cl in items:
-                    partial_seen = False
+                    whole_seen = False
                     for tile, kb0, kb1 in cl:
                         if tile >= nw:
-                            partial_seen = True
+                            assert not whole_seen
                         else:
-                            assert not partial_seen and (kb0, kb1) == (0, plan["kb"])
+                            whole_seen = True
+                            assert (kb0, kb1) == (0, plan["kb"])
                         for kb in range(kb0, kb1):
                             cover[(tile, kb)] = cover.get((tile, kb), 0) + 1
                 assert len(cover) == tiles * plan["kb"] and set(cover.values()) == {1}, (I, J, R, plan)
                 if nt:
-                    seen_mode3 += 1
+                    seen_mode3[f32] += 1
                     assert plan["mode"] == 3 and plan["kb"] >= 24 and nt * 4 <= 148 // plan["cg"]
                     assert nw % plan["clusters"] == 0 and r0 == (nw // plan["tn"]) * 128 * plan["cg"]
                     assert (I - r0) * J <= 512 * J        # the scratch rows the model provides
+                    assert not (f32 and plan["bn"] == 256 and plan["cg"] == 2)   # never a 4-stage ring for a split tail
                 else:
                     assert plan["mode"] == 0
-        assert seen_mode3 >= 10
+        assert seen_mode3[0] >= 10 and seen_mode3[1] >= 3, seen_mode3
         lib.vitk_set_sm_budget(116)
-        assert _tail_plan(lib, M64, 768, 3072, 0)[1] == 0           # 58 CTA pairs: 150 tiles = 2.6 waves, last wave well filled
+        assert _tail_plan(lib, M64, 768, 3072, 1)[1] == 0           # 58 CTA pairs: 150 tiles = 2.6 waves, last wave well filled
     finally:
         lib.vitk_set_sm_budget(prev)

@@ -81,7 +81,7 @@ PROTOTYPES = {
     "vitk_set_sm_budget": (i32, [i32]),
     "vitk_gemm_plan": (i32, [i32, i32, i32, i32, i32] + [C.POINTER(i32)] * 7),
     "vitk_gemm_plan_items": (i32, [i32, i32, i32, i32, i32, i32, C.POINTER(i32), i32]),
-    "vitk_gemm_tail_plan": (i32, [i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "vitk_gemm_tail_plan": (i32, [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "vitk_gemm_tail_scratch_floats": (sz, [i32]),
     "vitk_launch_count": (C.c_longlong, []),
     "vitk_prof_enable": (i32, [i32]),

@@ -65,8 +65,8 @@ struct TcParams {
   int32_t n_tiles_m, n_tiles_n, kb_total;
   int32_t streamk;          // 0: tile-strided, full K per tile; 1: contiguous (tile, k-block) unit range per CTA;
                             // 2: sliced split-K, CTA c owns k-slice c / tiles of tile c % tiles;
-                            // 3: split tail -- tiles [0, n_whole) tile-strided with the fused epilogue, then the (tile, k-block)
-                            //    units of the last tiles [n_whole, tiles) in contiguous ranges over ALL clusters (see tc_tail_plan)
+                            // 3: split tail -- the (tile, k-block) units of the last tiles [n_whole, tiles) in contiguous ranges
+                            //    over ALL clusters, then tiles [0, n_whole) tile-strided with the fused epilogue (tc_tail_plan)
   int64_t units_per_cta;    // stream-K: ceil(tiles * kb_total / gridDim.x); sliced split-K: number of k-slices; split tail:
                             // ceil((tiles - n_whole) * kb_total / gridDim.x)
   int32_t n_whole;          // split tail: number of whole-K tiles
@@ -412,7 +412,7 @@ struct TcWorkIter {
     const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n;
     stride = n_clusters;
     tcur = tend = 0;
-    if (p.streamk == 3) {          // whole tiles first, then one contiguous range of the tail's units
+    if (p.streamk == 3) {          // one contiguous range of the tail's units, then whole tiles
       cur = cluster;
       end = p.n_whole;
       const int64_t total = (tiles - p.n_whole) * p.kb_total;
@@ -438,19 +438,21 @@ struct TcWorkIter {
   }
   __host__ __device__ __forceinline__ bool next_raw(const TcParams& p, TcWork& w) {
     if (p.streamk == 3) {
-      if (cur < end) {             // whole-K tile, fused epilogue
-        w.tile = (int)cur;
-        w.kb0 = 0;
-        w.kb1 = p.kb_total;
-        cur += stride;
+      // this cluster's share of the tail tiles FIRST (w.tile >= p.n_whole): the fix-up behind a partial item -- fence, ticket,
+      // the last arriver's read-back and epilogue -- then runs under the mainloop of the cluster's first whole tile
+      if (tcur < tend) {
+        w.tile = p.n_whole + (int)(tcur / p.kb_total);
+        w.kb0 = (int)(tcur % p.kb_total);
+        const int64_t left = tend - tcur;
+        w.kb1 = (int)((int64_t)(p.kb_total - w.kb0) < left ? p.kb_total : w.kb0 + left);
+        tcur += w.kb1 - w.kb0;
         return true;
       }
-      if (tcur >= tend) return false;
-      w.tile = p.n_whole + (int)(tcur / p.kb_total);    // partial item of a tail tile (w.tile >= p.n_whole)
-      w.kb0 = (int)(tcur % p.kb_total);
-      const int64_t left = tend - tcur;
-      w.kb1 = (int)((int64_t)(p.kb_total - w.kb0) < left ? p.kb_total : w.kb0 + left);
-      tcur += w.kb1 - w.kb0;
+      if (cur >= end) return false;
+      w.tile = (int)cur;             // whole-K tile, fused epilogue
+      w.kb0 = 0;
+      w.kb1 = p.kb_total;
+      cur += stride;
       return true;
     }
     if (cur >= end) return false;
@@ -730,11 +732,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int row0 = i0 + q * 32;
         const bool active = row0 < p.I;   // warps whose 32 rows are all past the end of the matrix have nothing to do
         if (p.streamk == 3 && w.tile >= p.n_whole) {
-          // ---- partial item of a tail tile (always after this cluster's whole tiles): this warp's 32 rows x BN/2 columns
+          // ---- partial item of a tail tile (always before this cluster's whole tiles): this warp's 32 rows x BN/2 columns
           // of the partial accumulator are added to the fp32 scratch; the warp that completes a region -- the last of the
           // clusters sharing the tile to arrive at the region's ticket -- reads the sums back, clears them and applies
           // the epilogue with per-thread global IO (epilogue_rows8: the same arithmetic as the fused TMA epilogue).
-          if (lane == 0) bulk_wait_read<0>();      // the staging tiles double as the transpose buffer: stores have read them out
+          if (lane == 0) bulk_wait_read<0>();      // the staging tiles double as the transpose buffer (no store is reading them)
           __syncwarp();
           mbar_wait(tfull_bar(acc), acc_phase);
           tc_fence_after();
@@ -797,6 +799,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           }
+          fence_proxy_async_smem();   // generic-proxy use of the staging tiles is ordered before the TMA loads / stores that follow
+          __syncwarp();
           continue;
         }
         // ---- before the accumulator is ready: bias values of this warp's columns, and the first second-operand tile
@@ -1100,8 +1104,16 @@ static int epilogue_kind(const EpiParams& ep) {
 // then fp32 [rows of the tail tiles][J].
 constexpr int TC_TAIL_TICKETS = 1024;
 struct TcTailPlan { int n_whole, tail_row0; int64_t units_per_cluster; };
-static bool tc_tail_plan(int I, int J, int R, int BN, int CG, int64_t scratch_floats, TcTailPlan* tp) {
+// f32_out: the epilogue kind stages fp32 tiles (8 KB per epilogue warp) -- with 256-wide tiles that leaves a 4-stage operand
+// ring, measured 40 % slower per k-block than the 5-stage 192-wide configuration (fc2 forward, bs 64: 73 vs 66 us in-step):
+// a split tail never justifies a ring shallower than 5 stages.
+static bool tc_tail_plan(int I, int J, int R, int BN, int CG, bool f32_out, int64_t scratch_floats, TcTailPlan* tp) {
   if (g_tc_debug[9] == 1 || scratch_floats <= TC_TAIL_TICKETS) return false;
+  {
+    const int tail_bytes = TC_EPI_WARPS * (int)tc_epi_warp_bytes(f32_out ? 2 /*EK_STORE_F32*/ : 1 /*EK_STORE_BF16*/) + TC_EPI_WARPS * 512 + 512;
+    const int stage_bytes = (int)TC_A_STAGE_BYTES + (BN / CG) * TC_BK * 2;
+    if ((227 * 1024 - 1024 - tail_bytes) / stage_bytes < 5) return false;
+  }
   const int kb = (R + TC_BK - 1) / TC_BK;
   const int rows_per_tile = TC_BM * CG;
   const int tiles_n = J / BN, tiles_m = (I + rows_per_tile - 1) / rows_per_tile;
@@ -1120,7 +1132,7 @@ static bool tc_tail_plan(int I, int J, int R, int BN, int CG, int64_t scratch_fl
 
 // ---- work decomposition (pure host logic; p.I / p.J / p.R set).  Returns the number of clusters (CTAs / CG) to launch.
 // tail_floats > 0: a non-accumulating GEMM whose epilogue mode permits the split tail, with that much scratch.
-static int tc_decompose(TcParams& p, bool accumulate, int BN, int CG, int64_t tail_floats = 0) {
+static int tc_decompose(TcParams& p, bool accumulate, int BN, int CG, int64_t tail_floats = 0, bool f32_out = false) {
   p.n_tiles_m = (p.I + TC_BM * CG - 1) / (TC_BM * CG);
   p.n_tiles_n = p.J / BN;
   p.kb_total = (p.R + TC_BK - 1) / TC_BK;
@@ -1132,7 +1144,7 @@ static int tc_decompose(TcParams& p, bool accumulate, int BN, int CG, int64_t ta
   p.n_whole = tiles;
   p.tail_row0 = 0;
   TcTailPlan tp;
-  if (!accumulate && tail_floats > 0 && tc_tail_plan(p.I, p.J, p.R, BN, CG, tail_floats, &tp)) {
+  if (!accumulate && tail_floats > 0 && tc_tail_plan(p.I, p.J, p.R, BN, CG, f32_out, tail_floats, &tp)) {
     p.streamk = 3;
     p.n_whole = tp.n_whole;
     p.tail_row0 = tp.tail_row0;
@@ -1168,7 +1180,8 @@ static int tc_decompose(TcParams& p, bool accumulate, int BN, int CG, int64_t ta
 // M = B*197 the tile count is rarely a multiple of the slot count (12608 x 768 on 74 CTA pairs: 150 tiles of 256x256 =
 // 3 waves for 2.03 waves of work, 200 tiles of 256x192 = 3 waves of 7/8 the bytes).  With a tail scratch (tail_floats > 0) a
 // nearly empty last wave costs only its share of k-blocks plus a fixed fix-up (tc_tail_plan): 150 tiles = 2 waves + 2 k-blocks.
-static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* bn_out, int* cg_out, int64_t tail_floats = 0) {
+static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* bn_out, int* cg_out, int64_t tail_floats = 0,
+                         bool f32_out = false) {
   int cg = 0, bn = 0;
   const int forced_bn = (g_tc_debug[2] == 128 || g_tc_debug[2] == 192 || g_tc_debug[2] == 256) ? g_tc_debug[2] : 0;
   if (accumulate) {
@@ -1192,7 +1205,7 @@ static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* b
         const double per_kb = ingest > mma ? ingest : mma;
         double cost = (double)waves * ((double)kb * per_kb + 1200.0);
         TcTailPlan tp;
-        if (tail_floats > 0 && tc_tail_plan(I, J, R, cand, c, tail_floats, &tp))
+        if (tail_floats > 0 && tc_tail_plan(I, J, R, cand, c, f32_out, tail_floats, &tp))
           cost = (double)(tiles / slots) * ((double)kb * per_kb + 1200.0) + (double)tp.units_per_cluster * per_kb + 6000.0;
         if (best < 0.0 || cost < best) { best = cost; bn = cand; cg = c; }
       }
@@ -1260,7 +1273,8 @@ static int launch_tc(const GemmProblem& pr, cudaStream_t st) {
     if (b_mn) { p.b_sbo = TC_BK * 128; p.b_lbo = 1024; }
   }
 #endif
-  const int grid = tc_decompose(p, pr.ep.mode == E_ACCUM, BN, CG, EK == EK_LEGACY ? 0 : tail_floats_of(pr));
+  const int grid = tc_decompose(p, pr.ep.mode == E_ACCUM, BN, CG, EK == EK_LEGACY ? 0 : tail_floats_of(pr),
+                                EK == EK_STORE_F32 || EK == EK_RESIDUAL);
   p.tail_tickets = reinterpret_cast<int*>(pr.tail_scratch);
   p.tail_acc = pr.tail_scratch ? pr.tail_scratch + TC_TAIL_TICKETS : nullptr;
   p.ep = pr.ep;
@@ -1310,7 +1324,8 @@ int gemm_tc(const GemmProblem& pr, cudaStream_t st) {
   const bool b_mn = pr.lb.s_row == 1 && pr.lb.s_col != 1;   // MN-major B: staged in 64-row atoms
   int cg = 0, bn = 0;
   const int ek = epilogue_kind(pr.ep);
-  tc_pick_tile(pr.I, pr.J, pr.R, pr.ep.mode == E_ACCUM, b_mn, &bn, &cg, ek == EK_LEGACY ? 0 : tail_floats_of(pr));
+  tc_pick_tile(pr.I, pr.J, pr.R, pr.ep.mode == E_ACCUM, b_mn, &bn, &cg, ek == EK_LEGACY ? 0 : tail_floats_of(pr),
+               ek == EK_STORE_F32 || ek == EK_RESIDUAL);
   if (bn == 0 || pr.J % bn != 0) { set_error("gemm_tc: no BLOCK_N divides J=%d", pr.J); return VITK_ERR_UNSUPPORTED; }
   if (pr.ep.colsum && !(ek == EK_GELU_BWD || (ek == EK_STORE_BF16 && !pr.ep.bias) || pr.ep.mode == E_GELU_BWD)) {
     set_error("gemm_tc: fused column sums need the TMA epilogue of a bias-free bf16 store or of the GELU' multiply");
@@ -1338,12 +1353,12 @@ extern "C" int vitk_gemm_plan(int I, int J, int R, int accumulate, int b_mn_majo
                               int* n_clusters, int* n_tiles_m, int* n_tiles_n, int* kb_total) {
   VITK_CHECK_ARG(I > 0 && J > 0 && R > 0 && J % 128 == 0);
   int bn = 0, cg = 0;
-  const int64_t tail_floats = accumulate == 2 ? vitk::plan_tail_floats(J) : 0;   // 2: no accumulation, tail scratch available
-  vitk::tc_pick_tile(I, J, R, accumulate == 1, b_mn_major != 0, &bn, &cg, tail_floats);
+  const int64_t tail_floats = accumulate >= 2 ? vitk::plan_tail_floats(J) : 0;   // 2 / 3: no accumulation, tail scratch, bf16 / fp32 out
+  vitk::tc_pick_tile(I, J, R, accumulate == 1, b_mn_major != 0, &bn, &cg, tail_floats, accumulate == 3);
   if (bn == 0 || J % bn != 0) { vitk::set_error("vitk_gemm_plan: no BLOCK_N divides J=%d", J); return VITK_ERR_UNSUPPORTED; }
   vitk::TcParams p{};
   p.I = I; p.J = J; p.R = R;
-  const int grid = vitk::tc_decompose(p, accumulate == 1, bn, cg, tail_floats);
+  const int grid = vitk::tc_decompose(p, accumulate == 1, bn, cg, tail_floats, accumulate == 3);
   if (block_n) *block_n = bn;
   if (cta_group) *cta_group = cg;
   if (mode) *mode = p.streamk;
@@ -1357,12 +1372,12 @@ extern "C" int vitk_gemm_plan(int I, int J, int R, int accumulate, int b_mn_majo
 extern "C" int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_mn_major, int cluster, int* items, int max_items) {
   if (!(I > 0 && J > 0 && R > 0 && J % 128 == 0 && items && max_items > 0)) return -VITK_ERR_ARG;
   int bn = 0, cg = 0;
-  const int64_t tail_floats = accumulate == 2 ? vitk::plan_tail_floats(J) : 0;
-  vitk::tc_pick_tile(I, J, R, accumulate == 1, b_mn_major != 0, &bn, &cg, tail_floats);
+  const int64_t tail_floats = accumulate >= 2 ? vitk::plan_tail_floats(J) : 0;
+  vitk::tc_pick_tile(I, J, R, accumulate == 1, b_mn_major != 0, &bn, &cg, tail_floats, accumulate == 3);
   if (bn == 0 || J % bn != 0) return -VITK_ERR_UNSUPPORTED;
   vitk::TcParams p{};
   p.I = I; p.J = J; p.R = R;
-  const int grid = vitk::tc_decompose(p, accumulate == 1, bn, cg, tail_floats);
+  const int grid = vitk::tc_decompose(p, accumulate == 1, bn, cg, tail_floats, accumulate == 3);
   if (cluster < 0 || cluster >= grid) return -VITK_ERR_ARG;
   vitk::TcWorkIter wi;
   wi.init(p, cluster, grid);
@@ -1377,15 +1392,15 @@ extern "C" int vitk_gemm_plan_items(int I, int J, int R, int accumulate, int b_m
 // Host-only view of the split tail (no launch) for a non-accumulating GEMM given a scratch of vitk_gemm_tail_scratch_floats(J)
 // floats: *n_whole = tiles that stay whole-K items with the fused epilogue, *n_tail = tiles whose k-blocks are dealt out to
 // all clusters (0: plain tile-strided launch), *tail_row0 = first matrix row of the first tail tile.
-extern "C" int vitk_gemm_tail_plan(int I, int J, int R, int b_mn_major, int* n_whole, int* n_tail, int* tail_row0) {
+extern "C" int vitk_gemm_tail_plan(int I, int J, int R, int b_mn_major, int f32_out, int* n_whole, int* n_tail, int* tail_row0) {
   VITK_CHECK_ARG(I > 0 && J > 0 && R > 0 && J % 128 == 0 && n_whole && n_tail && tail_row0);
   int bn = 0, cg = 0;
   const int64_t tail_floats = vitk::plan_tail_floats(J);
-  vitk::tc_pick_tile(I, J, R, false, b_mn_major != 0, &bn, &cg, tail_floats);
+  vitk::tc_pick_tile(I, J, R, false, b_mn_major != 0, &bn, &cg, tail_floats, f32_out != 0);
   if (bn == 0 || J % bn != 0) { vitk::set_error("vitk_gemm_tail_plan: no BLOCK_N divides J=%d", J); return VITK_ERR_UNSUPPORTED; }
   vitk::TcParams p{};
   p.I = I; p.J = J; p.R = R;
-  vitk::tc_decompose(p, false, bn, cg, tail_floats);
+  vitk::tc_decompose(p, false, bn, cg, tail_floats, f32_out != 0);
   *n_whole = p.n_whole;
   *n_tail = p.n_tiles_m * p.n_tiles_n - p.n_whole;
   *tail_row0 = p.streamk == 3 ? p.tail_row0 : 0;
