@@ -261,6 +261,38 @@ def test_split_tail_dgrad_other_batches(batch):
     assert int(torch.count_nonzero(scratch)) == 0
 
 
+def test_split_tail_shallow_reductions_behind_knob():
+    """vitk_debug_set(9, 12) lowers the depth threshold of the split tail from 24 to 12 k-blocks (A/B knob): qkv forward (head-
+    major scatter epilogue, 450 tiles = 6 waves + 6 tiles) and fc1 forward (bias + GELU, two outputs, 600 tiles = 8 waves + 8
+    tiles) then take it too -- the last arriver's per-thread epilogue implements every mode."""
+    E = L.ENGINE_TCGEN05
+    lib = L.load()
+    scratch = _tail_scratch()
+    x = _randn(M, 768, seed=71).to(torch.bfloat16)
+    lib.vitk_debug_set(9, 12)
+    try:
+        assert _tail_plan(M, 2304, 768, 0)[1] == 6 and _tail_plan(M, 3072, 768, 0)[1] == 8
+        w = _randn(2304, 768, seed=72, scale=0.03).to(torch.bfloat16)
+        b = _randn(2304, seed=73, scale=0.5)
+        ref = x.float() @ w.float().t() + b
+        plain = K.from_headmajor(K.linear_fwd(x, w, b, L.EPI_QKV_SCATTER, E)).float()
+        for _ in range(3):
+            y = K.from_headmajor(K.linear_fwd(x, w, b, L.EPI_QKV_SCATTER, E, scratch=scratch)).float()
+            assert K.rel_err(y, ref) < 2e-2 and float((y - plain).abs().max()) <= 2e-2 * float(ref.abs().max())
+        w1 = _randn(3072, 768, seed=74, scale=0.03).to(torch.bfloat16)
+        b1 = _randn(3072, seed=75, scale=0.5)
+        g0, d0 = K.linear_fwd(x, w1, b1, L.EPI_BIAS_GELU, E)
+        for _ in range(3):
+            g, dg = K.linear_fwd(x, w1, b1, L.EPI_BIAS_GELU, E, scratch=scratch)
+            # the tail rows apply erf-GELU to the same bf16-rounded pre-activation the fused epilogue's fast GELU sees
+            assert float((g.float() - g0.float()).abs().max()) <= 2e-2 * float(g0.float().abs().max())
+            assert float((dg.float() - d0.float()).abs().max()) <= 2e-2
+        torch.cuda.synchronize()
+        assert int(torch.count_nonzero(scratch)) == 0
+    finally:
+        lib.vitk_debug_set(9, 0)
+
+
 def test_attention_bs64_vs_sdpa():
     """the full-size attention grids (768 (batch, head) items on 148 persistent CTAs: 5.2 items per CTA)."""
     qkv = _randn(M, 2304, seed=41, scale=1.0).to(torch.bfloat16)

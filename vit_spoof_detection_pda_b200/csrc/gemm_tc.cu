@@ -1032,7 +1032,7 @@ static int make_operand_map(const void* base, const MatLayout& l, int rows, int 
 
 // Tuning overrides (vitk_debug_set): process-wide, for tests and A/B timing; every one of them yields valid results.
 //   1 whole-K tiles for accumulate GEMMs, 2 forced BLOCK_N, 4 CTA group, 5 per-thread epilogue IO, 6 no programmatic
-//   dependent launch, 9 no row-tail split, 13 stream-K instead of sliced split-K (> 1: fill threshold in percent).
+//   dependent launch, 9 split tail (1: off, n > 1: minimum reduction depth in k-blocks instead of 24), 13 stream-K instead of sliced split-K (> 1: fill threshold in percent).
 // Development build only (libvitk_dev.so): 0 swap LBO/SBO of MN-major operands, 7 timing-only bit mask (results INVALID),
 //   12 whole qkv bias gradient from the attention kernel.
 static int g_tc_debug[16] = {0};
@@ -1119,7 +1119,8 @@ static bool tc_tail_plan(int I, int J, int R, int BN, int CG, bool f32_out, int6
   const int tiles_n = J / BN, tiles_m = (I + rows_per_tile - 1) / rows_per_tile;
   const int tiles = tiles_m * tiles_n, slots = sm_count() / CG;
   const int full = tiles / slots, rem = tiles % slots;
-  if (kb < 24 || full < 1 || rem == 0 || rem * 4 > slots) return false;
+  const int min_kb = g_tc_debug[9] > 1 ? g_tc_debug[9] : 24;     // knob 9 = n > 1: A/B of the depth threshold
+  if (kb < min_kb || full < 1 || rem == 0 || rem * 4 > slots) return false;
   const int n_whole = tiles - rem;
   const int tail_row0 = (n_whole / tiles_n) * rows_per_tile;
   if ((int64_t)(I - tail_row0) * J > scratch_floats - TC_TAIL_TICKETS) return false;
@@ -1216,11 +1217,11 @@ static void tc_pick_tile(int I, int J, int R, bool accumulate, bool b_mn, int* b
 }
 
 // epilogue modes whose partial items the kernel's per-thread fix-up path may finish (epilogue_rows8 implements every mode; the
-// fused column sums and the two-output GELU epilogue stay whole-tile only)
+// epilogues with fused column sums stay whole-tile only)
 static int64_t plan_tail_floats(int J) { return (int64_t)TC_TAIL_TICKETS + (int64_t)512 * J; }
 static int64_t tail_floats_of(const GemmProblem& pr) {
   if (!pr.tail_scratch || pr.ep.colsum || ((uintptr_t)pr.tail_scratch & 15)) return 0;
-  if (!(pr.ep.mode == E_BIAS_RESIDUAL || pr.ep.mode == E_STORE)) return 0;
+  if (!(pr.ep.mode == E_BIAS_RESIDUAL || pr.ep.mode == E_STORE || pr.ep.mode == E_BIAS_GELU || pr.ep.mode == E_QKV_SCATTER)) return 0;
   return pr.tail_scratch_floats;
 }
 

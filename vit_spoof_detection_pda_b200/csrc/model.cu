@@ -272,14 +272,14 @@ extern "C" int vitk_model_fwd(const vitk_model* m, void* stream) {
     float* lse = c.save ? (float*)c.at(pl.lse, pl.lse_stride, l) : nullptr;
 
     VITK_TRY(vitk_layernorm_fwd(x, D, c.P(b.n1w), c.P(b.n1b), ln1, dt, mean1, rstd1, M, 1e-6f, st));
-    VITK_TRY(vitk_linear_fwd(ln1, VITK_LAYOUT_ROWMAJOR, c.W(b.qkvw), c.P(b.qkvb), qkv, nullptr, M, 3 * D, D,
-                             VITK_EPI_QKV_SCATTER, dt, eng, st));
+    VITK_TRY(vitk_linear_fwd_ws(ln1, VITK_LAYOUT_ROWMAJOR, c.W(b.qkvw), c.P(b.qkvb), qkv, nullptr, M, 3 * D, D,
+                                VITK_EPI_QKV_SCATTER, dt, eng, c.tail, c.tail_floats, st));
     VITK_TRY(attn_fwd_dispatch(qkv, ao, lse, m->batch, dt, eng, c.st));
     VITK_TRY(vitk_linear_fwd(ao, VITK_LAYOUT_ROWMAJOR, c.W(b.projw), c.P(b.projb), xmid, x, M, D, D,
                              VITK_EPI_BIAS_RESIDUAL, dt, eng, st));
     VITK_TRY(vitk_layernorm_fwd(xmid, D, c.P(b.n2w), c.P(b.n2b), ln2, dt, mean2, rstd2, M, 1e-6f, st));
-    VITK_TRY(vitk_linear_fwd(ln2, VITK_LAYOUT_ROWMAJOR, c.W(b.fc1w), c.P(b.fc1b), g, u, M, MLP, D,
-                             VITK_EPI_BIAS_GELU, dt, eng, st));
+    VITK_TRY(vitk_linear_fwd_ws(ln2, VITK_LAYOUT_ROWMAJOR, c.W(b.fc1w), c.P(b.fc1b), g, u, M, MLP, D,
+                                VITK_EPI_BIAS_GELU, dt, eng, c.tail, c.tail_floats, st));
     VITK_TRY(vitk_linear_fwd_ws(g, VITK_LAYOUT_ROWMAJOR, c.W(b.fc2w), c.P(b.fc2b), xout, xmid, M, D, MLP,
                                 VITK_EPI_BIAS_RESIDUAL, dt, eng, c.tail, c.tail_floats, st));
   }
