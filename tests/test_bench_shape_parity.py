@@ -166,15 +166,23 @@ def _tail_scratch():
     return torch.zeros(L.load().vitk_gemm_tail_scratch_floats(768), dtype=torch.float32, device=DEV)
 
 
-@pytest.mark.parametrize("which", ["fc1_dgrad", "qkv_dgrad", "bf16_fwd"])
+@pytest.mark.parametrize("which", ["fc2_fwd", "fc1_dgrad", "qkv_dgrad", "bf16_fwd"])
 def test_split_tail_m12608(which):
-    """The deep J = 768 bf16-output GEMMs of a bs-64 step with the split tail (vitk_linear_*_ws: 148 whole tiles with the fused
+    """The deep J = 768 GEMMs of a bs-64 step with the split tail (vitk_linear_*_ws: 148 whole tiles with the fused
     epilogue, the k-blocks of the last two tiles dealt out to all 74 CTA pairs, last-arriver epilogue) against the fp32 product
     AND against the plain launch; the scratch (tickets + partial sums) comes back all zero, five times in a row -- it is
     reused by the next GEMM of the step."""
     E = L.ENGINE_TCGEN05
     scratch = _tail_scratch()
-    if which == "bf16_fwd":
+    if which == "fc2_fwd":
+        x = _randn(M, 3072, seed=51).to(torch.bfloat16)
+        w = _randn(768, 3072, seed=52, scale=0.03).to(torch.bfloat16)
+        b = _randn(768, seed=53, scale=0.5)
+        res = _randn(M, 768, seed=54)
+        plan = _tail_plan(M, 768, 3072, 0, 1)
+        ref = x.float() @ w.float().t() + b + res
+        run = lambda s: K.linear_fwd(x, w, b, L.EPI_BIAS_RESIDUAL, E, residual=res, scratch=s)   # noqa: E731
+    elif which == "bf16_fwd":
         x = _randn(M, 3072, seed=51).to(torch.bfloat16)
         w = _randn(768, 3072, seed=52, scale=0.03).to(torch.bfloat16)
         b = _randn(768, seed=53, scale=0.5)
@@ -211,9 +219,9 @@ def test_split_tail_m12608(which):
 
 @pytest.mark.parametrize("batch", [32, 33, 49, 50])
 def test_split_tail_fp32_residual_epilogue(batch):
-    """fc2 forward (bias + fp32 residual, fp32 out) at the batch sizes whose tile grids take a split tail with a >= 5-stage
-    ring: 256 x 128 tiles with 2 / 8 tail tiles (bs 32 / 33), 256 x 192 tiles with 4 / 8 tail tiles (bs 49 / 50) -- cluster
-    ranges that straddle tail tiles, tails that start in the middle of a tile row."""
+    """fc2 forward (bias + fp32 residual, fp32 out) at other tail geometries: 256 x 256 tiles (single fp32 staging slot) with
+    1 / 4 tail tiles (bs 32 / 33), 256 x 192 tiles (two slots) with 4 / 8 tail tiles (bs 49 / 50) -- cluster ranges that
+    straddle tail tiles, tails that start in the middle of a tile row."""
     E = L.ENGINE_TCGEN05
     Mb = batch * 197
     nw, nt, r0 = _tail_plan(Mb, 768, 3072, 0, 1)

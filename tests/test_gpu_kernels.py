@@ -288,6 +288,24 @@ def test_focal_per_class_alpha():
     assert K.rel_err(zz.grad.cpu(), zr.grad) < FP32_TOL
 
 
+def test_focal_out_of_range_target_is_nan_not_oob():
+    """A label outside [0, C) (F.cross_entropy device-asserts; ignore_index is not supported): that sample's loss and gradient
+    become NaN and alpha[y] is never read out of bounds; the other samples are untouched (head_loss.cu)."""
+    import vit_spoof_detection_pda_b200 as pkg
+    z = randn(8, 2, seed=73, scale=2.0)
+    t = torch.randint(0, 2, (8,), generator=_g(74), device=DEV)
+    good = pkg.FocalLoss(0.25, 2.0, reduction="none")(z, t)
+    for bad in (-100, 2, 7):
+        tb = t.clone()
+        tb[3] = bad
+        zz = z.clone().requires_grad_(True)
+        per = pkg.FocalLoss(0.25, 2.0, reduction="none")(zz, tb)
+        per.sum().backward()
+        assert torch.isnan(per[3]) and torch.isnan(zz.grad[3]).all()
+        keep = [i for i in range(8) if i != 3]
+        assert torch.equal(per[keep], good[keep]) and torch.isfinite(zz.grad[keep]).all()
+
+
 # ------------------------------------------------------------------ fused Adam / AdamW / clip vs torch.optim
 @pytest.mark.parametrize("adamw,lr,wd", [(True, 3e-4, 0.05), (False, 1e-5, 1e-4)])
 @pytest.mark.parametrize("clip", [None, 1.0])

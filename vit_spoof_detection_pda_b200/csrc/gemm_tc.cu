@@ -374,13 +374,19 @@ __device__ __forceinline__ void epilogue_rows8(const EpiParams& ep, int i, int j
 enum { EK_LEGACY = 0, EK_STORE_BF16 = 1, EK_STORE_F32 = 2, EK_GELU = 3, EK_RESIDUAL = 4, EK_SCATTER = 5, EK_GELU_BWD = 6 };
 // staging per epilogue warp: two 4 KB slots for fp32 tiles, two 2 KB slots for bf16 tiles (EK_GELU: one slot pair g | u).
 // Every KB not spent here is operand-ring depth: the mainloop needs ~1.5 us of loads in flight to ride out DRAM latency.
-__host__ __device__ constexpr uint32_t tc_epi_warp_bytes(int ek) { return (ek == EK_STORE_F32 || ek == EK_RESIDUAL) ? 8192u : 4096u; }
+// Under 256-wide CTA-pair tiles (32 KB stages) the second fp32 slot would cost the ring its fifth stage -- measured 20 % per
+// k-block (fc2 forward at bs 64: 35 us per wave with 4 stages against 29 us of equal work with 256 x 192 tiles and 5) -- so
+// those kernels stage through ONE slot per warp: the chunks of a tile then serialise on their TMA store / load round trips,
+// which the 20+ us mainloop of the next tile hides (double-buffered accumulators).
+__host__ __device__ constexpr uint32_t tc_epi_warp_bytes(int ek, int bn, int cg) {
+  return (ek == EK_STORE_F32 || ek == EK_RESIDUAL) ? ((bn == 256 && cg == 2) ? 4096u : 8192u) : 4096u;
+}
 
 template <int BN, int CG, int EK> struct TcCfg {
   static constexpr int B_ROWS = BN / CG;                                   // rows of the B tile this CTA stages
   static constexpr uint32_t B_STAGE_BYTES = B_ROWS * TC_BK * 2;
   static constexpr uint32_t STAGE_BYTES = TC_A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr uint32_t EPI_WARP_BYTES = tc_epi_warp_bytes(EK);
+  static constexpr uint32_t EPI_WARP_BYTES = tc_epi_warp_bytes(EK, BN, CG);
   static constexpr uint32_t TAIL_BYTES = TC_EPI_WARPS * EPI_WARP_BYTES + TC_EPI_WARPS * 512 + 512;  // staging | bias | barriers
   static constexpr int STAGES_FIT = (227 * 1024 - 1024 - (int)TAIL_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
@@ -723,6 +729,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t kTileBytes = kF32 ? 4096u : 2048u;
       constexpr int NCH = BN / 64;                                             // 32-column chunks per warp and tile
       constexpr uint32_t kSlotBytes = kF32 ? 4096u : 2048u;
+      constexpr bool kOneSlot = kF32 && Cfg::EPI_WARP_BYTES == 4096u;          // see tc_epi_warp_bytes
       const uint32_t stg = smem_base + Cfg::EPI_OFF + (uint32_t)we * Cfg::EPI_WARP_BYTES;   // slot s at stg + s * kSlotBytes
       const uint32_t sbias = smem_base + Cfg::BIAS_OFF + (uint32_t)we * 512;
       uint32_t eph = 0;            // phase bits of this warp's two load barriers
@@ -833,9 +840,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 1
         for (int k = 0; k < NCH; ++k) {
           const int col = j0 + (half + 2 * k) * 32;
-          const uint32_t s = (EK == EK_GELU) ? 0u : slot;   // EK_GELU: both 2 KB slots hold one chunk (g | g')
-          slot ^= 1;
-          if constexpr (kLoads) {
+          const uint32_t s = (EK == EK_GELU || kOneSlot) ? 0u : slot;   // EK_GELU: both 2 KB slots hold one chunk (g | g')
+          if constexpr (!kOneSlot) slot ^= 1;
+          if constexpr (kLoads && !kOneSlot) {
             if (k + 1 < NCH && lane == 0) {
               bulk_wait_read<0>();     // chunk k-1's store (slot s^1) has been read out
               issue_load(k + 1, s ^ 1);
@@ -859,7 +866,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // the staging slot is reusable once the TMA store that last read it has drained it (two chunks ago; EK_GELU: the
           // previous chunk) -- checked as late as possible, after this chunk's math, so the drain overlaps it
           auto slot_ready = [&]() {
-            if (lane == 0) { if constexpr (EK == EK_GELU) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
+            if (lane == 0) { if constexpr (EK == EK_GELU || kOneSlot) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
             __syncwarp();
           };
           if constexpr (kLoads) {
@@ -937,6 +944,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
             bulk_commit();
+            if constexpr (kLoads && kOneSlot) {
+              if (k + 1 < NCH) {         // single slot: the next chunk's second operand may land once this store has read the slot
+                bulk_wait_read<0>();
+                issue_load(k + 1, 0u);
+              }
+            }
           }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -1104,13 +1117,12 @@ static int epilogue_kind(const EpiParams& ep) {
 // then fp32 [rows of the tail tiles][J].
 constexpr int TC_TAIL_TICKETS = 1024;
 struct TcTailPlan { int n_whole, tail_row0; int64_t units_per_cluster; };
-// f32_out: the epilogue kind stages fp32 tiles (8 KB per epilogue warp) -- with 256-wide tiles that leaves a 4-stage operand
-// ring, measured 40 % slower per k-block than the 5-stage 192-wide configuration (fc2 forward, bs 64: 73 vs 66 us in-step):
-// a split tail never justifies a ring shallower than 5 stages.
+// f32_out: the epilogue kind stages fp32 tiles (tc_epi_warp_bytes).  A split tail never justifies an operand ring shallower than
+// 5 stages (fc2 forward at bs 64 with a 4-stage ring: 73 us in-step against 66 us for three waves of 256 x 192 tiles).
 static bool tc_tail_plan(int I, int J, int R, int BN, int CG, bool f32_out, int64_t scratch_floats, TcTailPlan* tp) {
   if (g_tc_debug[9] == 1 || scratch_floats <= TC_TAIL_TICKETS) return false;
   {
-    const int tail_bytes = TC_EPI_WARPS * (int)tc_epi_warp_bytes(f32_out ? 2 /*EK_STORE_F32*/ : 1 /*EK_STORE_BF16*/) + TC_EPI_WARPS * 512 + 512;
+    const int tail_bytes = TC_EPI_WARPS * (int)tc_epi_warp_bytes(f32_out ? EK_STORE_F32 : EK_STORE_BF16, BN, CG) + TC_EPI_WARPS * 512 + 512;
     const int stage_bytes = (int)TC_A_STAGE_BYTES + (BN / CG) * TC_BK * 2;
     if ((227 * 1024 - 1024 - tail_bytes) / stage_bytes < 5) return false;
   }
