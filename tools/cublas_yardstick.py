@@ -33,6 +33,10 @@ res = [torch.randn(M, 768, device=DEV) for _ in range(NCOPY)]
 w_fc1, w_fc2, w_proj, w_qkv = rnd(3072, 768, scale=.05), rnd(768, 3072, scale=.05), rnd(768, 768, scale=.05), rnd(2304, 768, scale=.05)
 b3072, b768, b2304 = torch.randn(3072, device=DEV), torch.randn(768, device=DEV), torch.randn(2304, device=DEV)
 
+# the training-mode configuration: a zeroed scratch lets the deep J = 768 GEMMs take the split tail;
+# SCRATCH=0 times the plain launches (eval mode)
+SCR = None if os.environ.get("SCRATCH") == "0" else torch.zeros(L.load().vitk_gemm_tail_scratch_floats(768), dtype=torch.float32, device=DEV)
+
 _dw = {}
 
 
@@ -49,11 +53,11 @@ CASES = [
     ("qkv fwd   12608x2304x768", 2304 * 768, lambda i: K.linear_fwd(x768[i], w_qkv, b2304, L.EPI_QKV_SCATTER, E), lambda i: x768[i] @ w_qkv.t()),
     ("proj fwd  12608x768x768", 768 * 768, lambda i: K.linear_fwd(x768[i], w_proj, b768, L.EPI_BIAS_RESIDUAL, E, residual=res[i]), lambda i: x768[i] @ w_proj.t()),
     ("fc1 fwd   12608x3072x768", 3072 * 768, lambda i: K.linear_fwd(x768[i], w_fc1, b3072, L.EPI_BIAS_GELU, E), lambda i: x768[i] @ w_fc1.t()),
-    ("fc2 fwd   12608x768x3072", 768 * 3072, lambda i: K.linear_fwd(x3072[i], w_fc2, b768, L.EPI_BIAS_RESIDUAL, E, residual=res[i]), lambda i: x3072[i] @ w_fc2.t()),
+    ("fc2 fwd   12608x768x3072", 768 * 3072, lambda i: K.linear_fwd(x3072[i], w_fc2, b768, L.EPI_BIAS_RESIDUAL, E, residual=res[i], scratch=SCR), lambda i: x3072[i] @ w_fc2.t()),
     ("fc2 dgrad 12608x3072x768", 3072 * 768, lambda i: K.linear_dgrad(x768[i], w_fc2, E, gelu_grad=x3072[(i + 1) % NCOPY]), lambda i: x768[i] @ w_fc2),
-    ("fc1 dgrad 12608x768x3072", 768 * 3072, lambda i: K.linear_dgrad(x3072[i], w_fc1, E), lambda i: x3072[i] @ w_fc1),
+    ("fc1 dgrad 12608x768x3072", 768 * 3072, lambda i: K.linear_dgrad(x3072[i], w_fc1, E, scratch=SCR), lambda i: x3072[i] @ w_fc1),
     ("proj dgrad 12608x768x768", 768 * 768, lambda i: K.linear_dgrad(x768[i], w_proj, E), lambda i: x768[i] @ w_proj),
-    ("qkv dgrad 12608x768x2304", 768 * 2304, lambda i: K.linear_dgrad(hm2304[i], w_qkv, E, dy_layout=L.LAYOUT_HEADMAJOR), lambda i: x2304[i] @ w_qkv),
+    ("qkv dgrad 12608x768x2304", 768 * 2304, lambda i: K.linear_dgrad(hm2304[i], w_qkv, E, dy_layout=L.LAYOUT_HEADMAJOR, scratch=SCR), lambda i: x2304[i] @ w_qkv),
     ("fc2 wgrad 768x3072x12608", 768 * 3072, lambda i: wgrad(x768[i], x3072[i], 768, 3072), lambda i: x768[i].t() @ x3072[i]),
     ("fc1 wgrad 3072x768x12608", 768 * 3072, lambda i: wgrad(x3072[i], x768[i], 3072, 768), lambda i: x3072[i].t() @ x768[i]),
     ("proj wgrad 768x768x12608", 768 * 768, lambda i: wgrad(x768[i], x768[(i + 1) % NCOPY], 768, 768), lambda i: x768[i].t() @ x768[(i + 1) % NCOPY]),
@@ -79,7 +83,7 @@ def timeit(fn):
 
 if os.environ.get("ONLY"):
     CASES = [c for c in CASES if os.environ["ONLY"] in c[0]]
-print("knobs:", os.environ.get("VITK_KNOBS", ""))
+print("knobs:", os.environ.get("VITK_KNOBS", ""), " split-tail scratch:", SCR is not None)
 print(f"{'shape':28s} {'ours (fused epilogue)':>24s} {'cuBLAS (plain GEMM)':>24s}")
 tot_o = tot_c = 0.0
 for name, nk, ours, cublas in CASES:
