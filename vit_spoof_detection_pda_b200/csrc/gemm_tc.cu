@@ -25,7 +25,10 @@
 // 12,608-deep reduction) split K and sum partial tiles with fp32 vector atomics: sliced split-K -- cluster c owns k-slice
 // c / tiles of tile c % tiles, so all clusters of a slice sweep the same k range in lock-step and drain one accumulator
 // each -- when tiles x slices fill >= 90 % of the clusters, contiguous stream-K ranges over the (tile, k-block) space
-// otherwise (tc_decompose; the plan is queryable on the host: vitk_gemm_plan).
+// otherwise (tc_decompose; the plan is queryable on the host: vitk_gemm_plan).  Non-accumulating GEMMs whose last wave would be
+// nearly empty (M = B*197: 150 tiles on 74 pairs) deal the k-blocks of the last tiles out to all clusters of the same launch;
+// partial accumulators meet in an fp32 scratch and the last cluster to arrive at a region's ticket applies the epilogue
+// (decomposition mode 3, tc_tail_plan; vitk_gemm_tail_plan).
 // Every launch carries the programmatic-dependent-launch attribute: barrier init, TMEM allocation and tensor-map
 // prefetch run before pdl_sync(), i.e. under the tail of the previous kernel.
 //
