@@ -33,7 +33,8 @@ class GuardArena:
 
     def check(self):
         """every byte that is not payload still holds the sentinel; returns the number of bytes checked"""
-        torch.cuda.synchronize()
+        if self.buf.is_cuda:
+            torch.cuda.synchronize()
         checked, prev = 0, 0
         for off, nbytes in self.spans + [(self.buf.numel(), 0)]:
             gap = self.buf[prev:off]

@@ -269,3 +269,31 @@ def test_gemm_split_tail_plan():
         assert _tail_plan(lib, M64, 768, 3072, 1)[1] == 0           # 58 CTA pairs: 150 tiles = 2.6 waves, last wave well filled
     finally:
         lib.vitk_set_sm_budget(prev)
+
+
+# ---------------------------------------------------------------------------------------------
+# the guard-band arena of the GPU suite (tests/kernels_api.py::GuardArena) must itself detect stray writes: exercised on CPU
+# ---------------------------------------------------------------------------------------------
+def test_guard_arena_detects_out_of_bounds_writes():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import kernels_api as K
+    arena = K.GuardArena(torch.device("cpu"), nbytes=1 << 20, guard=4096)
+    a = arena.alloc((100, 7), torch.float32, zero=True)
+    b = arena.alloc((33,), torch.bfloat16, zero=False)
+    a.fill_(1.0)
+    b.fill_(2.0)
+    if True:
+        assert arena.check() == (1 << 20) - a.numel() * 4 - b.numel() * 2      # every non-payload byte was looked at
+        off_a = arena.spans[0][0]
+        arena.buf[off_a + a.numel() * 4] = 0            # one byte past the end of `a`
+        with pytest.raises(AssertionError):
+            arena.check()
+        arena.buf[off_a + a.numel() * 4] = K.GuardArena.BYTE
+        arena.buf[arena.spans[1][0] - 1] = 7            # one byte in front of `b`
+        with pytest.raises(AssertionError):
+            arena.check()
+        arena.buf[arena.spans[1][0] - 1] = K.GuardArena.BYTE
+        arena.buf[-1] = 1                               # the unallocated remainder
+        with pytest.raises(AssertionError):
+            arena.check()
