@@ -1047,7 +1047,7 @@ static int make_operand_map(const void* base, const MatLayout& l, int rows, int 
 
 
 // Tuning overrides (vitk_debug_set): process-wide, for tests and A/B timing; every one of them yields valid results.
-//   1 whole-K tiles for accumulate GEMMs, 2 forced BLOCK_N, 3 LayerNorm backward CTA shape (8: 8-warp CTAs), 4 CTA group, 5 per-thread epilogue IO, 6 no programmatic
+//   1 whole-K tiles for accumulate GEMMs, 2 forced BLOCK_N, 4 CTA group, 5 per-thread epilogue IO, 6 no programmatic
 //   dependent launch, 9 split tail (1: off, n > 1: minimum reduction depth in k-blocks instead of 24), 13 stream-K instead of sliced split-K (> 1: fill threshold in percent).
 // Development build only (libvitk_dev.so): 0 swap LBO/SBO of MN-major operands, 7 timing-only bit mask (results INVALID),
 //   12 whole qkv bias gradient from the attention kernel.
@@ -1056,7 +1056,7 @@ static bool knob_allowed(int key) {
 #ifdef VITK_DEV
   return key >= 0 && key < 16;
 #else
-  return key == 1 || key == 2 || key == 3 || key == 4 || key == 5 || key == 6 || key == 9 || key == 13;
+  return key == 1 || key == 2 || key == 4 || key == 5 || key == 6 || key == 9 || key == 13;
 #endif
 }
 int tune_knob(int key) { return knob_allowed(key) ? g_tc_debug[key] : 0; }

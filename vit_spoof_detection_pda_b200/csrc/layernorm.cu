@@ -8,8 +8,6 @@
 
 namespace vitk {
 
-int tune_knob(int key);     // gemm_tc.cu: vitk_debug_set(key, v)
-
 constexpr int LN_COLS = VITK_DIM;        // 768
 constexpr int LN_VEC = LN_COLS / 128;    // 6 float4 per lane
 constexpr int LN_WARPS = 8;
@@ -143,18 +141,13 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __rest
 }
 
 // Persistent over rows.  dgamma/dbeta partials live in per-warp shared-memory accumulators (only the owning
-// warp touches its slice, so no synchronisation until the end) instead of 48 registers per lane (~9 KB of loads in flight per
-// warp).  Final cross-warp sum -> one fp32 atomicAdd per column per CTA into dgamma/dbeta.
-// CTA shape (template W = warps per CTA).  In the backward pass this kernel runs on the main stream while a weight-gradient
-// GEMM of the side stream holds one 202 KB CTA on (nearly) every SM.  With W = 8 (72 KB of accumulators) an LN CTA cannot share
-// an SM with a GEMM CTA: the device-side timeline shows it waiting ~40 us for the GEMM's CTAs to retire and then running
-// alone.  With W = 2 (18 KB, 64 threads x <= 128 registers) ONE LN CTA fits next to a resident GEMM CTA (207 + 19 KB of the
-// SM's 228 KB; 51 K + 8 K of its 64 K registers): the HBM-bound LayerNorm then runs UNDER the tensor-bound GEMM instead of
-// after it, and on a free SM eight such CTAs give the same 16 warps as before.
-template <int W> constexpr int ln_bwd_smem() { return W * 3 * LN_COLS * (int)sizeof(float); }   // dgamma, dbeta, colsum(dx) per warp
+// warp touches its slice, so no synchronisation until the end) instead of 48 registers per lane: the kernel
+// then fits 2 co-resident CTAs (16 warps, ~9 KB of loads in flight per warp) per SM in one persistent wave.
+// Final cross-warp sum -> one fp32 atomicAdd per column per CTA into dgamma/dbeta.
+constexpr int LN_BWD_SMEM = LN_WARPS * 3 * LN_COLS * (int)sizeof(float);  // 72 KB: dgamma, dbeta, colsum(dx)
 
-template <typename T, int W>
-__global__ void __launch_bounds__(W * 32, W == 8 ? 2 : 8)
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_stride,
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* dres, float* dx, bf16* __restrict__ dx16,  // dres may alias dx (in-place residual-grad update)
@@ -171,7 +164,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_s
     *reinterpret_cast<float4*>(acc_b + (i * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(acc_c + (i * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int row = blockIdx.x * W + warp; row < rows; row += gridDim.x * W) {
+  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
     const float* xr = x + (int64_t)row * x_stride;
     const T* dyr = dy + (int64_t)row * LN_COLS;
     const float mu = mean[row], rs = rstd[row];
@@ -219,12 +212,12 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, int64_t x_s
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 3 * LN_COLS; c += W * 32) {
+  for (int c = threadIdx.x; c < 3 * LN_COLS; c += LN_WARPS * 32) {
     float* dst = c < LN_COLS ? dgamma : (c < 2 * LN_COLS ? dbeta : dx_colsum);
     if (!dst) continue;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < W; ++w) s += ln_acc[(size_t)w * 3 * LN_COLS + c];
+    for (int w = 0; w < LN_WARPS; ++w) s += ln_acc[(size_t)w * 3 * LN_COLS + c];
     atomicAdd(dst + (c % LN_COLS), s);
   }
   trace_end(TK_LN_BWD);
@@ -266,28 +259,15 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int dy_dtype, const float* x, 
   VITK_CHECK_ARG(x_stride % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)dx % 16) == 0);
   if (rows == 0) return VITK_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  // CTA shape: see ln_bwd_kernel.  vitk_debug_set(3, 8) restores the 8-warp CTAs (A/B timing).
-  if (tune_knob(3) == 8) {
-    VITK_TRY(set_max_dyn_smem_once((const void*)ln_bwd_kernel<float, 8>, ln_bwd_smem<8>()));
-    VITK_TRY(set_max_dyn_smem_once((const void*)ln_bwd_kernel<bf16, 8>, ln_bwd_smem<8>()));
-    int grid = (rows + 7) / 8;
-    const int cap = sm_count() * 2;  // 2 CTAs per SM are co-resident (launch bounds): one persistent wave
-    if (grid > cap) grid = cap;
-    if (dy_dtype == VITK_F32)
-      VITK_LAUNCH((ln_bwd_kernel<float, 8>), grid, 256, ln_bwd_smem<8>(), st, (const float*)dy, x, x_stride, gamma, mean, rstd, dres, dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
-    else if (dy_dtype == VITK_BF16)
-      VITK_LAUNCH((ln_bwd_kernel<bf16, 8>), grid, 256, ln_bwd_smem<8>(), st, (const bf16*)dy, x, x_stride, gamma, mean, rstd, dres, dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
-    else
-      VITK_CHECK_ARG(!"bad dtype");
-    return VITK_OK;
-  }
-  int grid = (rows + 1) / 2;
-  const int cap = sm_count() * 8;    // one persistent wave: eight 2-warp CTAs per free SM, one next to a resident GEMM CTA
+  VITK_TRY(set_max_dyn_smem_once((const void*)ln_bwd_kernel<float>, LN_BWD_SMEM));
+  VITK_TRY(set_max_dyn_smem_once((const void*)ln_bwd_kernel<bf16>, LN_BWD_SMEM));
+  int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int cap = sm_count() * 2;  // 2 CTAs per SM are co-resident (launch bounds): one persistent wave
   if (grid > cap) grid = cap;
   if (dy_dtype == VITK_F32)
-    VITK_LAUNCH((ln_bwd_kernel<float, 2>), grid, 64, ln_bwd_smem<2>(), st, (const float*)dy, x, x_stride, gamma, mean, rstd, dres, dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
+    VITK_LAUNCH((ln_bwd_kernel<float>), grid, LN_WARPS * 32, LN_BWD_SMEM, st, (const float*)dy, x, x_stride, gamma, mean, rstd, dres, dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
   else if (dy_dtype == VITK_BF16)
-    VITK_LAUNCH((ln_bwd_kernel<bf16, 2>), grid, 64, ln_bwd_smem<2>(), st, (const bf16*)dy, x, x_stride, gamma, mean, rstd, dres, dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
+    VITK_LAUNCH((ln_bwd_kernel<bf16>), grid, LN_WARPS * 32, LN_BWD_SMEM, st, (const bf16*)dy, x, x_stride, gamma, mean, rstd, dres, dx, (bf16*)dx16, dgamma, dbeta, dx_colsum, rows);
   else
     VITK_CHECK_ARG(!"bad dtype");
   return VITK_OK;
